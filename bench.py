@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native NeRF-LOAM hot path (BASELINE.json metric):
+neural-SDF samples/s per mapping iteration on a synthetic 100k-ray KITTI-shape scan.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one full mapping iteration of bundle_adjust_frames' loop body on every ray of one scan per GPU:
+pose -> rays -> octree traversal -> inverse-CDF sampling -> embedding gather + trilinear -> 16-256-256-1 MLP
+-> SDF/free-space loss -> backward (decoder, embeddings, pose) -> Adam on all three.  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+CFG = dict(step_size=0.5 * 0.3, voxel_size=0.3, max_distance=40.0, truncation=0.3, max_depth=40.0, fs_weight=1.0, sdf_weight=10000.0)
+LR = (0.01, 0.005, 0.001)                     # kitti.yaml learning_rate_emb / _decorder / _pose
+BYTES_PER_SAMPLE_MAP = 1116                   # algorithmic HBM bytes / valid sample, MAP mode
+FLOPS_PER_SAMPLE_MAP_DEC = 419328             # MLP fwd + bwd-data + bwd-weight
+WORKLOAD = "synthetic 100k-ray KITTI-shape scan (64x1563 beams, 82.7k returns), single-scan 0.3 m map, " \
+           "mapping iteration on ALL rays, decoder+embeddings+pose updated, Adam included"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(gpu)],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_problem(nl, n_maps_scans, device):
+    """Replicated map from `n_maps_scans` scans (deterministic, identical on every rank)."""
+    syn = nl.synthetic
+    scans = [syn.make_scan(seed=777 + i) for i in range(n_maps_scans)]
+    mu = nl.mapping.MapUpdater(CFG["voxel_size"], init_std=0.01, seed=777, device=device)
+    for pts, cos, pose in scans:
+        mu.svo.insert(torch.from_numpy(syn.voxelize(pts, pose, CFG["voxel_size"])))
+    ms = mu.update_grid_features()
+    torch.manual_seed(777)
+    dec = nl.lidar.Decoder(depth=2, width=256, in_dim=16, skips=[], embedder="none", multires=0).to(device)
+    return scans, mu, ms, dec
+
+
+def host_rays(pts, cos):
+    P = torch.from_numpy(pts)
+    dirs = (P / (P.norm(dim=-1, keepdim=True) + 1e-8)).float().contiguous()
+    gt = (torch.norm(P, 2, -1) * torch.from_numpy(cos)).float().contiguous()
+    return dirs.pin_memory(), gt.pin_memory(), torch.from_numpy(cos).float().contiguous().pin_memory()
+
+
+def run_ours(args):
+    import nerfloam_b200 as nl
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    scans, mu, ms, dec = build_problem(nl, world, dev)
+    pts, cos, pose = scans[rank]
+    h_dirs, h_gt, h_cos = host_rays(pts, cos)
+    R = h_dirs.shape[0]
+    d_dirs, d_gt, d_cos = h_dirs.to(dev), h_gt.to(dev), h_cos.to(dev)
+    pose6 = nl.se3pose.OptimizablePose.from_matrix(torch.from_numpy(pose)).data.detach().reshape(1, 6).to(dev).contiguous()
+    eng = nl.engine.SDFEngine(R, R * 20, dev)
+    bufs = nl.engine.DecoderBuffers(dec, dev)
+    emb = ms.emb
+    state = {"opt": None}
+
+    def step(dirs, gt, cosv):
+        eng.rays_from_poses(pose6, dirs, None)
+        eng.forward_backward(ms, bufs, R, CFG, gt, cosv, dir_local=dirs, ray_frame=None, n_frames=1, rng_seed=12345,
+                             update_decoder=True, update_emb=True, update_pose=True, pose6=pose6, group=group)
+        if state["opt"] is None:
+            groups = [dict(param=emb, grad=eng.grad_emb, lr=LR[0])]
+            groups += [dict(param=p.data, grad=g, lr=LR[1]) for p, g in zip(bufs.params, bufs.grads)]
+            groups += [dict(param=pose6[0], grad=eng.pose_grad[0], lr=LR[2])]
+            state["opt"] = nl.engine.FusedAdam(groups)
+        state["opt"].step()
+
+    def sync_all():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing (value) ----------------
+    for _ in range(max(args.warmup, 3)):
+        step(d_dirs, d_gt, d_cos)
+    sync_all()
+    clocks = ClockSampler(local)
+    eng.events = {}
+    l0 = nl._capi.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    samples = 0
+    e0.record()
+    for _ in range(args.steps):
+        step(d_dirs, d_gt, d_cos)
+    e1.record()
+    sync_all()
+    ms_total = e0.elapsed_time(e1)
+    launches = nl._capi.LAUNCHES - l0
+    ev = eng.events
+    eng.events = None
+    st = eng.read_stats()
+    n_local = st.n_samples
+    t_mlp = float(np.mean([a.elapsed_time(b) for a, b in zip(ev["t_gather_fwd"], ev["t_mlp"])]))
+    t_gf = float(np.mean([a.elapsed_time(b) for a, b in zip(ev["t_samples"], ev["t_gather_fwd"])]))
+    t_gb = float(np.mean([a.elapsed_time(b) for a, b in zip(ev["t_mlp"], ev["t_gather_bwd"])]))
+    t_smp = float(np.mean([a.elapsed_time(b) for a, b in zip(ev["t0"], ev["t_samples"])]))
+
+    # ---------------- end-to-end through the public step with host buffers (e2e) ----------------
+    loss_host = torch.empty(nl.engine.STATS_BYTES, dtype=torch.uint8).pin_memory()
+    s_dirs, s_gt, s_cos = torch.empty_like(d_dirs), torch.empty_like(d_gt), torch.empty_like(d_cos)
+
+    def step_e2e():
+        s_dirs.copy_(h_dirs, non_blocking=True); s_gt.copy_(h_gt, non_blocking=True); s_cos.copy_(h_cos, non_blocking=True)
+        step(s_dirs, s_gt, s_cos)
+        loss_host.copy_(eng.stats, non_blocking=True)
+    for _ in range(3):
+        step_e2e()
+    sync_all()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    f1.record()
+    sync_all()
+    ms_e2e = f0.elapsed_time(f1)
+    clk = clocks.stop()
+    loss_val = nl._capi.RenderStats.from_buffer_copy(loss_host.numpy().tobytes()).loss
+
+    # ---------------- aggregate over ranks (max time, sum samples) ----------------
+    t = torch.tensor([ms_total, ms_e2e, float(n_local)], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ts = t.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        ms_total, ms_e2e, n_total = float(tm[0]), float(tm[1]), float(ts[2])
+    else:
+        n_total = float(n_local)
+    if rank != 0:
+        return
+    pk = peaks()
+    value = n_total * args.steps / (ms_total * 1e-3)
+    e2e = n_total * args.steps / (ms_e2e * 1e-3)
+    flops = n_local * FLOPS_PER_SAMPLE_MAP_DEC
+    ach_tf = flops / (t_mlp * 1e-3) / 1e12
+    gather_gbs = n_local * BYTES_PER_SAMPLE_MAP / ((t_gf + t_gb) * 1e-3) / 1e9
+    out = {
+        "metric": "neural-SDF samples/sec per mapping iter", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rays_per_gpu": R, "samples_per_gpu_step": n_local, "octree_nodes": ms.n_nodes,
+                   "embedding_rows": int(ms.emb.shape[0]), "decoder": "16-256-256-1 fp32", "parallelism": f"ray-sharded dp{world}, map replicated",
+                   "l2": "per-step working set (samples x ~2.2 KB activations+features) ~1.9 GB >> 126 MB L2; no flush needed",
+                   "sampler_noise": "in-kernel counter RNG", "loss": loss_val},
+        "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": int(R * 20 * world), "d2h_bytes_per_step": int(160 * world),
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "k_mlp<256,train,wgrad> + k_dw1 (fp32 CUDA-core FMA; tensor pipe not used yet)",
+                     "achieved": ach_tf, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach_tf / pk["bf16_sustained"],
+                     "traffic": None, "peak_source": pk["src"] + " bf16 dense (sustained); fp32 FMA peak of 148 SMs is ~72 TFLOP/s at 1.9 GHz",
+                     "ms_per_launch": t_mlp, "algorithmic_flops_per_sample": FLOPS_PER_SAMPLE_MAP_DEC},
+        "roofline_gather": {"bound": "hbm", "kernel": "k_gather_fwd + k_gather_bwd", "achieved": gather_gbs, "peak": pk["hbm"], "unit": "GB/s",
+                            "frac": gather_gbs / pk["hbm"], "ms_fwd": t_gf, "ms_bwd": t_gb, "algorithmic_bytes_per_sample": BYTES_PER_SAMPLE_MAP},
+        "stage_ms": {"traverse_sample": t_smp, "gather_fwd": t_gf, "mlp_fwd_bwd": t_mlp, "gather_bwd": t_gb},
+        "clocks": clk,
+    }
+    if world == 1:
+        out["cpu_baseline"] = cpu_baseline(n_rays=4096, iters=3)
+    print(json.dumps(out))
+
+
+def cpu_baseline(n_rays=4096, iters=3, threads=None):
+    """The oracle port of the reference path (oracle/: C traversal + sampler, torch fp32 chain, autograd,
+    torch.optim.Adam) timed on this box's host cores on a bounded sample of the same workload."""
+    from oracle import chain as OC
+    from oracle import kernels as OK
+    import importlib
+    syn = importlib.import_module("nerf-loam_b200.synthetic")
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    pts, cos, pose = syn.make_scan(seed=777)
+    o = OK.Octree(); o.init(256 * 256 * 4, 16, CFG["voxel_size"])
+    o.insert(syn.voxelize(pts, pose, CFG["voxel_size"]))
+    voxels, children, features = o.get_centres_and_children()
+    centres, structure, vertex = OK.map_arrays(voxels, children, features, CFG["voxel_size"])
+    flat = vertex.reshape(-1); used = flat[flat >= 0]
+    uniq, first = np.unique(used, return_index=True)
+    v2r = np.full(vertex.shape[0], -1, np.int64); v2r[uniq[np.argsort(first)]] = np.arange(len(uniq))
+    map_np = {"centres": centres, "structure": structure, "vertex_rows": np.where(vertex >= 0, v2r[np.clip(vertex, 0, None)], -1)}
+    g = torch.Generator().manual_seed(777)
+    emb = (torch.randn(len(uniq), 16, generator=g) * 0.01).to(torch.bfloat16).requires_grad_()
+    torch.manual_seed(777)
+    dec = OC.Decoder(depth=2, width=256, in_dim=16)
+    pose6 = torch.nn.Parameter(OC.pose_from_matrix(torch.from_numpy(pose)))
+    opt = torch.optim.Adam([{"params": [emb], "lr": LR[0]}, {"params": list(dec.parameters()), "lr": LR[1]}, {"params": [pose6], "lr": LR[2]}])
+    sel = np.random.default_rng(0).choice(pts.shape[0], n_rays, replace=False); sel.sort()
+    P = torch.from_numpy(pts[sel]); C_ = torch.from_numpy(cos[sel])
+    frame = dict(pose=pose6, dirs=P / (P.norm(dim=-1, keepdim=True) + 1e-8), points=P, cos=C_)
+    cfg = dict(CFG)
+    times, nsamp = [], 0
+    for it in range(iters + 1):
+        t0 = time.perf_counter()
+        loss, out = OC.mapping_iteration([frame], map_np, emb, dec, cfg, deterministic=True)
+        opt.zero_grad(); loss.backward(); opt.step()
+        dt = time.perf_counter() - t0
+        nsamp = int(out["valid_mask"].sum())
+        if it > 0:
+            times.append(dt)
+    return {"value": nsamp / float(np.median(times)), "unit": "samples/s", "cores": threads, "kind": "port",
+            "sample": f"{n_rays} rays of the same scan ({nsamp} samples) per iteration, median of {iters} after 1 warm-up; "
+                      "oracle port: C traversal/sampler + PyTorch fp32 CPU chain + autograd + torch.optim.Adam",
+            "ms_per_iter": float(np.median(times)) * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    n_rays = 8192
+    t0 = time.perf_counter()
+    cb = cpu_baseline(n_rays=n_rays, iters=max(1, args.steps), threads=os.cpu_count())
+    out = {"impl": "reference", "metric": "neural-SDF samples/sec per mapping iter", "value": cb["value"], "unit": "samples/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": 1, "ms_per_step": cb["ms_per_iter"], "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": WORKLOAD, "note": f"reference algorithm on host cores; each step = a bounded sample of {n_rays} rays"},
+           "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+           "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device for --impl ours (there is no CPU fallback)")
+        run_ours(a)

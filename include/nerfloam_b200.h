@@ -1,0 +1,229 @@
+/*
+ * nerfloam_b200.h -- C ABI of libnerfloam_b200.so: the B200-native (sm_100a) replacement for the
+ * per-iteration neural-SDF hot path of NeRF-LOAM.
+ *
+ * Conventions
+ *   - plain C: raw pointers, explicit sizes, no torch / C++ types.  `stream` is a cudaStream_t
+ *     passed as void* (NULL = legacy default stream).  Every device entry point is asynchronous and
+ *     stream-ordered, allocates nothing, never synchronises and NEVER calls exit() (the reference
+ *     does: third_party/sparse_voxels/include/cuda_utils.h:37-48).
+ *   - all pointers named d_* are device pointers; h_* are host pointers.
+ *   - return value: 0 = ok, <0 = error (nl_last_error() returns a thread-local message).
+ *   - all reference citations are relative to /root/reference.
+ */
+#ifndef NERFLOAM_B200_H
+#define NERFLOAM_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define NL_API __attribute__((visibility("default")))
+#else
+#define NL_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NL_OK 0
+#define NL_ERR_INVALID (-1)
+#define NL_ERR_CUDA (-2)
+#define NL_ERR_UNSUPPORTED (-3)
+
+#define NL_MAX_HITS 20     /* voxel_helpers.py:533 hard-codes n_max = 20 */
+#define NL_EMB_DIM 16      /* configs/*: decoder_specs.in_dim = 16 */
+#define NL_SAMPLE_G 200    /* voxel_helpers.py:274: sampler batches */
+#define NL_SAMPLE_CHUNK 800 /* voxel_helpers.py:304: 4*G rays per launch and batch */
+#define NL_MAX_DEPTH_FILL 80.0f /* voxel_helpers.py:24 MAX_DEPTH */
+
+NL_API const char *nl_last_error(void);
+NL_API int nl_version(void);
+/* sizeof(nl_render_stats), offsetof(nl_render_stats, n_samples), sizeof(nl_render_args), sizeof(nl_mlp_weights):
+ * lets a foreign-language binding verify its struct layout at load time */
+NL_API void nl_abi_sizes(int32_t out[4]);
+
+/* ============================================================================================
+ * 1. Host octree -- replaces torch.classes.svo.Octree
+ *    (third_party/sparse_octree/src/bindings.cpp:11-31, src/octree.cpp, include/octree.h).
+ *    Flat-array octree; node ids are creation-order ids, bit-identical to the reference's
+ *    Octant::index_ (octree.h:19).  One handle = one independent tree (the reference's node counter
+ *    is a process global, octree.h:62; here it is per tree).
+ * ============================================================================================ */
+typedef struct nl_octree nl_octree;
+
+NL_API nl_octree *nl_octree_create(int64_t grid_dim, int64_t feat_dim, double voxel_size); /* Octree::init   octree.cpp:34-49   */
+NL_API void nl_octree_destroy(nl_octree *t);
+NL_API int nl_octree_insert(nl_octree *t, const int32_t *h_vox, int64_t n);               /* Octree::insert octree.cpp:51-111  */
+NL_API double nl_octree_try_insert(nl_octree *t, const int32_t *h_vox, int64_t n);        /* try_insert     octree.cpp:113-149 */
+NL_API int64_t nl_octree_count_nodes(const nl_octree *t);                                  /* count_nodes    octree.cpp:344-364 */
+NL_API int64_t nl_octree_count_export_nodes(const nl_octree *t);                           /* rows of get_centres_and_children (octree.cpp:295-297) */
+NL_API int64_t nl_octree_count_leaf_nodes(const nl_octree *t);                             /* count_leaf_nodes octree.cpp:366-389 */
+NL_API int nl_octree_has_voxel(const nl_octree *t, const int32_t h_xyz[3]);                /* has_voxel      octree.cpp:173-206 */
+/* get_centres_and_children (octree.cpp:293-342): voxels f32[n,4], children f32[n,8], features i32[n,8],
+ * n = nl_octree_count_export_nodes(). */
+NL_API int nl_octree_export(const nl_octree *t, float *h_voxels, float *h_children, int32_t *h_features);
+/* The same export already in the layout the hot path consumes (src/mapping.py:320-326):
+ * centres f32[n,3] = (xyz + side/2) * voxel_size, structure i32[n,9] = 8 child ids + side, vertex i32[n,8]. */
+NL_API int nl_octree_export_map(const nl_octree *t, float *h_centres, int32_t *h_structure, int32_t *h_vertex);
+NL_API int64_t nl_octree_get_voxels(const nl_octree *t, float *h_out, int64_t cap_rows);       /* get_voxels      octree.cpp:228-252 : [n,4] preorder */
+NL_API int64_t nl_octree_get_leaf_voxels(const nl_octree *t, float *h_out, int64_t cap_rows);  /* get_leaf_voxels octree.cpp:212-226 : [n,3] */
+NL_API uint64_t nl_morton_encode(int x, int y, int z);                                         /* svo.encode      utils.h:106-109    */
+
+/* Vertex -> embedding-row table (src/mapping.py:294-317 Mapping.get_embeddings, de-duplicated: one row
+ * per distinct vertex id, numbered by first appearance in vertex.reshape(-1)).  vertex2row i32[n_nodes]
+ * (-1 = no row yet) is updated in place; returns the new number of rows (>= n_rows_before). */
+NL_API int64_t nl_assign_embedding_rows(const int32_t *h_vertex, int64_t n_nodes, int32_t *h_vertex2row, int64_t n_rows_before);
+
+/* ============================================================================================
+ * 2. Drop-ins for the two live `grid` kernels (third_party/sparse_voxels/src/binding.cpp:12-20)
+ * ============================================================================================ */
+/* grid.svo_intersect (intersect.cpp:83-112, intersect_gpu.cu:193-272).  ray_start/ray_dir f32[b,m,3],
+ * points f32[b,n,3], children i32[b,n,9]; outputs [b,m,n_max] (idx -1 / depths 0 where empty). */
+NL_API int nl_svo_intersect(int b, int n, int m, float voxelsize, int n_max, const float *d_ray_start, const float *d_ray_dir,
+                     const float *d_points, const int32_t *d_children, int32_t *d_idx, float *d_min_depth,
+                     float *d_max_depth, void *stream);
+/* grid.inverse_cdf_sampling (sample.cpp:56-95, sample_gpu.cu:133-239), including both index quirks. */
+NL_API int nl_inverse_cdf_sampling(int b, int num_rays, int max_hits, int max_steps, float fixed_step_size,
+                            const int32_t *d_pts_idx, const float *d_min_depth, const float *d_max_depth,
+                            const float *d_noise, const float *d_probs, const float *d_steps, int32_t *d_sampled_idx,
+                            float *d_sampled_depth, float *d_sampled_dists, void *stream);
+
+/* ============================================================================================
+ * 3. Fused renderer: rays -> compact sample list (no host sync, no padded [R,S] tensors)
+ *    replaces ray_intersect + ray_sample (voxel_helpers.py:530-598) and the mask/gather glue of
+ *    render_rays (render_helpers.py:207-257).
+ * ============================================================================================ */
+typedef struct {
+    int32_t n_hit_rays;    /* R_hit  = hits.sum()                        render_helpers.py:216   */
+    int32_t max_hits;      /* P      = max valid hits per ray            voxel_helpers.py:555    */
+    int32_t max_samples;   /* S_max  = max valid samples per ray         voxel_helpers.py:332    */
+    int32_t n_samples;     /* M      = sample_mask.sum()                 render_helpers.py:242   */
+    int32_t error;         /* bit0: sum(dists) > 10*MAX_DEPTH (ray_sample returns None, voxel_helpers.py:579)
+                              bit1: sample capacity exceeded, bit2: DFS stack overflow                  */
+    int32_t max_steps_ceil;/* ceil(steps).max(); the reference's noise width is this + P (voxel_helpers.py:294) */
+    int32_t _pad[2];
+    /* raw loss-mask counters over the padded [R_hit, S_max] matrix (criterion.py:67-88); additive across
+     * ray shards (multi-GPU: all-reduce SUM these, MAX max_samples, then call nl_loss_prepare) */
+    int64_t cnt_fs_valid, cnt_sdf_valid;     /* front_mask / sdf_mask set among valid samples            */
+    int64_t pad_fs_rays, pad_fs_nsamp;       /* rays whose padded cells (z = 80*cos) are front; their sum of nsamp */
+    int64_t pad_sdf_rays, pad_sdf_nsamp;     /* same for sdf_mask                                         */
+    double pad_sdf_d2, pad_sdf_d2_nsamp;     /* sum depth^2 (and depth^2*nsamp) over those rays           */
+    /* derived by nl_loss_prepare */
+    float n_fs, n_sdf;     /* count_nonzero(front_mask), count_nonzero(sdf_mask) */
+    float w_fs, w_sdf;     /* 1 - n_fs/(n_fs+n_sdf), 1 - n_sdf/(n_fs+n_sdf)      */
+    float g_fs, g_sdf;     /* weight * w / (R_hit*S_max): d loss / d(sum of squared errors) */
+    float pad_fs_sum, pad_sdf_sum; /* squared-error contribution of the padded (invalid) cells */
+    /* accumulated by nl_mlp_train, consumed by nl_loss_finalize */
+    double fs_sum, sdf_sum;
+    float loss, fs_loss, sdf_loss, _padf;
+} nl_render_stats;
+
+typedef struct {
+    /* sizes */
+    int32_t n_rays;          /* R */
+    int32_t n_nodes;         /* octree nodes n */
+    int32_t sample_capacity; /* rows available in the d_s_* arrays */
+    int32_t reference_compat;/* 1: reproduce the two sampler quirks exactly */
+    float voxel_size, step_size, max_distance;
+    float truncation, max_depth;      /* criterion.py: sdf_truncation, data_specs.max_depth */
+    float fs_weight, sdf_weight;      /* criterion.py:11-12 */
+    /* map (device) */
+    const float *d_centres;      /* f32[n,3]  voxel_center_xyz   */
+    const int32_t *d_structure;  /* i32[n,9]  voxel_structure    */
+    /* rays (device) */
+    const float *d_ray_o, *d_ray_d;   /* f32[R,3] */
+    const float *d_gt_depth;          /* f32[R] = ||p|| * cos  (criterion.py:30-32), may be NULL for eval */
+    const float *d_cos;               /* f32[R]  pointsCos, may be NULL (= 1) */
+    /* noise: NULL = constant 0.5 (deterministic=True, voxel_helpers.py:298-299); else f32[R_hit_padded, noise_stride] */
+    const float *d_noise;
+    int32_t noise_stride;
+    uint32_t rng_seed;                /* used when d_noise == NULL and rng_seed != 0: counter-based uniform noise */
+    /* workspace (device), sizes from nl_render_workspace_bytes */
+    void *d_workspace;
+    int64_t workspace_bytes;
+    /* outputs (device) */
+    nl_render_stats *d_stats;
+    int32_t *d_hit_rank;   /* i32[R]: rank among hit rays or -1           (ray_mask)               */
+    int32_t *d_s_ray;      /* i32[cap] ray index of each valid sample, row-major (ray, step) order */
+    int32_t *d_s_vox;      /* i32[cap] sampled_point_voxel_idx                                      */
+    float *d_s_depth;      /* f32[cap] sampled_point_depth                                          */
+    float *d_s_xyz;        /* f32[cap,3] ray_o + ray_d * depth (mul then add, unfused) render_helpers.py:9-10 */
+    uint8_t *d_s_flag;     /* u8[cap] bit0 front_mask, bit1 sdf_mask (criterion.py:67-82); 0 if d_gt_depth NULL */
+    int32_t *d_ray_nsamp;  /* i32[R] valid samples per ray (0 for missed rays) */
+    int32_t *d_ray_offset; /* i32[R] offset of the ray's first sample in the compact list */
+} nl_render_args;
+
+NL_API int64_t nl_render_workspace_bytes(int32_t n_rays);
+NL_API int nl_render_samples(const nl_render_args *args, void *stream);
+
+/* ============================================================================================
+ * 4. Embedding gather + trilinear interpolation (render_helpers.py:40-93) and its backward
+ * ============================================================================================ */
+/* feats[M,16] = sum_k w_k(xyz, centre[vox]) * float(emb[vox2row[vox,k]])   (emb: bf16 [V,16]) */
+NL_API int nl_gather_trilinear_fwd(int64_t M, const int32_t *d_M_dev, const float *d_xyz, const int32_t *d_vox,
+                            const float *d_centres, const int32_t *d_vox2row, const uint16_t *d_emb_bf16,
+                            float voxel_size, float *d_feats, void *stream);
+/* Backward: scatters d feats into the fp32 gradient table (atomics; each contribution rounded to bf16 first
+ * when round_bf16 != 0, which is where autograd rounds for the reference's bf16 table), and reduces
+ * dL/dxyz into per-frame pose accumulators acc[F,12] = (dL/dt[3], dL/dR[3,3]) via rays.
+ * Any of d_grad_emb / d_dxyz / d_pose_acc may be NULL. */
+NL_API int nl_gather_trilinear_bwd(int64_t M, const int32_t *d_M_dev, const float *d_xyz, const int32_t *d_vox,
+                            const float *d_centres, const int32_t *d_vox2row, const uint16_t *d_emb_bf16,
+                            float voxel_size, const float *d_dfeats, int round_bf16, float *d_grad_emb, float *d_dxyz,
+                            const int32_t *d_s_ray, const float *d_s_depth, const float *d_ray_dir_local,
+                            const int32_t *d_ray_frame, int n_frames, float *d_pose_acc, void *stream);
+
+/* ============================================================================================
+ * 5. SDF decoder MLP in_dim(16) -> W -> W -> 1 with ReLU (src/variations/lidar.py:109-131) + loss
+ *    (src/criterion.py:92-103) + backward.  Weights are nn.Linear layout: W0[W,16], W1[W,W], W2[1,W].
+ * ============================================================================================ */
+typedef struct {
+    int32_t width;                 /* W: 256 (all shipped configs) or any multiple of 32 up to 256 */
+    const float *W0, *b0, *W1, *b1, *W2, *b2;   /* device */
+    const float *W0t, *W1t;        /* device: transposes [16,W], [W,W] (nl_mlp_prepare writes them) */
+} nl_mlp_weights;
+
+typedef struct {
+    float *gW0, *gb0, *gW1, *gb1, *gW2, *gb2;   /* device fp32 gradient accumulators (same shapes) */
+} nl_mlp_grads;
+
+NL_API int nl_mlp_prepare(int32_t width, const float *d_W0, const float *d_W1, float *d_W0t, float *d_W1t, void *stream);
+/* forward only: sdf[M] */
+NL_API int nl_mlp_forward(int64_t M, const int32_t *d_M_dev, const float *d_feats, const nl_mlp_weights *w, float *d_sdf,
+                   void *stream);
+/* forward + loss + backward in one pass.  Per-sample loss terms come from d_s_flag / d_s_depth / rays and the
+ * constants in d_stats (nl_loss_prepare).  Writes sdf[M], dfeats[M,16]; accumulates the squared-error sums into
+ * d_stats; if grads != NULL also accumulates decoder gradients (d_act_h1 / d_act_dh2: [cap,W] scratch for the
+ * dW1 GEMM, required then).  If d_dsdf_ext != NULL the loss is skipped and d loss / d sdf is read from it
+ * (f32[M]; this is the backward of a plain Decoder.forward under autograd; d_s_* / d_stats may then be NULL). */
+NL_API int nl_mlp_train(int64_t M, const int32_t *d_M_dev, const float *d_feats, const nl_mlp_weights *w,
+                 const uint8_t *d_s_flag, const float *d_s_depth, const int32_t *d_s_ray, const float *d_cos,
+                 const float *d_gt_depth, nl_render_stats *d_stats, float truncation, float *d_sdf, float *d_dfeats,
+                 const nl_mlp_grads *grads, float *d_act_h1, float *d_act_dh2, const float *d_dsdf_ext, void *stream);
+/* loss constants from the sample statistics (criterion.py:84-88, 97-100); call after nl_render_samples */
+NL_API int nl_loss_prepare(nl_render_stats *d_stats, float fs_weight, float sdf_weight, void *stream);
+NL_API int nl_loss_finalize(nl_render_stats *d_stats, float fs_weight, float sdf_weight, void *stream);
+
+/* ============================================================================================
+ * 6. SE(3) pose (src/se3pose.py): 6-vector [t, w] -> R(w) (11-term Taylor A,B), ray generation and
+ *    the pose Jacobian (autograd through rotation()/translation() in the reference).
+ * ============================================================================================ */
+NL_API int nl_pose_matrices(int n_frames, const float *d_pose6, float *d_Rt12, void *stream);  /* [F,12] = R row-major, t */
+NL_API int nl_rays_from_poses(int64_t R, const float *d_dir_local, const int32_t *d_ray_frame, const float *d_Rt12,
+                       float *d_ray_o, float *d_ray_d, void *stream);                    /* render_helpers.py:374-376 */
+NL_API int nl_pose_grad(int n_frames, const float *d_pose6, const float *d_pose_acc, float *d_grad6, void *stream);
+
+/* ============================================================================================
+ * 7. Optimiser (torch.optim.Adam semantics, render_helpers.py:353/448): fp32 tensors and the bf16
+ *    embedding table (every intermediate rounded to bf16 where torch's per-op kernels round).
+ * ============================================================================================ */
+NL_API int nl_adam_f32(int64_t n, float *d_param, const float *d_grad, float *d_m, float *d_v, double lr, double beta1,
+                double beta2, double eps, int step, void *stream);
+NL_API int nl_adam_bf16(int64_t n, uint16_t *d_param, const float *d_grad_f32, uint16_t *d_m, uint16_t *d_v, double lr,
+                 double beta1, double beta2, double eps, int step, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NERFLOAM_B200_H */

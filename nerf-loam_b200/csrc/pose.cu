@@ -1,0 +1,123 @@
+// SE(3) pose parameterisation of src/se3pose.py (OptimizablePose): data = [t(3), w(3)],
+// R = I + A(theta) [w]x + B(theta) [w]x^2 with the 11-term Taylor polynomials of se3pose.py:63-82,
+// ray generation (render_helpers.py:372-376 / 467-471) and the pose Jacobian that the reference gets
+// from autograd through rotation() / translation().
+#include "nl_cuda.cuh"
+
+namespace {
+
+// se3pose.py:63-72: sum_{i<=10} (-1)^i x^(2i) / (2i+1)!   (denominators accumulated like the Python loop)
+__device__ void taylor_AB(float x, float &A, float &B, float &dA, float &dB) {
+    // values in fp32 term by term (the reference evaluates in fp32 tensors), derivatives in double
+    float a = 0.f, b = 0.f;
+    double da = 0.0, db = 0.0;
+    double denA = 1.0, denB = 1.0;
+    const double xd = (double)x;
+    for (int i = 0; i <= 10; ++i) {
+        if (i > 0) denA *= (double)((2 * i) * (2 * i + 1));
+        denB *= (double)((2 * i + 1) * (2 * i + 2));
+        const float sgn = (i & 1) ? -1.f : 1.f;
+        const float xp = powf(x, (float)(2 * i));  // x ** (2*i); pow(0,0) = 1
+        a = a + sgn * xp / (float)denA;
+        b = b + sgn * xp / (float)denB;
+        if (i > 0) {
+            const double dxp = (double)(2 * i) * pow(xd, (double)(2 * i - 1));
+            da += (double)sgn * dxp / denA;
+            db += (double)sgn * dxp / denB;
+        }
+    }
+    A = a; B = b; dA = (float)da; dB = (float)db;
+}
+
+__device__ void rotation_from_w(const float w[3], float R[9]) {
+    const float theta = sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    float A, B, dA, dB;
+    taylor_AB(theta, A, B, dA, dB);
+    const float W[9] = {0.f, -w[2], w[1], w[2], 0.f, -w[0], -w[1], w[0], 0.f};  // se3pose.py:53-61
+    float W2[9];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) W2[r * 3 + c] = W[r * 3] * W[c] + W[r * 3 + 1] * W[3 + c] + W[r * 3 + 2] * W[6 + c];
+    for (int i = 0; i < 9; ++i) R[i] = ((i % 4 == 0) ? 1.f : 0.f) + A * W[i] + B * W2[i];
+}
+
+__global__ void k_pose_matrices(int F, const float *__restrict__ pose6, float *__restrict__ Rt12) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    float R[9];
+    rotation_from_w(pose6 + f * 6 + 3, R);
+    for (int i = 0; i < 9; ++i) Rt12[f * 12 + i] = R[i];
+    for (int i = 0; i < 3; ++i) Rt12[f * 12 + 9 + i] = pose6[f * 6 + i];
+}
+
+// rays_d = dirs @ R^T, rays_o = t (render_helpers.py:374-376)
+__global__ void k_rays_from_poses(long long n, const float *__restrict__ dir_local, const int32_t *__restrict__ ray_frame,
+                                  const float *__restrict__ Rt12, float *__restrict__ ray_o, float *__restrict__ ray_d) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const float *P = Rt12 + (size_t)(ray_frame ? ray_frame[r] : 0) * 12;
+    const float x = dir_local[r * 3], y = dir_local[r * 3 + 1], z = dir_local[r * 3 + 2];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        ray_d[r * 3 + a] = fmaf(z, P[a * 3 + 2], fmaf(y, P[a * 3 + 1], x * P[a * 3]));
+        ray_o[r * 3 + a] = P[9 + a];
+    }
+}
+
+// grad6 = [dL/dt, dL/dw] from acc = (dL/dt[3], dL/dR[3][3]).
+// dR/dw_i = A' (w_i/theta) W + A E_i + B' (w_i/theta) W^2 + B (E_i W + W E_i), theta' = w_i/theta (0 at theta = 0,
+// matching torch's norm backward).
+__global__ void k_pose_grad(int F, const float *__restrict__ pose6, const float *__restrict__ acc, float *__restrict__ grad6) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const float *w = pose6 + f * 6 + 3;
+    const float *G = acc + f * 12 + 3;
+    const float theta = sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    float A, B, dA, dB;
+    taylor_AB(theta, A, B, dA, dB);
+    const float W[9] = {0.f, -w[2], w[1], w[2], 0.f, -w[0], -w[1], w[0], 0.f};
+    float W2[9];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) W2[r * 3 + c] = W[r * 3] * W[c] + W[r * 3 + 1] * W[3 + c] + W[r * 3 + 2] * W[6 + c];
+    for (int i = 0; i < 3; ++i) {
+        float E[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (i == 0) { E[5] = -1.f; E[7] = 1.f; }
+        if (i == 1) { E[2] = 1.f; E[6] = -1.f; }
+        if (i == 2) { E[1] = -1.f; E[3] = 1.f; }
+        const float dth = theta > 0.f ? w[i] / theta : 0.f;
+        float g = 0.f;
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) {
+                const float EW = E[r * 3] * W[c] + E[r * 3 + 1] * W[3 + c] + E[r * 3 + 2] * W[6 + c];
+                const float WE = W[r * 3] * E[c] + W[r * 3 + 1] * E[3 + c] + W[r * 3 + 2] * E[6 + c];
+                const float dR = dA * dth * W[r * 3 + c] + A * E[r * 3 + c] + dB * dth * W2[r * 3 + c] + B * (EW + WE);
+                g += G[r * 3 + c] * dR;
+            }
+        grad6[f * 6 + 3 + i] = g;
+        grad6[f * 6 + i] = acc[f * 12 + i];
+    }
+}
+
+}  // namespace
+
+extern "C" int nl_pose_matrices(int F, const float *pose6, float *Rt12, void *stream) {
+    if (F <= 0 || !pose6 || !Rt12) return nl_set_error("nl_pose_matrices: bad arguments");
+    k_pose_matrices<<<nl_div_up(F, 64), 64, 0, (cudaStream_t)stream>>>(F, pose6, Rt12);
+    NL_CHECK_LAUNCH("nl_pose_matrices");
+    return NL_OK;
+}
+
+extern "C" int nl_rays_from_poses(int64_t R, const float *dir_local, const int32_t *ray_frame, const float *Rt12,
+                                  float *ray_o, float *ray_d, void *stream) {
+    if (R < 0 || !dir_local || !Rt12 || !ray_o || !ray_d) return nl_set_error("nl_rays_from_poses: bad arguments");
+    if (R == 0) return NL_OK;
+    k_rays_from_poses<<<nl_div_up(R, 256), 256, 0, (cudaStream_t)stream>>>(R, dir_local, ray_frame, Rt12, ray_o, ray_d);
+    NL_CHECK_LAUNCH("nl_rays_from_poses");
+    return NL_OK;
+}
+
+extern "C" int nl_pose_grad(int F, const float *pose6, const float *acc, float *grad6, void *stream) {
+    if (F <= 0 || !pose6 || !acc || !grad6) return nl_set_error("nl_pose_grad: bad arguments");
+    k_pose_grad<<<nl_div_up(F, 64), 64, 0, (cudaStream_t)stream>>>(F, pose6, acc, grad6);
+    NL_CHECK_LAUNCH("nl_pose_grad");
+    return NL_OK;
+}

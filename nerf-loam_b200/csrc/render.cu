@@ -1,0 +1,387 @@
+// Fused renderer front end: rays -> sorted/clipped voxel hits -> inverse-CDF samples -> compact
+// sample list + loss-mask statistics, with no host synchronisation and no padded [R, S_max] tensors.
+//
+// Replaces, for the hot path (SURVEY.md section 8 a-2 .. a-5):
+//   src/variations/voxel_helpers.py:92-137, 530-567   svo_ray_intersect wrapper + ray_intersect
+//   src/variations/voxel_helpers.py:262-344, 570-598  InverseCDFRaySampling wrapper + ray_sample
+//   src/variations/render_helpers.py:207-257          hit/sample masking and `ray()` of render_rays
+//   src/criterion.py:67-88                            get_masks (the masks depend on depths only)
+//
+// Kernel chain (all on one stream):
+//   k_traverse_sort : 1 thread/ray  DFS + stable sort by min_depth + distance clipping  -> hit planes [20][R]
+//   k_scan<HITS>    : 1 block       exclusive scan of hit flags -> rank of every hit ray, R_hit
+//   k_sample<false> : 1 thread/hit ray  sampler dry run -> samples per ray, S_max, loss-mask counters
+//   k_scan<SAMPLES> : 1 block       exclusive scan of samples per ray -> offsets, M
+//   k_sample<true>  : 1 thread/hit ray  sampler again, writes the compact sample list
+// The reference keeps every intermediate as a padded dense tensor and syncs the host 6 times to size them.
+#include "traverse.cuh"
+
+namespace {
+
+struct Workspace {
+    int32_t *h_idx;   // [20][R]
+    float *h_min;     // [20][R]
+    float *h_max;     // [20][R]
+    int32_t *nvalid;  // [R]
+    int32_t *hitray;  // [R] ray index of the q-th hit ray
+};
+
+__host__ __device__ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+inline Workspace carve(void *base, int R) {
+    char *p = (char *)base;
+    Workspace w;
+    w.h_idx = (int32_t *)p; p += align256(sizeof(int32_t) * NL_MAX_HITS * (size_t)R);
+    w.h_min = (float *)p; p += align256(sizeof(float) * NL_MAX_HITS * (size_t)R);
+    w.h_max = (float *)p; p += align256(sizeof(float) * NL_MAX_HITS * (size_t)R);
+    w.nvalid = (int32_t *)p; p += align256(sizeof(int32_t) * (size_t)R);
+    w.hitray = (int32_t *)p; p += align256(sizeof(int32_t) * (size_t)R);
+    return w;
+}
+
+__device__ __forceinline__ int warp_max(int v) { return __reduce_max_sync(0xffffffffu, v); }
+
+// ------------------------------------------------------------------------------------------------
+// k_traverse_sort: svo_intersect + ray_intersect (voxel_helpers.py:530-567) for one ray per thread.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_traverse_sort(int R, float voxel_size, float max_distance,
+                                                        const float *__restrict__ centres,
+                                                        const int32_t *__restrict__ structure,
+                                                        const float *__restrict__ ray_o, const float *__restrict__ ray_d,
+                                                        Workspace ws, int32_t *__restrict__ ray_nsamp, nl_render_stats *stats) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    int nv = 0;
+    if (r < R) {
+        int32_t idx[NL_MAX_HITS];
+        float mn[NL_MAX_HITS], mx[NL_MAX_HITS];
+        const NlRay ray = nl_make_ray(ray_o[r * 3], ray_o[r * 3 + 1], ray_o[r * 3 + 2], ray_d[r * 3], ray_d[r * 3 + 1], ray_d[r * 3 + 2]);
+        int cnt = 0;
+        const int rc = nl_traverse(ray, centres, structure, voxel_size * 0.5f, NL_MAX_HITS, [&](int k, float lo, float hi) {
+            // stable insertion by min_depth (ties keep DFS emission order; torch.sort at voxel_helpers.py:546
+            // leaves the order of equal keys unspecified)
+            int p = cnt;
+            while (p > 0 && mn[p - 1] > lo) { idx[p] = idx[p - 1]; mn[p] = mn[p - 1]; mx[p] = mx[p - 1]; --p; }
+            idx[p] = k; mn[p] = lo; mx[p] = hi;
+            ++cnt;
+        });
+        if (rc < 0) atomicOr(&stats->error, 4);
+        const float two_md = 2.0f * max_distance;
+#pragma unroll
+        for (int c = 0; c < NL_MAX_HITS; ++c) {
+            int32_t i = -1;
+            float a = max_distance, b = max_distance;
+            if (c < cnt && !(mx[c] > two_md) && !(mn[c] > max_distance)) { i = idx[c]; a = mn[c]; b = mx[c]; ++nv; }
+            ws.h_idx[(size_t)c * R + r] = i;
+            ws.h_min[(size_t)c * R + r] = a;
+            ws.h_max[(size_t)c * R + r] = b;
+        }
+        ws.nvalid[r] = nv;
+        ray_nsamp[r] = 0;
+    }
+    const int wm = warp_max(nv);
+    if ((threadIdx.x & 31) == 0 && wm > 0) atomicMax(&stats->max_hits, wm);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_scan: single-block exclusive scan over n <= 2^31 ints (n is ~1e5..1e6; ~10 us).
+//   HITS:    in = nvalid (flag = nvalid > 0) -> hit_rank[r] (or -1), hitray[rank] = r, total -> n_hit_rays
+//   SAMPLES: in = ray_nsamp                  -> ray_offset[r],                         total -> n_samples
+// ------------------------------------------------------------------------------------------------
+enum { SCAN_HITS = 0, SCAN_SAMPLES = 1 };
+
+template <int MODE>
+__global__ void __launch_bounds__(1024) k_scan(int n, const int32_t *__restrict__ in, int32_t *__restrict__ out,
+                                                int32_t *__restrict__ hitray, nl_render_stats *stats, int sample_capacity) {
+    __shared__ int part[1024];
+    const int t = threadIdx.x;
+    const int per = (n + 1023) / 1024;
+    const int lo = min(n, t * per), hi = min(n, lo + per);
+    int s = 0;
+    for (int i = lo; i < hi; ++i) s += (MODE == SCAN_HITS) ? (in[i] > 0) : in[i];
+    part[t] = s;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {  // Hillis-Steele inclusive scan
+        int v = (t >= off) ? part[t - off] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    int run = part[t] - s;
+    for (int i = lo; i < hi; ++i) {
+        if (MODE == SCAN_HITS) {
+            const bool h = in[i] > 0;
+            out[i] = h ? run : -1;
+            if (h) { hitray[run] = i; ++run; }
+        } else {
+            out[i] = run;
+            run += in[i];
+        }
+    }
+    if (t == 1023) {
+        if (MODE == SCAN_HITS) {
+            stats->n_hit_rays = part[1023];
+        } else {
+            stats->n_samples = part[1023];
+            if (part[1023] > sample_capacity) atomicOr(&stats->error, 2);
+        }
+    }
+}
+
+// counter-based uniform noise in (0,1) for the stochastic sampler when no noise tensor is passed in
+__device__ __forceinline__ float hash_uniform(uint32_t seed, uint32_t ray, uint32_t step) {
+    uint32_t x = seed ^ (ray * 0x9E3779B1u) ^ (step * 0x85EBCA77u);
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    const float u = (float)(x >> 8) * (1.0f / 16777216.0f);
+    return fminf(fmaxf(u, 0.001f), 0.999f);  // voxel_helpers.py:301 clamp
+}
+
+struct SampleParams {
+    int R, sample_capacity, compat;
+    float step_size, truncation, max_depth;
+    const float *ray_o, *ray_d, *gt_depth, *cosv, *noise;
+    int noise_stride;
+    uint32_t rng_seed;
+    int32_t *s_ray, *s_vox;
+    float *s_depth, *s_xyz;
+    uint8_t *s_flag;
+    int32_t *ray_nsamp;
+    const int32_t *ray_offset;
+};
+
+// criterion.py:67-82 for one cell: bit0 front_mask, bit1 sdf_mask
+__device__ __forceinline__ uint32_t loss_flags(float z, float d, float trunc, float max_depth) {
+    const bool front = z < __fsub_rn(d, trunc);
+    const bool back = z > __fadd_rn(d, trunc);
+    const bool dm = (d > 0.0f) && (d < max_depth);
+    return (front ? 1u : 0u) | ((!front && !back && dm) ? 2u : 0u);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_sample: ray_sample + InverseCDFRaySampling.forward + inverse_cdf_sampling_kernel for the q-th hit ray.
+// The [200, K', P] padding / 800-ray chunking of the reference wrapper only matters through the two
+// index quirks of the kernel tail; they are reproduced from (q, R_hit, P) directly.
+// ------------------------------------------------------------------------------------------------
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_sample(SampleParams p, Workspace ws, nl_render_stats *stats) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int R_hit = stats->n_hit_rays;
+    const int R = p.R;
+    long long c_fs = 0, c_sdf = 0;
+    int nsamp = 0, steps_ceil = 0;
+    if (q < R_hit) {
+        const int r = ws.hitray[q];
+        const int P = stats->max_hits;
+        int32_t bidx[NL_MAX_HITS];
+        float bmin[NL_MAX_HITS], bmax[NL_MAX_HITS], prob[NL_MAX_HITS];
+        float tot = 0.f;
+#pragma unroll
+        for (int c = 0; c < NL_MAX_HITS; ++c) {
+            if (c < P) {
+                bidx[c] = ws.h_idx[(size_t)c * R + r];
+                bmin[c] = ws.h_min[(size_t)c * R + r];
+                bmax[c] = ws.h_max[(size_t)c * R + r];
+                prob[c] = (bidx[c] == -1) ? 0.f : __fsub_rn(bmax[c], bmin[c]);  // voxel_helpers.py:572-575
+                tot = __fadd_rn(tot, prob[c]);                                   // left-to-right fp32 sum
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < NL_MAX_HITS; ++c)
+            if (c < P) prob[c] = __fdiv_rn(prob[c], tot);                        // :576
+        const float steps = __fdiv_rn(tot, p.step_size);                         // :577
+        if (!FILL) {
+            if (tot > 10.0f * NL_MAX_DEPTH_FILL) atomicOr(&stats->error, 1);      // :579
+            steps_ceil = (int)ceilf(steps);
+        }
+        // position of this ray in the reference's [200, K', P] layout and 800-wide launches (voxel_helpers.py:274-316)
+        const int Kp = (R_hit + NL_SAMPLE_G - 1) / NL_SAMPLE_G;
+        const int b = q / Kp, j0 = q - b * Kp;
+        const int ch = j0 / NL_SAMPLE_CHUNK, j = j0 - ch * NL_SAMPLE_CHUNK;
+        const int num_rays = min(NL_SAMPLE_CHUNK, Kp - ch * NL_SAMPLE_CHUNK);
+        const int r_lead = ws.hitray[b * Kp + ch * NL_SAMPLE_CHUNK];            // ray 0 of this (batch, chunk)
+        const int H = j * P;
+
+        const float cosr = p.cosv ? p.cosv[r] : 1.0f;
+        const float gd = p.gt_depth ? p.gt_depth[r] : 0.0f;
+        const bool with_loss = p.gt_depth != nullptr;
+        const float ox = p.ray_o[r * 3], oy = p.ray_o[r * 3 + 1], oz = p.ray_o[r * 3 + 2];
+        const float dx = p.ray_d[r * 3], dy = p.ray_d[r * 3 + 1], dz = p.ray_d[r * 3 + 2];
+        const int base = FILL ? p.ray_offset[r] : 0;
+
+        auto emit = [&](int vox, float depth) {
+            uint32_t fl = 0;
+            if (with_loss) fl = loss_flags(__fmul_rn(depth, cosr), gd, p.truncation, p.max_depth);
+            if (FILL) {
+                const int m = base + nsamp;
+                if (m < p.sample_capacity) {
+                    p.s_ray[m] = r;
+                    p.s_vox[m] = vox;
+                    p.s_depth[m] = depth;
+                    p.s_xyz[(size_t)m * 3 + 0] = __fadd_rn(ox, __fmul_rn(dx, depth));  // ray(): mul then add (render_helpers.py:9-10)
+                    p.s_xyz[(size_t)m * 3 + 1] = __fadd_rn(oy, __fmul_rn(dy, depth));
+                    p.s_xyz[(size_t)m * 3 + 2] = __fadd_rn(oz, __fmul_rn(dz, depth));
+                    p.s_flag[m] = (uint8_t)fl;
+                }
+            } else {
+                c_fs += (fl & 1u);
+                c_sdf += (fl >> 1) & 1u;
+            }
+            ++nsamp;
+        };
+
+        // ---- sample_gpu.cu:165-238 ----
+        int curr_bin = 0;
+        float curr_min_depth = bmin[0], curr_max_depth = bmax[0];
+        float curr_min_cdf = 0.f, curr_max_cdf = prob[0];
+        const float inv_steps = __frcp_rn(steps);
+        float z_low = curr_min_depth;
+        const int total_steps = (int)ceilf(steps);
+        bool done = false;
+        for (int curr_step = 0; curr_step < total_steps; ++curr_step) {
+            float nz = 0.5f;
+            if (p.noise) nz = p.noise[(size_t)q * p.noise_stride + curr_step];
+            else if (p.rng_seed) nz = hash_uniform(p.rng_seed, (uint32_t)r, (uint32_t)curr_step);
+            const float curr_cdf = __fmul_rn(__fadd_rn((float)curr_step, nz), inv_steps);
+            while (curr_cdf > curr_max_cdf) {
+                emit(bidx[curr_bin], __fmul_rn(__fadd_rn(curr_max_depth, z_low), 0.5f));
+                ++curr_bin;
+                if (curr_bin >= P || bidx[curr_bin] == -1) { done = true; break; }
+                curr_min_depth = bmin[curr_bin];
+                curr_max_depth = bmax[curr_bin];
+                curr_min_cdf = curr_max_cdf;
+                curr_max_cdf = __fadd_rn(curr_max_cdf, prob[curr_bin]);
+                z_low = curr_min_depth;
+            }
+            if (done) break;
+            const float u = __fdiv_rn(__fsub_rn(curr_cdf, curr_min_cdf), __fsub_rn(curr_max_cdf, curr_min_cdf));
+            const float z = __fmaf_rn(u, __fsub_rn(curr_max_depth, curr_min_depth), curr_min_depth);
+            emit(bidx[curr_bin], __fmul_rn(__fadd_rn(z, z_low), 0.5f));
+            z_low = z;
+        }
+        // tail (sample_gpu.cu:224-238).  compat: `num_rays > j*P + curr_bin` gate and the leader ray's pts_idx
+        // in the continuation test; otherwise the evidently intended per-ray versions.
+        while ((z_low < curr_max_depth) && !done && (!p.compat || num_rays > (H + curr_bin))) {
+            emit(bidx[curr_bin], __fmul_rn(__fadd_rn(curr_max_depth, z_low), 0.5f));
+            ++curr_bin;
+            if (curr_bin >= P) break;
+            const int probe = p.compat ? ws.h_idx[(size_t)curr_bin * R + r_lead] : bidx[curr_bin];
+            if (probe == -1) break;
+            curr_min_depth = bmin[curr_bin];
+            curr_max_depth = bmax[curr_bin];
+            z_low = curr_min_depth;
+        }
+
+        if (!FILL) {
+            p.ray_nsamp[r] = nsamp;
+            if (with_loss) {  // padded cells of this row: z_vals = MAX_DEPTH (voxel_helpers.py:590), sdf = 1, valid = 0
+                const uint32_t fl = loss_flags(__fmul_rn(NL_MAX_DEPTH_FILL, cosr), gd, p.truncation, p.max_depth);
+                if (fl & 1u) {
+                    atomicAdd((unsigned long long *)&stats->pad_fs_rays, 1ULL);
+                    atomicAdd((unsigned long long *)&stats->pad_fs_nsamp, (unsigned long long)nsamp);
+                }
+                if (fl & 2u) {
+                    atomicAdd((unsigned long long *)&stats->pad_sdf_rays, 1ULL);
+                    atomicAdd((unsigned long long *)&stats->pad_sdf_nsamp, (unsigned long long)nsamp);
+                    atomicAdd(&stats->pad_sdf_d2, (double)gd * (double)gd);
+                    atomicAdd(&stats->pad_sdf_d2_nsamp, (double)gd * (double)gd * (double)nsamp);
+                }
+            }
+        }
+    }
+    if (!FILL) {
+        const int wm = warp_max(nsamp);
+        const int wsc = warp_max(steps_ceil);
+        for (int off = 16; off > 0; off >>= 1) {
+            c_fs += __shfl_down_sync(0xffffffffu, c_fs, off);
+            c_sdf += __shfl_down_sync(0xffffffffu, c_sdf, off);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (wm > 0) atomicMax(&stats->max_samples, wm);
+            if (wsc > 0) atomicMax(&stats->max_steps_ceil, wsc);
+            if (c_fs) atomicAdd((unsigned long long *)&stats->cnt_fs_valid, (unsigned long long)c_fs);
+            if (c_sdf) atomicAdd((unsigned long long *)&stats->cnt_sdf_valid, (unsigned long long)c_sdf);
+        }
+    }
+}
+
+// criterion.py:84-88 and the mean() denominators of :97-100
+__global__ void k_loss_prepare(nl_render_stats *s, float fs_weight, float sdf_weight) {
+    const long long S = s->max_samples;
+    const long long n_fs = s->cnt_fs_valid + s->pad_fs_rays * S - s->pad_fs_nsamp;
+    const long long n_sdf = s->cnt_sdf_valid + s->pad_sdf_rays * S - s->pad_sdf_nsamp;
+    const float nfs = (float)n_fs, nsdf = (float)n_sdf;
+    const float num = __fadd_rn(nsdf, nfs);
+    s->n_fs = nfs;
+    s->n_sdf = nsdf;
+    s->w_fs = __fsub_rn(1.0f, __fdiv_rn(nfs, num));
+    s->w_sdf = __fsub_rn(1.0f, __fdiv_rn(nsdf, num));
+    const float N = (float)((long long)s->n_hit_rays * S);
+    const bool ok = (N > 0.f) && (num > 0.f);   // no hit rays: nothing to optimise, keep the constants finite
+    s->g_fs = ok ? fs_weight * s->w_fs / N : 0.f;
+    s->g_sdf = ok ? sdf_weight * s->w_sdf / N : 0.f;
+    s->pad_fs_sum = (float)(s->pad_fs_rays * S - s->pad_fs_nsamp);           // each padded front cell: (0 - 1)^2
+    s->pad_sdf_sum = (float)(s->pad_sdf_d2 * (double)S - s->pad_sdf_d2_nsamp); // each padded sdf cell: (0 - depth)^2
+    s->fs_sum = 0.0;
+    s->sdf_sum = 0.0;
+    s->loss = s->fs_loss = s->sdf_loss = 0.f;
+}
+
+__global__ void k_loss_finalize(nl_render_stats *s, float fs_weight, float sdf_weight) {
+    const double N = (double)((long long)s->n_hit_rays * (long long)s->max_samples);
+    s->fs_loss = (float)((s->fs_sum + (double)s->pad_fs_sum) / N) * s->w_fs;
+    s->sdf_loss = (float)((s->sdf_sum + (double)s->pad_sdf_sum) / N) * s->w_sdf;
+    s->loss = fs_weight * s->fs_loss + sdf_weight * s->sdf_loss;
+}
+
+}  // namespace
+
+extern "C" int64_t nl_render_workspace_bytes(int32_t n_rays) {
+    if (n_rays < 0) return -1;
+    const size_t R = (size_t)(n_rays > 0 ? n_rays : 1);
+    return (int64_t)(3 * align256(4 * NL_MAX_HITS * R) + 2 * align256(4 * R) + 256);
+}
+
+extern "C" int nl_render_samples(const nl_render_args *a, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!a) return nl_set_error("nl_render_samples: null args");
+    if (a->n_rays <= 0 || a->n_nodes <= 0) return nl_set_error("nl_render_samples: n_rays and n_nodes must be positive");
+    if (!a->d_centres || !a->d_structure || !a->d_ray_o || !a->d_ray_d || !a->d_stats || !a->d_hit_rank || !a->d_s_ray ||
+        !a->d_s_vox || !a->d_s_depth || !a->d_s_xyz || !a->d_s_flag || !a->d_ray_nsamp || !a->d_ray_offset || !a->d_workspace)
+        return nl_set_error("nl_render_samples: null pointer");
+    if (a->workspace_bytes < nl_render_workspace_bytes(a->n_rays)) return nl_set_error("nl_render_samples: workspace too small");
+    if (!(a->step_size > 0.f) || !(a->voxel_size > 0.f)) return nl_set_error("nl_render_samples: step_size and voxel_size must be > 0");
+    if (a->d_noise && a->noise_stride <= 0) return nl_set_error("nl_render_samples: noise_stride must be > 0 with d_noise");
+    const int R = a->n_rays;
+    Workspace ws = carve(a->d_workspace, R);
+    cudaMemsetAsync(a->d_stats, 0, sizeof(nl_render_stats), stream);
+    const int blocks = nl_div_up(R, 128);
+    k_traverse_sort<<<blocks, 128, 0, stream>>>(R, a->voxel_size, a->max_distance, a->d_centres, a->d_structure, a->d_ray_o,
+                                                a->d_ray_d, ws, a->d_ray_nsamp, a->d_stats);
+    k_scan<SCAN_HITS><<<1, 1024, 0, stream>>>(R, ws.nvalid, a->d_hit_rank, ws.hitray, a->d_stats, 0);
+    SampleParams p;
+    p.R = R; p.sample_capacity = a->sample_capacity; p.compat = a->reference_compat;
+    p.step_size = a->step_size; p.truncation = a->truncation; p.max_depth = a->max_depth;
+    p.ray_o = a->d_ray_o; p.ray_d = a->d_ray_d; p.gt_depth = a->d_gt_depth; p.cosv = a->d_cos; p.noise = a->d_noise;
+    p.noise_stride = a->noise_stride; p.rng_seed = a->rng_seed;
+    p.s_ray = a->d_s_ray; p.s_vox = a->d_s_vox; p.s_depth = a->d_s_depth; p.s_xyz = a->d_s_xyz; p.s_flag = a->d_s_flag;
+    p.ray_nsamp = a->d_ray_nsamp; p.ray_offset = a->d_ray_offset;
+    k_sample<false><<<blocks, 128, 0, stream>>>(p, ws, a->d_stats);
+    k_scan<SCAN_SAMPLES><<<1, 1024, 0, stream>>>(R, a->d_ray_nsamp, a->d_ray_offset, nullptr, a->d_stats, a->sample_capacity);
+    k_sample<true><<<blocks, 128, 0, stream>>>(p, ws, a->d_stats);
+    if (a->d_gt_depth) k_loss_prepare<<<1, 1, 0, stream>>>(a->d_stats, a->fs_weight, a->sdf_weight);
+    NL_CHECK_LAUNCH("nl_render_samples");
+    return NL_OK;
+}
+
+extern "C" int nl_loss_prepare(nl_render_stats *d_stats, float fs_weight, float sdf_weight, void *stream) {
+    if (!d_stats) return nl_set_error("nl_loss_prepare: null stats");
+    k_loss_prepare<<<1, 1, 0, (cudaStream_t)stream>>>(d_stats, fs_weight, sdf_weight);
+    NL_CHECK_LAUNCH("nl_loss_prepare");
+    return NL_OK;
+}
+
+extern "C" int nl_loss_finalize(nl_render_stats *d_stats, float fs_weight, float sdf_weight, void *stream) {
+    if (!d_stats) return nl_set_error("nl_loss_finalize: null stats");
+    k_loss_finalize<<<1, 1, 0, (cudaStream_t)stream>>>(d_stats, fs_weight, sdf_weight);
+    NL_CHECK_LAUNCH("nl_loss_finalize");
+    return NL_OK;
+}

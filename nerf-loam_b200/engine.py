@@ -1,0 +1,323 @@
+"""SDFEngine: the fused per-iteration pipeline (rays -> samples -> features -> SDF -> loss -> gradients)
+as a chain of C-ABI kernel launches on one CUDA stream, with persistent device buffers and no host
+synchronisation inside an iteration.
+
+This is the host-side orchestration of SURVEY.md section 8 a-2 .. a-12; the arithmetic is all in
+libnerfloam_b200.so.  torch is used for device memory and streams only.
+"""
+import ctypes as C
+
+import torch
+
+from . import _capi
+from ._capi import MlpGrads, MlpWeights, RenderArgs, RenderStats
+
+STATS_BYTES = C.sizeof(RenderStats)
+N_SAMPLES_OFFSET = RenderStats.n_samples.offset
+
+
+class MapState:
+    """Device-resident map in hot-path layout: centres f32[n,3], structure i32[n,9], vox2row i32[n,8],
+    emb bf16[V,16].  Built from the reference's map_states dict (mapping.py:328-337) by composing
+    voxel_vertex_idx with voxel_id2embedding_id once per map update (instead of the 8 GB CPU lookup
+    and the D2H/H2D detour of get_features, render_helpers.py:88, on every chunk of every iteration)."""
+
+    def __init__(self, centres, structure, vox2row, emb, device="cuda"):
+        self.centres = centres.detach().to(device=device, dtype=torch.float32).contiguous()
+        self.structure = structure.detach().to(device=device, dtype=torch.int32).contiguous()
+        self.vox2row = vox2row.detach().to(device=device, dtype=torch.int32).contiguous()
+        self.emb = emb if (emb.is_cuda and emb.dtype == torch.bfloat16 and emb.is_contiguous()) else \
+            emb.detach().to(device=device, dtype=torch.bfloat16).contiguous()
+        assert self.centres.shape[1] == 3 and self.structure.shape[1] == 9 and self.vox2row.shape[1] == 8
+        assert self.emb.shape[1] == 16, "embedding dim must be 16 (decoder_specs.in_dim of every shipped config)"
+        self.n_nodes = self.centres.shape[0]
+
+    _cache = {}
+
+    @classmethod
+    def from_map_states(cls, map_states, device="cuda"):
+        """map_states: the reference dict.  vox2row is cached on the identity/version of the index tensors."""
+        vidx = map_states["voxel_vertex_idx"]
+        id2 = map_states["voxel_id2embedding_id"]
+        key = (vidx.data_ptr(), vidx._version, tuple(vidx.shape), id2.data_ptr(), id2._version)
+        hit = cls._cache.get("key") == key
+        if not hit:
+            v = vidx.detach().cpu().long()
+            flat = id2.detach().cpu().reshape(-1)
+            rows = torch.where(v >= 0, flat[v.clamp(min=0)].long(), torch.full_like(v, -1))
+            cls._cache = {"key": key, "vox2row": rows.to(torch.int32).to(device).contiguous(),
+                          "centres": map_states["voxel_center_xyz"].detach().to(device=device, dtype=torch.float32).contiguous(),
+                          "structure": map_states["voxel_structure"].detach().to(device=device, dtype=torch.int32).contiguous()}
+        c = cls._cache
+        obj = cls.__new__(cls)
+        obj.centres, obj.structure, obj.vox2row = c["centres"], c["structure"], c["vox2row"]
+        emb = map_states["voxel_vertex_emb"]
+        obj.emb = emb if (emb.is_cuda and emb.dtype == torch.bfloat16 and emb.is_contiguous()) else \
+            emb.detach().to(device=device, dtype=torch.bfloat16).contiguous()
+        obj.n_nodes = obj.centres.shape[0]
+        return obj
+
+
+class DecoderBuffers:
+    """Flat device views of the decoder parameters for the kernels + transposes + fp32 gradient buffers."""
+
+    def __init__(self, decoder, device):
+        lin = list(decoder.pts_linears)
+        if len(lin) != 2 or getattr(decoder, "skips", []) not in ([], None):
+            raise NotImplementedError("fused decoder kernel supports depth=2, skips=[] (every shipped config)")
+        self.params = [lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias, decoder.sdf_out.weight, decoder.sdf_out.bias]
+        W = lin[0].weight.shape[0]
+        if lin[0].weight.shape[1] != 16 or tuple(lin[1].weight.shape) != (W, W) or W not in (32, 64, 128, 256):
+            raise NotImplementedError(f"unsupported decoder shape in_dim={lin[0].weight.shape[1]} width={W}")
+        for p in self.params:
+            if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
+                raise RuntimeError("decoder parameters must be contiguous fp32 CUDA tensors (call decoder.cuda())")
+        self.width = W
+        self.W0t = torch.empty((16, W), device=device, dtype=torch.float32)
+        self.W1t = torch.empty((W, W), device=device, dtype=torch.float32)
+        self.grads = [torch.zeros_like(p) for p in self.params]
+
+    def weights_struct(self):
+        p = self.params
+        return MlpWeights(self.width, *[C.c_void_p(t.data_ptr()) for t in p], C.c_void_p(self.W0t.data_ptr()),
+                          C.c_void_p(self.W1t.data_ptr()))
+
+    def grads_struct(self):
+        return MlpGrads(*[C.c_void_p(g.data_ptr()) for g in self.grads])
+
+    def refresh_transposes(self):
+        _capi.check(_capi.lib().nl_mlp_prepare(self.width, _capi.ptr(self.params[0]), _capi.ptr(self.params[2]), _capi.ptr(self.W0t),
+                                               _capi.ptr(self.W1t), _capi.stream_ptr()), "nl_mlp_prepare")
+        _capi.LAUNCHES += 2
+
+
+class SDFEngine:
+    """Persistent buffers for up to `max_rays` rays and `max_samples` samples per iteration."""
+
+    def __init__(self, max_rays, max_samples, device="cuda", width=256, want_decoder_grads=True):
+        self.device = torch.device(device)
+        self.max_rays, self.max_samples = int(max_rays), int(max_samples)
+        d = self.device
+        R, M = self.max_rays, self.max_samples
+        f32, i32 = torch.float32, torch.int32
+        self.ws_bytes = int(_capi.lib().nl_render_workspace_bytes(R))
+        self.workspace = torch.empty(self.ws_bytes, dtype=torch.uint8, device=d)
+        self.stats = torch.zeros(STATS_BYTES, dtype=torch.uint8, device=d)
+        self.ray_o = torch.empty((R, 3), dtype=f32, device=d)
+        self.ray_d = torch.empty((R, 3), dtype=f32, device=d)
+        self.hit_rank = torch.empty(R, dtype=i32, device=d)
+        self.ray_nsamp = torch.empty(R, dtype=i32, device=d)
+        self.ray_offset = torch.empty(R, dtype=i32, device=d)
+        self.s_ray = torch.empty(M, dtype=i32, device=d)
+        self.s_vox = torch.empty(M, dtype=i32, device=d)
+        self.s_depth = torch.empty(M, dtype=f32, device=d)
+        self.s_xyz = torch.empty((M, 3), dtype=f32, device=d)
+        self.s_flag = torch.empty(M, dtype=torch.uint8, device=d)
+        self.feats = torch.empty((M, 16), dtype=f32, device=d)
+        self.dfeats = torch.empty((M, 16), dtype=f32, device=d)
+        self.sdf = torch.empty(M, dtype=f32, device=d)
+        self.act_h1 = self.act_dh2 = None
+        self._act_width = 0
+        self.want_decoder_grads = want_decoder_grads
+        self.grad_emb = None          # fp32 [V,16]
+        self.pose_acc = None          # fp32 [F,12]
+        self.Rt12 = None
+        self.pose_grad = None
+        self._stats_host = torch.empty(STATS_BYTES, dtype=torch.uint8).pin_memory() if torch.cuda.is_available() else None
+        self.events = None            # set to {} to record CUDA events around the main kernels (bench.py)
+        # typed views of the stats block for collectives (multi-GPU ray sharding)
+        self._st_i32 = self.stats.view(torch.int32)
+        self._st_i64 = self.stats.view(torch.int64)
+        self._st_f64 = self.stats.view(torch.float64)
+
+    def _mark(self, name):
+        if self.events is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.events.setdefault(name, []).append(ev)
+
+    def allreduce_sample_stats(self, group):
+        """Ray sharding: make the loss-mask counters global (SUM), S_max global (MAX), R_hit global (SUM)."""
+        import torch.distributed as dist
+        dist.all_reduce(self._st_i64[4:10], op=dist.ReduceOp.SUM, group=group)      # cnt_* / pad_* counters
+        dist.all_reduce(self._st_f64[10:12], op=dist.ReduceOp.SUM, group=group)     # pad_sdf_d2, pad_sdf_d2_nsamp
+        dist.all_reduce(self._st_i32[0:1], op=dist.ReduceOp.SUM, group=group)       # n_hit_rays
+        dist.all_reduce(self._st_i32[2:3], op=dist.ReduceOp.MAX, group=group)       # max_samples
+
+    def allreduce_loss_sums(self, group):
+        import torch.distributed as dist
+        dist.all_reduce(self._st_f64[16:18], op=dist.ReduceOp.SUM, group=group)     # fs_sum, sdf_sum
+
+    # ------------------------------------------------------------------ helpers
+    @property
+    def n_samples_dev(self):
+        return C.c_void_p(self.stats.data_ptr() + N_SAMPLES_OFFSET)
+
+    def read_stats(self):
+        """Device -> host copy of nl_render_stats (synchronises the stream)."""
+        self._stats_host.copy_(self.stats, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return RenderStats.from_buffer_copy(self._stats_host.numpy().tobytes())
+
+    def _ensure_act(self, width):
+        if self.act_h1 is None or self._act_width != width:
+            self.act_h1 = torch.empty((self.max_samples, width), dtype=torch.float32, device=self.device)
+            self.act_dh2 = torch.empty((self.max_samples, width), dtype=torch.float32, device=self.device)
+            self._act_width = width
+
+    # ------------------------------------------------------------------ stages
+    def rays_from_poses(self, pose6, dir_local, ray_frame):
+        """pose6 f32[F,6] (device), dir_local f32[R,3], ray_frame i32[R] or None -> fills ray_o / ray_d."""
+        F, R = pose6.shape[0], dir_local.shape[0]
+        if self.Rt12 is None or self.Rt12.shape[0] < F:
+            self.Rt12 = torch.empty((F, 12), dtype=torch.float32, device=self.device)
+        st = _capi.stream_ptr()
+        _capi.check(_capi.lib().nl_pose_matrices(F, _capi.ptr(pose6), _capi.ptr(self.Rt12), st), "nl_pose_matrices")
+        _capi.check(_capi.lib().nl_rays_from_poses(R, _capi.ptr(dir_local), _capi.ptr(ray_frame), _capi.ptr(self.Rt12),
+                                                   _capi.ptr(self.ray_o), _capi.ptr(self.ray_d), st), "nl_rays_from_poses")
+        _capi.LAUNCHES += 2
+
+    def render_samples(self, m, R, cfg, ray_o=None, ray_d=None, gt_depth=None, cos=None, noise=None, rng_seed=0,
+                       reference_compat=True):
+        """rays -> compact sample list (nl_render_samples).  cfg: dict(voxel_size, step_size, max_distance,
+        truncation, max_depth, fs_weight, sdf_weight)."""
+        assert R <= self.max_rays
+        a = RenderArgs()
+        a.n_rays, a.n_nodes, a.sample_capacity, a.reference_compat = R, m.n_nodes, self.max_samples, int(bool(reference_compat))
+        a.voxel_size, a.step_size, a.max_distance = cfg["voxel_size"], cfg["step_size"], cfg["max_distance"]
+        a.truncation, a.max_depth = cfg.get("truncation", 0.0), cfg.get("max_depth", 0.0)
+        a.fs_weight, a.sdf_weight = cfg.get("fs_weight", 0.0), cfg.get("sdf_weight", 0.0)
+        a.d_centres, a.d_structure = m.centres.data_ptr(), m.structure.data_ptr()
+        a.d_ray_o = (ray_o if ray_o is not None else self.ray_o).data_ptr()
+        a.d_ray_d = (ray_d if ray_d is not None else self.ray_d).data_ptr()
+        a.d_gt_depth = gt_depth.data_ptr() if gt_depth is not None else None
+        a.d_cos = cos.data_ptr() if cos is not None else None
+        if noise is not None:
+            assert noise.is_cuda and noise.dtype == torch.float32 and noise.is_contiguous() and noise.dim() == 2
+            a.d_noise, a.noise_stride = noise.data_ptr(), noise.shape[1]
+        a.rng_seed = int(rng_seed) & 0xffffffff
+        a.d_workspace, a.workspace_bytes = self.workspace.data_ptr(), self.ws_bytes
+        a.d_stats, a.d_hit_rank = self.stats.data_ptr(), self.hit_rank.data_ptr()
+        a.d_s_ray, a.d_s_vox, a.d_s_depth = self.s_ray.data_ptr(), self.s_vox.data_ptr(), self.s_depth.data_ptr()
+        a.d_s_xyz, a.d_s_flag = self.s_xyz.data_ptr(), self.s_flag.data_ptr()
+        a.d_ray_nsamp, a.d_ray_offset = self.ray_nsamp.data_ptr(), self.ray_offset.data_ptr()
+        _capi.check(_capi.lib().nl_render_samples(C.byref(a), _capi.stream_ptr()), "nl_render_samples")
+        _capi.LAUNCHES += 6 if gt_depth is not None else 5
+
+    def gather_forward(self, m, M_cap=None, xyz=None, vox=None, M_dev=True, feats=None):
+        M_cap = self.max_samples if M_cap is None else M_cap
+        _capi.check(_capi.lib().nl_gather_trilinear_fwd(
+            M_cap, self.n_samples_dev if M_dev else None, _capi.ptr(xyz if xyz is not None else self.s_xyz),
+            _capi.ptr(vox if vox is not None else self.s_vox), _capi.ptr(m.centres), _capi.ptr(m.vox2row), _capi.ptr(m.emb),
+            float(self._vs), _capi.ptr(feats if feats is not None else self.feats), _capi.stream_ptr()), "nl_gather_trilinear_fwd")
+        _capi.LAUNCHES += 1
+
+    # ------------------------------------------------------------------ full passes
+    def forward(self, m, dec, R, cfg, ray_o=None, ray_d=None, noise=None, rng_seed=0, reference_compat=True):
+        """Forward only (render_rays / evaluation): fills s_*, feats, sdf.  Returns nothing; read_stats() for sizes."""
+        self._vs = cfg["voxel_size"]
+        self.render_samples(m, R, cfg, ray_o, ray_d, None, None, noise, rng_seed, reference_compat)
+        dec.refresh_transposes()
+        self.gather_forward(m)
+        w = dec.weights_struct()
+        _capi.check(_capi.lib().nl_mlp_forward(self.max_samples, self.n_samples_dev, _capi.ptr(self.feats), C.byref(w),
+                                               _capi.ptr(self.sdf), _capi.stream_ptr()), "nl_mlp_forward")
+        _capi.LAUNCHES += 1
+
+    def forward_backward(self, m, dec, R, cfg, gt_depth, cos, dir_local=None, ray_frame=None, n_frames=1, ray_o=None,
+                         ray_d=None, noise=None, rng_seed=0, reference_compat=True, update_decoder=True, update_emb=True,
+                         update_pose=True, pose6=None, group=None):
+        """One optimisation iteration without the optimiser step.  Gradients land in
+        self.grad_emb (fp32 [V,16]), dec.grads (fp32), self.pose_grad (fp32 [F,6]); the loss in stats."""
+        lib = _capi.lib()
+        st = _capi.stream_ptr()
+        self._vs = cfg["voxel_size"]
+        self._mark("t0")
+        self.render_samples(m, R, cfg, ray_o, ray_d, gt_depth, cos, noise, rng_seed, reference_compat)
+        if group is not None:   # the loss normalisation is global (criterion.py:84-100): one tiny exchange before backward
+            self.allreduce_sample_stats(group)
+            _capi.check(lib.nl_loss_prepare(C.c_void_p(self.stats.data_ptr()), float(cfg["fs_weight"]), float(cfg["sdf_weight"]), st),
+                        "nl_loss_prepare")
+            _capi.LAUNCHES += 1
+        self._mark("t_samples")
+        dec.refresh_transposes()
+        self.gather_forward(m)
+        self._mark("t_gather_fwd")
+        grads_p = None
+        if update_decoder:
+            self._ensure_act(dec.width)
+            for g in dec.grads:
+                g.zero_()
+            gs = dec.grads_struct()
+            grads_p = C.byref(gs)
+        w = dec.weights_struct()
+        _capi.check(lib.nl_mlp_train(self.max_samples, self.n_samples_dev, _capi.ptr(self.feats), C.byref(w), _capi.ptr(self.s_flag),
+                                     _capi.ptr(self.s_depth), _capi.ptr(self.s_ray), _capi.ptr(cos), _capi.ptr(gt_depth),
+                                     C.c_void_p(self.stats.data_ptr()), float(cfg["truncation"]), _capi.ptr(self.sdf),
+                                     _capi.ptr(self.dfeats), grads_p, _capi.ptr(self.act_h1) if update_decoder else None,
+                                     _capi.ptr(self.act_dh2) if update_decoder else None, None, st), "nl_mlp_train")
+        _capi.LAUNCHES += 2 if update_decoder else 1
+        self._mark("t_mlp")
+        if update_emb:
+            if self.grad_emb is None or self.grad_emb.shape[0] != m.emb.shape[0]:
+                self.grad_emb = torch.zeros((m.emb.shape[0], 16), dtype=torch.float32, device=self.device)
+            else:
+                self.grad_emb.zero_()
+        want_pose = update_pose and dir_local is not None
+        if want_pose:
+            if self.pose_acc is None or self.pose_acc.shape[0] != n_frames:
+                self.pose_acc = torch.zeros((n_frames, 12), dtype=torch.float32, device=self.device)
+                self.pose_grad = torch.zeros((n_frames, 6), dtype=torch.float32, device=self.device)
+            else:
+                self.pose_acc.zero_()
+        if update_emb or want_pose:
+            _capi.check(lib.nl_gather_trilinear_bwd(
+                self.max_samples, self.n_samples_dev, _capi.ptr(self.s_xyz), _capi.ptr(self.s_vox), _capi.ptr(m.centres),
+                _capi.ptr(m.vox2row), _capi.ptr(m.emb), float(cfg["voxel_size"]), _capi.ptr(self.dfeats), 1,
+                _capi.ptr(self.grad_emb) if update_emb else None, None, _capi.ptr(self.s_ray), _capi.ptr(self.s_depth),
+                _capi.ptr(dir_local) if want_pose else None, _capi.ptr(ray_frame) if want_pose else None, int(n_frames),
+                _capi.ptr(self.pose_acc) if want_pose else None, st), "nl_gather_trilinear_bwd")
+            _capi.LAUNCHES += 1
+        self._mark("t_gather_bwd")
+        if group is not None:
+            import torch.distributed as dist
+            self.allreduce_loss_sums(group)
+            if update_emb:
+                dist.all_reduce(self.grad_emb, group=group)
+            if update_decoder:
+                for g in dec.grads:
+                    dist.all_reduce(g, group=group)
+            if want_pose:
+                dist.all_reduce(self.pose_acc, group=group)
+        if want_pose:
+            _capi.check(lib.nl_pose_grad(n_frames, _capi.ptr(pose6), _capi.ptr(self.pose_acc), _capi.ptr(self.pose_grad), st),
+                        "nl_pose_grad")
+            _capi.LAUNCHES += 1
+        _capi.check(lib.nl_loss_finalize(C.c_void_p(self.stats.data_ptr()), float(cfg["fs_weight"]), float(cfg["sdf_weight"]), st),
+                    "nl_loss_finalize")
+        _capi.LAUNCHES += 1
+
+
+class FusedAdam:
+    """torch.optim.Adam semantics (fresh state per construction, like render_helpers.py:353 / :448) with one
+    fused kernel per tensor.  groups: list of dict(param=tensor, grad=tensor(fp32), lr=float)."""
+
+    def __init__(self, groups, betas=(0.9, 0.999), eps=1e-8):
+        self.groups = groups
+        self.betas, self.eps = betas, eps
+        self.step_count = 0
+        for g in groups:
+            p = g["param"]
+            g["m"] = torch.zeros_like(p)
+            g["v"] = torch.zeros_like(p)
+
+    def step(self):
+        self.step_count += 1
+        lib = _capi.lib()
+        st = _capi.stream_ptr()
+        for g in self.groups:
+            p = g["param"]
+            fn = lib.nl_adam_bf16 if p.dtype == torch.bfloat16 else lib.nl_adam_f32
+            _capi.check(fn(p.numel(), _capi.ptr(p), _capi.ptr(g["grad"]), _capi.ptr(g["m"]), _capi.ptr(g["v"]), float(g["lr"]),
+                           self.betas[0], self.betas[1], self.eps, self.step_count, st), "nl_adam")
+            _capi.LAUNCHES += 1

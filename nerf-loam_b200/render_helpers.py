@@ -1,0 +1,319 @@
+"""Drop-in for src/variations/render_helpers.py: render_rays (:190), bundle_adjust_frames (:321),
+track_frame (:428), get_scores (:97) with the reference signatures, running on the fused sm_100a kernel
+chain (engine.SDFEngine) instead of ~60 eager PyTorch ops + 2 CUDA kernels + autograd per iteration.
+
+Behavioural notes (also in DESIGN.md):
+  * ray/voxel intersection order for hits with bit-identical min_depth is the DFS emission order (the
+    reference leaves it to an unstable torch.sort);
+  * stochastic sampling noise comes from a counter-based generator inside the kernel seeded from torch's
+    global generator (the reference draws a data-dependent-shaped uniform_() tensor); pass
+    deterministic=True or noise=<tensor> for bit-reproducible sampling against the reference;
+  * `max_voxel_hit` and render_rays' `truncation` are accepted and ignored exactly like the reference
+    (voxel_helpers.py:531-533; render_helpers.py:190-318);
+  * the unused autograd.grad(sdf, xyz) of render_helpers.py:293-297 is not computed.
+"""
+from copy import deepcopy
+
+import torch
+
+from . import _capi
+from .engine import DecoderBuffers, FusedAdam, MapState, SDFEngine
+
+MAX_DEPTH = 80.0
+
+_ENGINES = {}
+
+
+def _engine(n_rays, min_samples, device):
+    """Engines are cached by capacity class (power-of-two rays / samples)."""
+    r = 1 << max(10, (int(n_rays) - 1).bit_length())
+    m = 1 << max(16, (int(min_samples) - 1).bit_length())
+    key = (r, m, str(device))
+    e = _ENGINES.get(key)
+    if e is None:
+        for k in [k for k in _ENGINES if k[0] <= r and k[1] <= m and k[2] == str(device)]:
+            del _ENGINES[k]
+        e = _ENGINES[key] = SDFEngine(r, m, device)
+    return e
+
+
+def _seed_from_torch():
+    return int(torch.randint(1, 2 ** 31 - 1, (1,)).item())
+
+
+def _cfg(step_size, voxel_size, max_distance, crit=None):
+    c = dict(step_size=float(step_size), voxel_size=float(voxel_size), max_distance=float(max_distance))
+    if crit is not None:
+        c.update(crit.kernel_config())
+    return c
+
+
+def _run_with_capacity(fn, n_rays, device, samples_per_ray=40):
+    """Run fn(engine) and grow the sample capacity if the kernels report it was exceeded."""
+    cap = n_rays * samples_per_ray
+    while True:
+        eng = _engine(n_rays, cap, device)
+        fn(eng)
+        st = eng.read_stats()
+        if st.error & 2:
+            cap = max(cap * 2, st.n_samples + 1)
+            continue
+        return eng, st
+
+
+class _RenderSDF(torch.autograd.Function):
+    """Attaches the autograd graph to the SDF values the fused forward already produced: sdf of the valid
+    samples as a differentiable function of (rays_o, rays_d, embeddings, decoder params).  backward runs
+    the fused MLP backward (forward recomputed in-kernel), the gather backward and the ray chain rule."""
+
+    @staticmethod
+    def forward(ctx, rays_o, rays_d, emb, pack, *dec_params):
+        ctx.pack = pack
+        return pack["sdf"]
+
+    @staticmethod
+    def backward(ctx, gsdf):
+        import ctypes as C
+        s = ctx.pack
+        m, dec_mod, cfg = s["m"], s["dec"], s["cfg"]
+        M = s["xyz"].shape[0]
+        dev = s["xyz"].device
+        bufs = DecoderBuffers(dec_mod, dev)
+        bufs.refresh_transposes()
+        need_dec = any(ctx.needs_input_grad[4:])
+        W = bufs.width
+        sdf = torch.empty(M, dtype=torch.float32, device=dev)
+        dfeats = torch.empty((M, 16), dtype=torch.float32, device=dev)
+        h1 = dh2 = None
+        gs = None
+        if need_dec:
+            h1 = torch.empty((M, W), dtype=torch.float32, device=dev)
+            dh2 = torch.empty((M, W), dtype=torch.float32, device=dev)
+            gs = bufs.grads_struct()
+        w = bufs.weights_struct()
+        g = gsdf.contiguous().float()
+        lib, st = _capi.lib(), _capi.stream_ptr()
+        _capi.check(lib.nl_mlp_train(M, None, _capi.ptr(s["feats"]), C.byref(w), None, None, None, None, None, None, 0.0,
+                                     _capi.ptr(sdf), _capi.ptr(dfeats), C.byref(gs) if need_dec else None, _capi.ptr(h1),
+                                     _capi.ptr(dh2), _capi.ptr(g), st), "nl_mlp_train")
+        _capi.LAUNCHES += 2 if need_dec else 1
+        need_emb = ctx.needs_input_grad[2]
+        need_rays = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        grad_emb = torch.zeros((m.emb.shape[0], 16), dtype=torch.float32, device=dev) if need_emb else None
+        dxyz = torch.empty((M, 3), dtype=torch.float32, device=dev) if need_rays else None
+        if need_emb or need_rays:
+            _capi.check(lib.nl_gather_trilinear_bwd(M, None, _capi.ptr(s["xyz"]), _capi.ptr(s["vox"]), _capi.ptr(m.centres),
+                                                    _capi.ptr(m.vox2row), _capi.ptr(m.emb), float(cfg["voxel_size"]),
+                                                    _capi.ptr(dfeats), 1, _capi.ptr(grad_emb), _capi.ptr(dxyz), None, None, None,
+                                                    None, 0, None, st), "nl_gather_trilinear_bwd")
+            _capi.LAUNCHES += 1
+        g_o = g_d = None
+        if need_rays:  # xyz = o + d * depth
+            ray = s["ray"].long()
+            g_o = torch.zeros((s["R"], 3), dtype=torch.float32, device=dev).index_add_(0, ray, dxyz)
+            g_d = torch.zeros((s["R"], 3), dtype=torch.float32, device=dev).index_add_(0, ray, dxyz * s["depth"].unsqueeze(-1))
+        dec_grads = bufs.grads if need_dec else [None] * 6
+        return (g_o, g_d, grad_emb.to(m.emb.dtype) if need_emb else None, None, *dec_grads)
+
+
+def _decoder_params(dec):
+    return [dec.pts_linears[0].weight, dec.pts_linears[0].bias, dec.pts_linears[1].weight, dec.pts_linears[1].bias,
+            dec.sdf_out.weight, dec.sdf_out.bias]
+
+
+def render_rays(rays_o, rays_d, map_states, sdf_network, step_size, voxel_size, truncation, max_voxel_hit, max_distance,
+                chunk_size=10000, profiler=None, return_raw=False, deterministic=False, noise=None, reference_compat=True):
+    """render_helpers.py:190-318.  rays_o / rays_d: [1,R,3] CUDA fp32.  Returns the reference's dict
+    (z_vals [R_hit,S_max], sdf, ray_mask [1,R], valid_mask, sampled_xyz) or None when nothing is hit.
+    The result is differentiable w.r.t. rays, embeddings and decoder parameters like the reference's."""
+    dev = rays_o.device
+    if dev.type != "cuda":
+        raise RuntimeError("render_rays runs on the GPU only (no CPU fallback)")
+    if profiler is not None:
+        profiler.tick("ray_intersect")
+    ro = rays_o.reshape(-1, 3).float().contiguous()
+    rd = rays_d.reshape(-1, 3).float().contiguous()
+    R = ro.shape[0]
+    m = map_states if isinstance(map_states, MapState) else MapState.from_map_states(map_states, dev)
+    emb_in = m.emb if isinstance(map_states, MapState) else map_states["voxel_vertex_emb"]
+    if not (emb_in.is_cuda and emb_in.dtype == torch.bfloat16):
+        emb_in = m.emb
+    cfg = _cfg(step_size, voxel_size, max_distance)
+    seed = 0 if (deterministic or noise is not None) else _seed_from_torch()
+    bufs = DecoderBuffers(sdf_network, dev)
+    with torch.no_grad():
+        eng, st = _run_with_capacity(lambda e: e.forward(m, bufs, R, cfg, ro.detach(), rd.detach(), noise, seed, reference_compat),
+                                     R, dev)
+    if profiler is not None:
+        profiler.tok("ray_intersect")
+    if st.n_hit_rays <= 0 or (st.error & 1) or st.n_samples == 0:
+        return None
+    M, Rh, S = st.n_samples, st.n_hit_rays, st.max_samples
+    pack = dict(xyz=eng.s_xyz[:M].clone(), vox=eng.s_vox[:M].clone(), ray=eng.s_ray[:M].clone(), depth=eng.s_depth[:M].clone(),
+                feats=eng.feats[:M].clone(), sdf=eng.sdf[:M].clone(), m=m, dec=sdf_network, cfg=cfg, R=R)
+    sdf_valid = _RenderSDF.apply(ro, rd, emb_in, pack, *_decoder_params(sdf_network))
+    ray = pack["ray"].long()
+    row = eng.hit_rank[:R].long()[ray]
+    col = torch.arange(M, device=dev) - eng.ray_offset[:R].long()[ray]
+    z_vals = torch.full((Rh, S), MAX_DEPTH, dtype=torch.float32, device=dev)
+    z_vals[row, col] = pack["depth"]
+    valid = torch.zeros((Rh, S), dtype=torch.bool, device=dev)
+    valid[row, col] = True
+    sdf = torch.ones((Rh, S), dtype=torch.float32, device=dev).index_put((row, col), sdf_valid)
+    return {"z_vals": z_vals, "sdf": sdf, "ray_mask": (eng.hit_rank[:R] >= 0).view(1, -1), "valid_mask": valid,
+            "sampled_xyz": pack["xyz"]}
+
+
+@torch.no_grad()
+def get_scores(sdf_network, map_states, voxel_size, bits=8):
+    """render_helpers.py:97-153: SDF on a res^3 lattice inside every voxel -> f32[n,res,res,res,1] (CPU)."""
+    dev = torch.device("cuda")
+    m = map_states if isinstance(map_states, MapState) else MapState.from_map_states(map_states, dev)
+    res = bits
+    lin = torch.linspace(-0.5, 0.5, res)
+    xx, yy, zz = torch.meshgrid(lin, lin, lin, indexing="ij")
+    offs = (torch.stack([xx, yy, zz], dim=-1).float().to(dev) * voxel_size).reshape(1, -1, 3)
+    bufs = DecoderBuffers(sdf_network, dev)
+    bufs.refresh_transposes()
+    n = m.n_nodes
+    out = []
+    chunk = 10000
+    import ctypes as C
+    for i in range(0, n, chunk):
+        c = m.centres[i:i + chunk]
+        xyz = (offs + c.unsqueeze(1)).reshape(-1, 3).contiguous()
+        vox = torch.arange(i, i + c.shape[0], device=dev, dtype=torch.int32)[:, None].expand(-1, res ** 3).reshape(-1).contiguous()
+        M = xyz.shape[0]
+        if M == 0:
+            continue
+        feats = torch.empty((M, 16), dtype=torch.float32, device=dev)
+        sdf = torch.empty(M, dtype=torch.float32, device=dev)
+        # voxels without embeddings (interior / FEATURE rows) have vox2row = -1: rows clamp to 0 there like any
+        # garbage the reference would read; they are never meshed (mesh_util only uses SURFACE voxels)
+        _capi.check(_capi.lib().nl_gather_trilinear_fwd(M, None, _capi.ptr(xyz), _capi.ptr(vox), _capi.ptr(m.centres),
+                                                        _capi.ptr(m.vox2row), _capi.ptr(m.emb), float(voxel_size), _capi.ptr(feats),
+                                                        _capi.stream_ptr()), "nl_gather_trilinear_fwd")
+        w = bufs.weights_struct()
+        _capi.check(_capi.lib().nl_mlp_forward(M, None, _capi.ptr(feats), C.byref(w), _capi.ptr(sdf), _capi.stream_ptr()),
+                    "nl_mlp_forward")
+        _capi.LAUNCHES += 2
+        out.append(sdf.reshape(-1, res ** 3, 1).cpu())
+    return torch.cat(out, 0).view(-1, res, res, res, 1)
+
+
+# ======================================================================================================
+# optimisation loops
+# ======================================================================================================
+class _FrameBatch:
+    """Device copies of the per-frame point data (uploaded once per call instead of per iteration)."""
+
+    def __init__(self, frames, dev):
+        self.frames = frames
+        self.dirs = [f.rays_d.reshape(-1, 3).float().to(dev) for f in frames]
+        self.cos = [f.pointsCos.float().view(-1).to(dev) for f in frames]
+        self.gt = [torch.norm(f.points.float().to(dev), 2, -1) * c for f, c in zip(frames, self.cos)]  # criterion.py:30-32
+
+    def select(self, N_rays, dev, track=False):
+        """Host ray selection like the reference (frame.sample_rays -> boolean mask, CPU RNG), gathered on the device."""
+        d, g, c, fid = [], [], [], []
+        for i, f in enumerate(self.frames):
+            f.sample_rays(N_rays, track=True) if track else f.sample_rays(N_rays)
+            idx = f.sample_mask.view(-1).nonzero().view(-1).to(dev, non_blocking=True)
+            d.append(self.dirs[i][idx]); g.append(self.gt[i][idx]); c.append(self.cos[i][idx])
+            fid.append(torch.full((idx.shape[0],), i, dtype=torch.int32, device=dev))
+        return torch.cat(d).contiguous(), torch.cat(g).contiguous(), torch.cat(c).contiguous(), torch.cat(fid).contiguous()
+
+
+def bundle_adjust_frames(keyframe_graph, embeddings, map_states, sdf_network, loss_criteria, voxel_size, step_size,
+                         N_rays=512, num_iterations=10, truncation=0.1, max_voxel_hit=10, max_distance=10,
+                         learning_rate=[1e-2, 1e-2, 5e-3], update_pose=True, update_decoder=True, profiler=None,
+                         deterministic=False, noise_per_iter=None, loss_log=None):
+    """render_helpers.py:321-425.  Mutates `embeddings` (bf16 CUDA table), the decoder parameters and the
+    frame poses in place, like the reference.  Returns None."""
+    dev = embeddings.device
+    if dev.type != "cuda":
+        raise RuntimeError("bundle_adjust_frames runs on the GPU only (no CPU fallback)")
+    frames = list(keyframe_graph)
+    F = len(frames)
+    m = map_states if isinstance(map_states, MapState) else MapState.from_map_states(map_states, dev)
+    emb = embeddings.detach()
+    if not (emb.dtype == torch.bfloat16 and emb.is_contiguous()):
+        raise RuntimeError("embeddings must be a contiguous bf16 CUDA tensor (mapping.py:305-314)")
+    m.emb = emb
+    cfg = _cfg(step_size, voxel_size, max_distance, loss_criteria)
+    bufs = DecoderBuffers(sdf_network, dev)
+    R = N_rays * F
+    eng = _engine(R, R * 40, dev)
+    batch = _FrameBatch(frames, dev)
+    pose6 = torch.stack([f.pose.data.detach().float().cpu() for f in frames]).to(dev).contiguous()
+    pose_opt = [(f.index != 0 and update_pose) for f in frames]   # render_helpers.py:346-351
+    for f, po in zip(frames, pose_opt):
+        if po:
+            f.pose.requires_grad_(True)
+    groups = [dict(param=emb, grad=None, lr=learning_rate[0])]
+    if update_decoder:
+        groups += [dict(param=p.data, grad=g, lr=learning_rate[1]) for p, g in zip(bufs.params, bufs.grads)]
+    pose_rows = [i for i, po in enumerate(pose_opt) if po]
+    pose_params = [pose6[i] for i in pose_rows]                    # views into pose6 (contiguous rows)
+    opt = None
+    for it in range(num_iterations):
+        dirs, gt, cos, fid = batch.select(N_rays, dev)
+        eng.rays_from_poses(pose6, dirs, fid)
+        noise = noise_per_iter[it] if noise_per_iter is not None else None
+        seed = 0 if (deterministic or noise is not None) else _seed_from_torch()
+        eng.forward_backward(m, bufs, dirs.shape[0], cfg, gt, cos, dir_local=dirs, ray_frame=fid, n_frames=F, noise=noise,
+                             rng_seed=seed, update_decoder=update_decoder, update_emb=True, update_pose=any(pose_opt), pose6=pose6)
+        if opt is None:
+            groups[0]["grad"] = eng.grad_emb
+            pg = [dict(param=pose_params[k], grad=eng.pose_grad[i], lr=learning_rate[2]) for k, i in enumerate(pose_rows)]
+            opt = FusedAdam(groups + pg)
+        st = eng.read_stats() if (loss_log is not None) else None
+        if st is not None:
+            if st.n_hit_rays <= 0 or (st.error & 1):
+                print("Encouter a bug while Mapping, currently not be fixed, Continue!!")  # render_helpers.py:407-409
+                continue
+            loss_log.append(st.loss)
+        opt.step()
+    with torch.no_grad():
+        host = pose6.cpu()
+        for i, f in enumerate(frames):
+            if pose_opt[i]:
+                f.pose.data.copy_(host[i].to(f.pose.data.device))
+
+
+def track_frame(frame_pose, curr_frame, map_states, sdf_network, loss_criteria, voxel_size, N_rays=512, step_size=0.05,
+                num_iterations=10, truncation=0.1, learning_rate=1e-3, max_voxel_hit=10, max_distance=10, profiler=None,
+                depth_variance=False, deterministic=False, noise_per_iter=None, loss_log=None):
+    """render_helpers.py:428-514: optimise the 6-vector pose of one scan against a frozen map.
+    Returns (OptimizablePose on the GPU, hit_mask bool[N_rays]) or (pose, None) if nothing was hit."""
+    dev = torch.device("cuda")
+    m = map_states if isinstance(map_states, MapState) else MapState.from_map_states(map_states, dev)
+    cfg = _cfg(step_size, voxel_size, max_distance, loss_criteria)
+    bufs = DecoderBuffers(sdf_network, dev)
+    init_pose = deepcopy(frame_pose).cuda()
+    init_pose.requires_grad_(True)
+    pose6 = init_pose.data.detach().reshape(1, 6).contiguous()     # shares storage with the parameter
+    lr = learning_rate * 2 if curr_frame.index < 2 else learning_rate / 3   # render_helpers.py:448-450
+    eng = _engine(N_rays, N_rays * 64, dev)
+    batch = _FrameBatch([curr_frame], dev)
+    opt = None
+    hit_mask = None
+    for it in range(num_iterations):
+        dirs, gt, cos, fid = batch.select(N_rays, dev, track=True)
+        eng.rays_from_poses(pose6, dirs, None)
+        noise = noise_per_iter[it] if noise_per_iter is not None else None
+        seed = 0 if (deterministic or noise is not None) else _seed_from_torch()
+        eng.forward_backward(m, bufs, dirs.shape[0], cfg, gt, cos, dir_local=dirs, ray_frame=None, n_frames=1, noise=noise,
+                             rng_seed=seed, update_decoder=False, update_emb=False, update_pose=True, pose6=pose6)
+        st = eng.read_stats()   # the reference syncs here too (hit_mask, None checks)
+        if st.n_hit_rays <= 0 or (st.error & 1) or st.n_samples == 0:
+            print("Encouter a bug while Tracking, currently not be fixed, Restarting!!")  # render_helpers.py:488-491
+            hit_mask = None
+            break
+        hit_mask = (eng.hit_rank[:dirs.shape[0]] >= 0).clone()
+        if loss_log is not None:
+            loss_log.append(st.loss)
+        if opt is None:
+            opt = FusedAdam([dict(param=pose6[0], grad=eng.pose_grad[0], lr=lr)])
+        opt.step()
+    return init_pose, hit_mask

@@ -1,0 +1,208 @@
+"""GPU parity tests of the individual C-ABI ops against the oracle, the golden vectors produced by the
+executed reference, and (when oracle/_ref/grid was built) the compiled unmodified reference kernels."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from util import bf16_from_bits, golden, product_map, ref_grid, load_decoder
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def nl():
+    import nerfloam_b200 as nl
+    assert torch.cuda.is_available()
+    return nl
+
+
+@pytest.fixture(scope="module")
+def scene(nl):
+    z = golden("render.npz")
+    m = product_map(z["vox"], float(z["voxel_size"]), z["id2emb"], z["emb_bf16"])
+    return z, m
+
+
+def canon_ties(idx, mn, mx):
+    """Order hits with bit-identical min_depth canonically (the tie order is unspecified in the reference)."""
+    key = np.lexsort((idx, mn), axis=-1) if False else None
+    out_i, out_a, out_b = idx.copy(), mn.copy(), mx.copy()
+    for r in range(idx.shape[0]):
+        o = np.lexsort((idx[r], mn[r]))
+        out_i[r], out_a[r], out_b[r] = idx[r][o], mn[r][o], mx[r][o]
+    return out_i, out_a, out_b
+
+
+def test_svo_intersect_vs_oracle_and_reference(nl, scene):
+    from oracle import kernels as OK
+    z, m = scene
+    vs = float(z["voxel_size"])
+    ro = torch.from_numpy(z["rays_o"]).cuda()[None].contiguous()
+    rd = torch.from_numpy(z["rays_d"]).cuda()[None].contiguous()
+    pts = m["centres"].cuda()[None].contiguous()
+    ch = m["structure"].cuda()[None].contiguous()
+    idx, mn, mx = nl.grid.svo_intersect(ro, rd, pts, ch, vs, 20)
+    oi, omn, omx = OK.svo_intersect(z["rays_o"], z["rays_d"], m["centres"].numpy(), m["structure"].numpy(), vs, 20)
+    assert np.array_equal(idx[0].cpu().numpy(), oi)                     # voxel ids: bit-exact, DFS order
+    np.testing.assert_allclose(mn[0].cpu().numpy(), omn, rtol=2e-6, atol=1e-6)   # __fdividef vs 1.0f/x
+    np.testing.assert_allclose(mx[0].cpu().numpy(), omx, rtol=2e-6, atol=1e-6)
+    g = ref_grid()
+    if g is not None:                                                   # the real reference kernel, same GPU
+        G = 4                                                           # its wrapper batches rays and replicates the octree
+        K = ro.shape[1] // G
+        rs = ro[:, :G * K].reshape(G, K, 3).contiguous()
+        rdd = rd[:, :G * K].reshape(G, K, 3).contiguous()
+        ri, rmn, rmx = g.svo_intersect(rs, rdd, pts.expand(G, -1, -1).contiguous(), ch.expand(G, -1, -1).contiguous(), vs, 20)
+        mi, mmn, mmx = nl.grid.svo_intersect(rs, rdd, pts.expand(G, -1, -1).contiguous(), ch.expand(G, -1, -1).contiguous(), vs, 20)
+        assert torch.equal(ri, mi) and torch.equal(rmn, mmn) and torch.equal(rmx, mmx)   # bit-exact incl. depths
+
+
+def test_inverse_cdf_sampling_vs_oracle_and_reference(nl, scene):
+    from oracle import kernels as OK
+    z, m = scene
+    hits = z["hits"]
+    P = z["hit_idx"].shape[1]
+    idx = z["hit_idx"][hits]; mn = z["hit_min"][hits]; mx = z["hit_max"][hits]
+    d = (mx - mn).astype(np.float32); d[idx == -1] = 0
+    tot = OK.seq_sum(d)
+    probs = (d / tot[:, None]).astype(np.float32)
+    steps = (tot / np.float32(z["step"])).astype(np.float32)
+    N = idx.shape[0]
+    Gb = 200
+    H = int(np.ceil(N / Gb)) * Gb
+    pad = lambda a: np.concatenate([a, np.broadcast_to(a[:1], (H - N,) + a.shape[1:])], 0)
+    I, A, B, PR, ST = [pad(a) for a in (idx, mn, mx, probs, steps)]
+    S = int(np.ceil(ST).max()) + P
+    rng = np.random.default_rng(0)
+    noise = rng.uniform(0.001, 0.999, size=(Gb, H // Gb, S)).astype(np.float32)
+    shp = (Gb, H // Gb, P)
+    t = lambda a, s: torch.from_numpy(np.ascontiguousarray(a.reshape(s))).cuda()
+    args = (t(I, shp), t(A, shp), t(B, shp), torch.from_numpy(noise).cuda(), t(PR, shp), t(ST, (Gb, H // Gb)))
+    si, sd, sl = nl.grid.inverse_cdf_sampling(*args, -1.0)
+    oi = np.empty((Gb, H // Gb, S), np.int32); od = np.empty_like(oi, dtype=np.float32); ol = np.empty_like(od)
+    a = [np.ascontiguousarray(x.cpu().numpy()) for x in args]
+    OK.lib().nlo_inverse_cdf_sampling(Gb, H // Gb, P, S, -1.0, OK._p(a[0]), OK._p(a[1]), OK._p(a[2]), OK._p(a[3]), OK._p(a[4]),
+                                      OK._p(a[5]), OK._p(oi), OK._p(od), OK._p(ol))
+    assert np.array_equal(si.cpu().numpy(), oi)
+    assert np.array_equal(sd.cpu().numpy(), od) and np.array_equal(sl.cpu().numpy(), ol)   # same fp ops incl. the FMA
+    g = ref_grid()
+    if g is not None:
+        ri, rd_, rl = g.inverse_cdf_sampling(*args, -1.0)
+        assert torch.equal(ri, si) and torch.equal(rd_, sd) and torch.equal(rl, sl)
+
+
+def test_reference_grid_pins_the_oracle(nl, scene):
+    """The oracle's C restatement of the two CUDA kernels against the compiled reference itself."""
+    g = ref_grid()
+    if g is None:
+        pytest.skip("oracle/_ref/grid not built")
+    from oracle import kernels as OK
+    z, m = scene
+    vs = float(z["voxel_size"])
+    ro = torch.from_numpy(z["rays_o"]).cuda()[None].contiguous()
+    rd = torch.from_numpy(z["rays_d"]).cuda()[None].contiguous()
+    ri, rmn, rmx = g.svo_intersect(ro, rd, m["centres"].cuda()[None].contiguous(), m["structure"].cuda()[None].contiguous(), vs, 20)
+    oi, omn, omx = OK.svo_intersect(z["rays_o"], z["rays_d"], m["centres"].numpy(), m["structure"].numpy(), vs, 20)
+    assert np.array_equal(ri[0].cpu().numpy(), oi)
+    np.testing.assert_allclose(rmn[0].cpu().numpy(), omn, rtol=2e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("width", [256, 32])
+def test_gather_and_mlp_vs_reference_golden(nl, width):
+    """get_embeddings + Decoder forward/backward (reference Python, executed on CPU) vs the CUDA kernels."""
+    z = golden("chain.npz")
+    M = z["xyz"].shape[0]
+    vs = float(z["voxel_size"])
+    dev = "cuda"
+    # every sample gets its own voxel with its own 8 rows: table [M*8,16], vox2row[m] = 8m..8m+7
+    emb = bf16_from_bits(z["feats_bf16"]).reshape(M * 8, 16).to(dev).contiguous()
+    vox = torch.arange(M, dtype=torch.int32, device=dev)
+    vox2row = torch.arange(M * 8, dtype=torch.int32, device=dev).reshape(M, 8).contiguous()
+    centres = torch.from_numpy(z["centre"]).to(dev).contiguous()
+    xyz = torch.from_numpy(z["xyz"]).to(dev).contiguous()
+    feats = torch.empty((M, 16), dtype=torch.float32, device=dev)
+    lib, cap = nl._capi.lib(), nl._capi
+    cap.check(lib.nl_gather_trilinear_fwd(M, None, cap.ptr(xyz), cap.ptr(vox), cap.ptr(centres), cap.ptr(vox2row), cap.ptr(emb), vs,
+                                          cap.ptr(feats), cap.stream_ptr()))
+    np.testing.assert_allclose(feats.cpu().numpy(), z[f"w{width}_emb"], atol=1e-7, rtol=1e-6)
+
+    dec = load_decoder(z, f"w{width}_p_", dev, width)
+    x = feats.clone().requires_grad_()
+    sdf = dec(x)["sdf"]
+    np.testing.assert_allclose(sdf.detach().cpu().numpy(), z[f"w{width}_sdf"], atol=1e-5)      # north-star tolerance
+    gout = torch.from_numpy(z[f"w{width}_gout"]).to(dev)
+    (sdf * gout).sum().backward()
+    for k, p in dec.state_dict(keep_vars=True).items():
+        ref = z[f"w{width}_g_{k}"]
+        np.testing.assert_allclose(p.grad.cpu().numpy(), ref, atol=1e-4 * max(1.0, np.abs(ref).max()), rtol=1e-4)
+    # gather backward: d feats -> rows (bf16-rounded like autograd) and d xyz
+    grad_emb = torch.zeros((M * 8, 16), dtype=torch.float32, device=dev)
+    dxyz = torch.empty((M, 3), dtype=torch.float32, device=dev)
+    dfe = x.grad.contiguous()
+    cap.check(lib.nl_gather_trilinear_bwd(M, None, cap.ptr(xyz), cap.ptr(vox), cap.ptr(centres), cap.ptr(vox2row), cap.ptr(emb), vs,
+                                          cap.ptr(dfe), 1, cap.ptr(grad_emb), cap.ptr(dxyz), None, None, None, None, 0, None,
+                                          cap.stream_ptr()))
+    ref_df = z[f"w{width}_dfeats"].reshape(M * 8, 16)
+    got = grad_emb.cpu().numpy()
+    # bf16 rounding of each contribution: equal up to one bf16 ulp where the fp32 product sat on a rounding boundary
+    assert np.mean(np.abs(got - ref_df) > 1e-2 * np.abs(ref_df) + 1e-9) < 2e-3
+    ref_dx = z[f"w{width}_dxyz"]
+    np.testing.assert_allclose(dxyz.cpu().numpy(), ref_dx, atol=2e-4 * np.abs(ref_dx).max(), rtol=1e-3)
+
+
+def test_pose_kernels_vs_reference_golden(nl):
+    z = golden("pose.npz")
+    dev = "cuda"
+    lib, cap = nl._capi.lib(), nl._capi
+    datas = torch.from_numpy(np.concatenate([z["data"][None], z["datas"]])).float().to(dev).contiguous()
+    F = datas.shape[0]
+    Rt = torch.empty((F, 12), dtype=torch.float32, device=dev)
+    cap.check(lib.nl_pose_matrices(F, cap.ptr(datas), cap.ptr(Rt), cap.stream_ptr()))
+    Rk = Rt[:, :9].reshape(F, 3, 3).cpu().numpy()
+    np.testing.assert_allclose(Rk[0], z["R"], atol=2e-6)
+    np.testing.assert_allclose(Rk[1:], z["Rs"], atol=2e-6)
+    np.testing.assert_allclose(Rt[:, 9:].cpu().numpy(), datas[:, :3].cpu().numpy())
+    # Jacobian: d (sum R*G) / d w  via acc = (dL/dt = 0, dL/dR = G)
+    acc = torch.zeros((F, 12), dtype=torch.float32, device=dev)
+    acc[:, 3:] = torch.from_numpy(z["G"]).reshape(1, 9).to(dev)
+    acc[0, :3] = torch.from_numpy(z["gt"]).to(dev)
+    g6 = torch.empty((F, 6), dtype=torch.float32, device=dev)
+    cap.check(lib.nl_pose_grad(F, cap.ptr(datas), cap.ptr(acc), cap.ptr(g6), cap.stream_ptr()))
+    np.testing.assert_allclose(g6[0].cpu().numpy(), z["grad"], atol=2e-5, rtol=1e-4)
+    np.testing.assert_allclose(g6[1:, 3:].cpu().numpy(), z["grads"][:, 3:], atol=5e-5, rtol=2e-4)
+    # the reference's own self-check (se3pose.py:95-105): from_matrix -> matrix round trip
+    P = nl.se3pose.OptimizablePose.from_matrix(torch.from_numpy(z["before"]))
+    np.testing.assert_allclose(P.matrix().detach().numpy()[:3, 3], z["before"][:3, 3], atol=1e-6)
+    np.testing.assert_allclose(P.data.detach().numpy(), z["data"], atol=1e-6)
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_fused_adam_vs_torch(nl, dtype):
+    torch.manual_seed(0)
+    dev = "cuda"
+    n = 4096 * 16 + 7
+    p0 = torch.randn(n, device=dev) * 0.05
+    if dtype == "bf16":
+        p0 = p0.to(torch.bfloat16)
+    p_ref = p0.clone().requires_grad_()
+    p_my = p0.clone()
+    opt_ref = torch.optim.Adam([p_ref], lr=0.01)
+    g32 = torch.zeros(n, dtype=torch.float32, device=dev)
+    opt_my = nl.engine.FusedAdam([dict(param=p_my, grad=g32, lr=0.01)])
+    for step in range(4):
+        g = torch.randn(n, device=dev) * (10.0 ** (-step))
+        if step == 2:
+            g[::3] = 0
+        p_ref.grad = g.to(p_ref.dtype)
+        g32.copy_(g)
+        opt_ref.step()
+        opt_my.step()
+        a, b = p_my.float().cpu().numpy(), p_ref.detach().float().cpu().numpy()
+        if dtype == "f32":
+            np.testing.assert_allclose(a, b, rtol=2e-6, atol=1e-8)
+        else:   # same rounding points: identical up to rare 1-ulp flips from reciprocal-vs-division inside torch
+            assert np.mean(a != b) < 2e-2
+            np.testing.assert_allclose(a, b, rtol=1e-2, atol=1e-4)

@@ -1,0 +1,252 @@
+"""GPU parity tests of the fused pipeline (render_rays / bundle_adjust_frames / track_frame) against the
+golden vectors produced by executing the reference's own Python (tests/golden/make_golden.py), and
+full-size (100k-ray scan) checks against the oracle and through size-independent properties."""
+import numpy as np
+import pytest
+import torch
+
+from util import Args, bf16_from_bits, golden, load_decoder, product_map
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def nl():
+    import nerfloam_b200 as nl
+    assert torch.cuda.is_available()
+    return nl
+
+
+def test_render_rays_vs_reference_golden(nl):
+    z = golden("render.npz")
+    vs, md, step = float(z["voxel_size"]), float(z["max_distance"]), float(z["step"])
+    m = product_map(z["vox"], vs, z["id2emb"], z["emb_bf16"])["state"]
+    dec = load_decoder(z, "dec_")
+    ro = torch.from_numpy(z["rays_o"]).cuda()[None]
+    rd = torch.from_numpy(z["rays_d"]).cuda()[None]
+    noise = torch.from_numpy(z["noise"]).reshape(-1, z["noise"].shape[-1]).cuda().contiguous()
+    out = nl.render_helpers.render_rays(ro, rd, m, dec, step, vs, 0.3, 20, md, chunk_size=-1, noise=noise)
+    assert out is not None
+    assert np.array_equal(out["ray_mask"].cpu().numpy(), z["out_ray_mask"])
+    assert out["z_vals"].shape == z["out_z"].shape
+    assert np.array_equal(out["valid_mask"].cpu().numpy(), z["out_valid"])       # same samples in the same cells
+    np.testing.assert_allclose(out["z_vals"].cpu().numpy(), z["out_z"], rtol=2e-6)
+    np.testing.assert_allclose(out["sdf"].detach().cpu().numpy(), z["out_sdf"], atol=1e-5)   # north-star: 1e-5 fp32
+    # sampled voxel ids: bit-exact (compact list == row-major valid cells of the reference's padded matrix)
+    eng = nl.render_helpers._engine(ro.shape[1], ro.shape[1] * 40, ro.device)
+    M = int(z["out_valid"].sum())
+    assert np.array_equal(eng.s_vox[:M].cpu().numpy(), z["s_idx"][z["s_idx"] != -1])
+    # deterministic sampling (noise = 0.5)
+    out_d = nl.render_helpers.render_rays(ro, rd, m, dec, step, vs, 0.3, 20, md, chunk_size=-1, deterministic=True)
+    assert np.array_equal(out_d["valid_mask"].cpu().numpy(), z["sd_idx"] != -1)
+    np.testing.assert_allclose(out_d["z_vals"].cpu().numpy(), z["sd_depth"], rtol=2e-6)
+
+
+def test_render_rays_autograd_matches_fused_backward(nl):
+    """Drop-in path (render_rays + Criterion.forward + autograd) and the fused forward_backward give the same
+    loss and gradients."""
+    z = golden("render.npz")
+    vs, md, step = float(z["voxel_size"]), float(z["max_distance"]), float(z["step"])
+    m = product_map(z["vox"], vs, z["id2emb"], z["emb_bf16"])["state"]
+    dec = load_decoder(z, "dec_")
+    crit = nl.criterion.Criterion(Args())
+    pts = torch.from_numpy(z["pts"]).cuda()
+    cos = torch.from_numpy(z["cos"]).cuda()
+    ro = torch.from_numpy(z["rays_o"]).cuda()
+    rd = torch.from_numpy(z["rays_d"]).cuda()
+    ms = m
+    out = nl.render_helpers.render_rays(ro[None], rd[None], ms, dec, step, vs, 0.3, 20, md, deterministic=True)
+    loss, _ = crit(out, pts[None], cos[None, :, None])
+    loss.backward()
+    g_dec = [p.grad.clone() for p in dec.parameters()]
+    # fused path
+    bufs = nl.engine.DecoderBuffers(dec, ro.device)
+    eng = nl.engine.SDFEngine(ro.shape[0], ro.shape[0] * 40)
+    cfg = dict(step_size=step, voxel_size=vs, max_distance=md, **crit.kernel_config())
+    gt = torch.norm(pts, 2, -1) * cos
+    eng.forward_backward(ms, bufs, ro.shape[0], cfg, gt, cos, ray_o=ro, ray_d=rd, update_decoder=True, update_emb=True,
+                         update_pose=False)
+    st = eng.read_stats()
+    np.testing.assert_allclose(st.loss, float(loss), rtol=2e-5)
+    for a, b in zip(bufs.grads, g_dec):
+        np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=2e-3, atol=2e-5 * float(b.abs().max()))
+
+
+class _Replay:
+    """Mixin: replay the ray-selection masks recorded from the reference run."""
+
+    def set_masks(self, masks):
+        self._masks = [torch.from_numpy(mk.astype(bool)).view(-1, 1) for mk in masks]
+
+    def sample_rays(self, N_rays, track=False):
+        self.sample_mask = self._masks.pop(0)
+        assert int(self.sample_mask.sum()) == N_rays
+
+
+def _frames(nl, z, name, n_it, scans=(0, 1, 2)):
+    class F(_Replay, nl.frame.LidarFrame):
+        pass
+    frames = []
+    for i in scans:
+        pts = torch.from_numpy(z[f"scan{i}_pts"])
+        pose = nl.se3pose.OptimizablePose(torch.from_numpy(z[f"{name}_pose0"][i].copy()))
+        f = F(i, pts, torch.from_numpy(z[f"scan{i}_cos"]), pose, new_keyframe=True)
+        f.set_masks([np.unpackbits(z[f"{name}_mask_it{it}_f{i}"])[:pts.shape[0]] for it in range(n_it)])
+        frames.append(f)
+    return frames
+
+
+@pytest.mark.parametrize("name,upd_dec", [("map", True), ("mapfrozen", False)])
+def test_bundle_adjust_frames_vs_reference_run(nl, name, upd_dec):
+    """3 iterations of the mapping loop (same rays, same sampling noise): per-iteration loss and the
+    embeddings / decoder / poses after Adam, against the executed reference."""
+    z = golden("mapping_tracking.npz")
+    vs, md = float(z["voxel_size"]), float(z["max_distance"])
+    m = product_map(z["vox"], vs, z["id2emb"], z["emb_bf16"])["state"]
+    emb = m.emb.clone()
+    dec = load_decoder(z, f"{name}_dec0_")
+    frames = _frames(nl, z, name, 3)
+    noise = [torch.from_numpy(z[f"{name}_noise{i}"]).reshape(-1, z[f"{name}_noise{i}"].shape[-1]).cuda().contiguous() for i in range(3)]
+    losses = []
+    nl.render_helpers.bundle_adjust_frames(frames, emb, m, dec, nl.criterion.Criterion(Args()), vs, 0.5 * vs, N_rays=256,
+                                           num_iterations=3, truncation=0.3, max_voxel_hit=20, max_distance=md,
+                                           learning_rate=[0.01, 0.005, 0.001], update_pose=True, update_decoder=upd_dec,
+                                           noise_per_iter=noise, loss_log=losses)
+    np.testing.assert_allclose(losses, z[f"{name}_loss"], rtol=3e-4)
+    poses = np.stack([f.pose.data.detach().cpu().numpy() for f in frames])
+    np.testing.assert_allclose(poses, z[f"{name}_pose_after"], atol=5e-5)
+    np.testing.assert_array_equal(poses[0], z[f"{name}_pose0"][0])              # frame index 0 is frozen
+    e_ref = bf16_from_bits(z[f"{name}_emb_after_bf16"]).float().numpy()
+    e = emb.float().cpu().numpy()
+    assert np.mean(np.abs(e - e_ref) > 2e-3) < 5e-3
+    assert np.abs(e - bf16_from_bits(z["emb_bf16"]).float().numpy()).max() > 1e-3   # it did move
+    for k, v in dec.state_dict().items():
+        ref = z[f"{name}_dec_after_{k}"]
+        if upd_dec:
+            np.testing.assert_allclose(v.cpu().numpy(), ref, atol=3e-4)
+        else:
+            np.testing.assert_array_equal(v.cpu().numpy(), z[f"{name}_dec0_{k}"])
+
+
+def test_track_frame_vs_reference_run(nl):
+    z = golden("mapping_tracking.npz")
+    vs, md = float(z["voxel_size"]), float(z["max_distance"])
+    m = product_map(z["vox"], vs, z["id2emb"], z["emb_bf16"])["state"]
+    dec = load_decoder(z, "map_dec0_")
+
+    class F(_Replay, nl.frame.LidarFrame):
+        pass
+    pts = torch.from_numpy(z["scan1_pts"])
+    pose = nl.se3pose.OptimizablePose(torch.from_numpy(z["track_pose0"].copy()))
+    f = F(1, pts, torch.from_numpy(z["scan1_cos"]), pose, new_keyframe=True)
+    f.set_masks([np.unpackbits(z["track_masks"][it])[:pts.shape[0]] for it in range(3)])
+    noise = [torch.from_numpy(z[f"track_noise{i}"]).reshape(-1, z[f"track_noise{i}"].shape[-1]).cuda().contiguous() for i in range(3)]
+    losses = []
+    pose_out, hit = nl.render_helpers.track_frame(pose, f, m, dec, nl.criterion.Criterion(Args()), vs, N_rays=256,
+                                                  step_size=0.2 * vs, num_iterations=3, truncation=0.3, learning_rate=0.06,
+                                                  max_voxel_hit=20, max_distance=md, noise_per_iter=noise, loss_log=losses)
+    np.testing.assert_allclose(losses[0], z["track_loss"][0], rtol=3e-4)
+    np.testing.assert_allclose(losses, z["track_loss"], rtol=5e-3)
+    np.testing.assert_allclose(pose_out.data.detach().cpu().numpy(), z["track_pose_after"], atol=2e-3)
+    assert np.array_equal(hit.cpu().numpy(), z["track_hit_mask"])
+    np.testing.assert_array_equal(pose.data.detach().numpy(), z["track_pose0"])   # the input pose object is not modified
+
+
+# ------------------------------------------------------------------------------------------------
+# full-size scan (BASELINE.json north star: 100k-point KITTI-shape scan)
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def fullscan(nl):
+    syn = nl.synthetic
+    pts, cos, pose = syn.make_scan()
+    mu = nl.mapping.MapUpdater(0.3, init_std=0.01, seed=1)
+    ms = mu.insert_voxels(torch.from_numpy(syn.voxelize(pts, pose, 0.3)))
+    torch.manual_seed(777)
+    dec = nl.lidar.Decoder(depth=2, width=256, in_dim=16, skips=[], embedder="none", multires=0).cuda()
+    P = torch.from_numpy(pts).cuda()
+    dirs = (P / (P.norm(dim=-1, keepdim=True) + 1e-8)).contiguous()
+    cosd = torch.from_numpy(cos).cuda()
+    gt = torch.norm(P, 2, -1) * cosd
+    pose6 = nl.se3pose.OptimizablePose.from_matrix(torch.from_numpy(pose)).data.detach().reshape(1, 6).cuda().contiguous()
+    cfg = dict(step_size=0.15, voxel_size=0.3, max_distance=40.0, truncation=0.3, max_depth=40.0, fs_weight=1.0, sdf_weight=10000.0)
+    return dict(ms=ms, mu=mu, dec=dec, dirs=dirs, cos=cosd, gt=gt, pose6=pose6, cfg=cfg, pts=pts, cosn=cos, pose=pose)
+
+
+def test_fullsize_properties(nl, fullscan):
+    s = fullscan
+    R = s["dirs"].shape[0]
+    eng = nl.engine.SDFEngine(R, R * 24)
+    bufs = nl.engine.DecoderBuffers(s["dec"], s["dirs"].device)
+
+    def run():
+        eng.rays_from_poses(s["pose6"], s["dirs"], None)
+        eng.forward_backward(s["ms"], bufs, R, s["cfg"], s["gt"], s["cos"], dir_local=s["dirs"], ray_frame=None, n_frames=1,
+                             update_decoder=True, update_emb=True, update_pose=True, pose6=s["pose6"])
+        return eng.read_stats()
+    st = run()
+    assert st.error == 0 and st.n_hit_rays > 0.95 * R
+    M = st.n_samples
+    nsamp = eng.ray_nsamp[:R].long()
+    off = eng.ray_offset[:R].long()
+    assert int(nsamp.sum()) == M and int(nsamp.max()) == st.max_samples
+    assert torch.equal(off, torch.cumsum(nsamp, 0) - nsamp)                                 # exclusive scan
+    assert bool(((nsamp > 0) <= (eng.hit_rank[:R] >= 0)).all())                             # samples only on hit rays
+    ray = eng.s_ray[:M].long()
+    assert bool((ray[1:] >= ray[:-1]).all())                                                # row-major (ray, step) order
+    d = eng.s_depth[:M]
+    same = ray[1:] == ray[:-1]
+    assert bool((d[1:][same] >= d[:-1][same]).all())                                        # depths ascend along a ray
+    c = s["ms"].centres[eng.s_vox[:M].long()]
+    assert float((eng.s_xyz[:M] - c).abs().max()) <= 0.15 + 2e-3                            # every sample inside its voxel
+    assert bool(torch.isfinite(eng.sdf[:M]).all()) and bool(torch.isfinite(eng.grad_emb).all())
+    rows = s["ms"].vox2row[eng.s_vox[:M].long()].reshape(-1).long()
+    touched = torch.zeros(eng.grad_emb.shape[0], dtype=torch.bool, device=rows.device)
+    touched[rows] = True
+    assert float(eng.grad_emb[~touched].abs().max()) == 0.0                                 # gradient only where gathered
+    # determinism of everything integer + loss reproducibility (float atomics reorder only)
+    vox1, dep1, loss1 = eng.s_vox[:M].clone(), d.clone(), st.loss
+    st2 = run()
+    assert st2.n_samples == M and torch.equal(eng.s_vox[:M], vox1) and torch.equal(eng.s_depth[:M], dep1)
+    np.testing.assert_allclose(st2.loss, loss1, rtol=1e-6)
+    # linearity of the gather in the embedding table: f(2E) = 2 f(E)
+    f1 = eng.feats[:M].clone()
+    ms2 = nl.engine.MapState(s["ms"].centres, s["ms"].structure, s["ms"].vox2row, (s["ms"].emb.float() * 2).to(torch.bfloat16))
+    eng._vs = 0.3
+    eng.gather_forward(ms2)
+    torch.testing.assert_close(eng.feats[:M], 2 * f1, rtol=1e-6, atol=1e-7)
+
+
+def test_fullsize_loss_and_ids_vs_oracle(nl, fullscan):
+    """Whole 82k-ray scan through the oracle (C traversal/sampler + torch fp32 chain, ~20 s of CPU) vs the kernels."""
+    from oracle import chain as OC
+    s = fullscan
+    R = s["dirs"].shape[0]
+    eng = nl.engine.SDFEngine(R, R * 24)
+    bufs = nl.engine.DecoderBuffers(s["dec"], s["dirs"].device)
+    eng.rays_from_poses(s["pose6"], s["dirs"], None)
+    ro, rd = eng.ray_o[:R].clone(), eng.ray_d[:R].clone()
+    eng.forward_backward(s["ms"], bufs, R, s["cfg"], s["gt"], s["cos"], ray_o=ro, ray_d=rd, update_decoder=False,
+                         update_emb=True, update_pose=False)
+    st = eng.read_stats()
+    M = st.n_samples
+    ms = s["ms"]
+    map_np = {"centres": ms.centres.cpu().numpy(), "structure": ms.structure.cpu().numpy(),
+              "vertex_rows": ms.vox2row.cpu().numpy().astype(np.int64)}
+    dec_o = OC.Decoder(depth=2, width=256, in_dim=16)
+    dec_o.load_state_dict({k: v.cpu() for k, v in s["dec"].state_dict().items()})
+    emb_o = ms.emb.cpu().float().requires_grad_()     # fp32 leaf: autograd accumulates the scatter in fp32
+    out = OC.render_rays(ro.cpu(), rd.cpu(), map_np, emb_o, dec_o, 0.15, 0.3, 40.0, deterministic=True)
+    assert int(out["valid_mask"].sum()) == M and st.n_hit_rays == int(out["ray_mask"].sum()) and st.max_samples == out["z_vals"].shape[1]
+    assert np.array_equal(eng.s_vox[:M].cpu().numpy(), out["sampled_idx"][out["valid_mask"]].numpy())     # bit-exact ids
+    np.testing.assert_allclose(eng.s_depth[:M].cpu().numpy(), out["z_vals"][out["valid_mask"]].numpy(), rtol=3e-6)
+    np.testing.assert_allclose(eng.sdf[:M].cpu().numpy(), out["sdf_valid"].detach().numpy(), atol=1e-5)
+    mask = out["ray_mask"]
+    loss, parts = OC.sdf_loss(out["z_vals"], out["sdf"], out["valid_mask"], torch.from_numpy(s["pts"])[mask],
+                              torch.from_numpy(s["cosn"])[mask], 0.3, 40.0, 1.0, 10000.0)
+    np.testing.assert_allclose(st.loss, float(loss), rtol=1e-4)
+    assert abs(st.n_fs - float(parts["n_fs"])) <= 2 and abs(st.n_sdf - float(parts["n_sdf"])) <= 2
+    loss.backward()
+    g_ref = emb_o.grad.float().numpy()
+    g = eng.grad_emb.cpu().numpy()
+    scale = np.abs(g_ref).max()
+    assert np.mean(np.abs(g - g_ref) > 1e-2 * np.abs(g_ref) + 1e-3 * scale) < 1e-3        # per-contribution bf16 rounding only
