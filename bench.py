@@ -216,8 +216,8 @@ def run_ours(args):
         "stage_ms": {"traverse_sample": t_smp, "gather_fwd": t_gf, "mlp_fwd_bwd": t_mlp, "gather_bwd": t_gb},
         "clocks": clk,
     }
-    if world == 1:
-        out["cpu_baseline"] = cpu_baseline(n_rays=4096, iters=3)
+    if world == 1 and not os.environ.get("NL_BENCH_SKIP_CPU"):
+        out["cpu_baseline"] = best_cpu_baseline(n_rays=4096, iters=3)
     print(json.dumps(out))
 
 
@@ -228,8 +228,9 @@ def cpu_baseline(n_rays=4096, iters=3, threads=None):
     from oracle import kernels as OK
     import importlib
     syn = importlib.import_module("nerf-loam_b200.synthetic")
-    threads = threads or os.cpu_count()
-    torch.set_num_threads(threads)
+    if threads is None:
+        threads = int(os.environ.get("NL_CPU_THREADS", 0)) or min(os.cpu_count(), 32)   # eager PyTorch stops scaling (and then
+    torch.set_num_threads(threads)                                                      # regresses) beyond a few dozen threads
     pts, cos, pose = syn.make_scan(seed=777)
     o = OK.Octree(); o.init(256 * 256 * 4, 16, CFG["voxel_size"])
     o.insert(syn.voxelize(pts, pose, CFG["voxel_size"]))
@@ -264,13 +265,27 @@ def cpu_baseline(n_rays=4096, iters=3, threads=None):
             "ms_per_iter": float(np.median(times)) * 1e3}
 
 
+def best_cpu_baseline(n_rays, iters):
+    """Pick the thread count at which the host path is fastest (a fair baseline: eager PyTorch on 128 threads is
+    ~100x slower than on 16) and report that run; `cores` is the thread count actually used."""
+    best = None
+    for th in sorted({min(os.cpu_count(), t) for t in (8, 16, 32)}):
+        cb = cpu_baseline(n_rays=n_rays, iters=1, threads=th)
+        if best is None or cb["value"] > best["value"]:
+            best = cb
+    full = cpu_baseline(n_rays=n_rays, iters=iters, threads=best["cores"])
+    full["sample"] += f"; thread count chosen as the fastest of 8/16/32 on a {os.cpu_count()}-CPU host"
+    return full
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
     n_rays = 8192
     t0 = time.perf_counter()
-    cb = cpu_baseline(n_rays=n_rays, iters=max(1, args.steps), threads=os.cpu_count())
+    probe = best_cpu_baseline(n_rays=2048, iters=1)
+    cb = cpu_baseline(n_rays=n_rays, iters=max(1, args.steps), threads=probe["cores"])
     out = {"impl": "reference", "metric": "neural-SDF samples/sec per mapping iter", "value": cb["value"], "unit": "samples/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": 1, "ms_per_step": cb["ms_per_iter"], "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

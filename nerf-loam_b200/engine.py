@@ -125,28 +125,12 @@ class SDFEngine:
         self.pose_grad = None
         self._stats_host = torch.empty(STATS_BYTES, dtype=torch.uint8).pin_memory() if torch.cuda.is_available() else None
         self.events = None            # set to {} to record CUDA events around the main kernels (bench.py)
-        # typed views of the stats block for collectives (multi-GPU ray sharding)
-        self._st_i32 = self.stats.view(torch.int32)
-        self._st_i64 = self.stats.view(torch.int64)
-        self._st_f64 = self.stats.view(torch.float64)
 
     def _mark(self, name):
         if self.events is not None:
             ev = torch.cuda.Event(enable_timing=True)
             ev.record()
             self.events.setdefault(name, []).append(ev)
-
-    def allreduce_sample_stats(self, group):
-        """Ray sharding: make the loss-mask counters global (SUM), S_max global (MAX), R_hit global (SUM)."""
-        import torch.distributed as dist
-        dist.all_reduce(self._st_i64[4:10], op=dist.ReduceOp.SUM, group=group)      # cnt_* / pad_* counters
-        dist.all_reduce(self._st_f64[10:12], op=dist.ReduceOp.SUM, group=group)     # pad_sdf_d2, pad_sdf_d2_nsamp
-        dist.all_reduce(self._st_i32[0:1], op=dist.ReduceOp.SUM, group=group)       # n_hit_rays
-        dist.all_reduce(self._st_i32[2:3], op=dist.ReduceOp.MAX, group=group)       # max_samples
-
-    def allreduce_loss_sums(self, group):
-        import torch.distributed as dist
-        dist.all_reduce(self._st_f64[16:18], op=dist.ReduceOp.SUM, group=group)     # fs_sum, sdf_sum
 
     # ------------------------------------------------------------------ helpers
     @property
@@ -235,7 +219,8 @@ class SDFEngine:
         self._mark("t0")
         self.render_samples(m, R, cfg, ray_o, ray_d, gt_depth, cos, noise, rng_seed, reference_compat)
         if group is not None:   # the loss normalisation is global (criterion.py:84-100): one tiny exchange before backward
-            self.allreduce_sample_stats(group)
+            from . import dist as nldist
+            nldist.allreduce_sample_stats(self.stats, group)
             _capi.check(lib.nl_loss_prepare(C.c_void_p(self.stats.data_ptr()), float(cfg["fs_weight"]), float(cfg["sdf_weight"]), st),
                         "nl_loss_prepare")
             _capi.LAUNCHES += 1
@@ -280,15 +265,10 @@ class SDFEngine:
             _capi.LAUNCHES += 1
         self._mark("t_gather_bwd")
         if group is not None:
-            import torch.distributed as dist
-            self.allreduce_loss_sums(group)
-            if update_emb:
-                dist.all_reduce(self.grad_emb, group=group)
-            if update_decoder:
-                for g in dec.grads:
-                    dist.all_reduce(g, group=group)
-            if want_pose:
-                dist.all_reduce(self.pose_acc, group=group)
+            from . import dist as nldist
+            nldist.allreduce_loss_sums(self.stats, group)
+            nldist.allreduce_grads([self.grad_emb if update_emb else None] + (list(dec.grads) if update_decoder else []) +
+                                   [self.pose_acc if want_pose else None], group)
         if want_pose:
             _capi.check(lib.nl_pose_grad(n_frames, _capi.ptr(pose6), _capi.ptr(self.pose_acc), _capi.ptr(self.pose_grad), st),
                         "nl_pose_grad")

@@ -156,14 +156,14 @@ def pose_from_matrix(Rt):
 # a-5  render_rays (render_helpers.py:190-318)
 # ------------------------------------------------------------------------------------------------
 def render_rays(rays_o, rays_d, map_np, emb, decoder, step_size, voxel_size, max_distance, deterministic=True,
-                noise=None):
+                noise=None, raw_hits=None):
     """rays_o/rays_d: torch fp32 [R,3] (may require grad).  map_np: dict of numpy arrays
     centres f32[n,3], structure i32[n,9], vertex_rows i64[n,8].  emb: torch [V,E] (bf16 or fp32).
     Returns dict like the reference (z_vals, sdf, ray_mask, valid_mask, sampled_xyz) plus the raw
     sample tensors, or None."""
     ro = rays_o.detach().numpy().astype(np.float32)
     rd = rays_d.detach().numpy().astype(np.float32)
-    inter, hits = K.ray_intersect(ro, rd, map_np["centres"], map_np["structure"], voxel_size, 20, max_distance)
+    inter, hits = K.ray_intersect(ro, rd, map_np["centres"], map_np["structure"], voxel_size, 20, max_distance, raw=raw_hits)
     if hits.sum() <= 0:
         return None
     inter_h = {k: v[hits] for k, v in inter.items()}

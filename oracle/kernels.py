@@ -105,9 +105,14 @@ def svo_intersect(ray_start, ray_dir, centres, structure, voxel_size, n_max=20):
     return idx, mn, mx
 
 
-def ray_intersect(ray_start, ray_dir, centres, structure, voxel_size, max_hits=None, max_distance=MAX_DEPTH):
-    """voxel_helpers.py:530-567 (max_hits argument is ignored there too: hard-coded 20)."""
-    pts_idx, min_depth, max_depth = svo_intersect(ray_start, ray_dir, centres, structure, voxel_size, 20)
+def ray_intersect(ray_start, ray_dir, centres, structure, voxel_size, max_hits=None, max_distance=MAX_DEPTH, raw=None):
+    """voxel_helpers.py:530-567 (max_hits argument is ignored there too: hard-coded 20).
+    raw: optional precomputed (idx, min_depth, max_depth) [R,20] of svo_intersect (e.g. from the GPU kernel that is
+    itself checked bit-exact against the compiled reference), so that everything downstream sees identical inputs."""
+    if raw is not None:
+        pts_idx, min_depth, max_depth = [np.array(a, copy=True) for a in raw]
+    else:
+        pts_idx, min_depth, max_depth = svo_intersect(ray_start, ray_dir, centres, structure, voxel_size, 20)
     md = np.float32(max_distance)
     min_depth[pts_idx == -1] = md
     max_depth[pts_idx == -1] = md
