@@ -56,9 +56,10 @@ __global__ void __launch_bounds__(128) k_gather_fwd(long long M_host, const int3
         const int rows[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
         uint4 raw[16];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {  // issue all 16 row loads before using any
-            raw[2 * k] = __ldg(emb + (size_t)rows[k] * 2);
-            raw[2 * k + 1] = __ldg(emb + (size_t)rows[k] * 2 + 1);
+        for (int k = 0; k < 8; ++k) {  // issue all 16 row loads before using any; a vertex without a row reads as zeros
+            const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+            raw[2 * k] = rows[k] >= 0 ? __ldg(emb + (size_t)rows[k] * 2) : z4;
+            raw[2 * k + 1] = rows[k] >= 0 ? __ldg(emb + (size_t)rows[k] * 2 + 1) : z4;
         }
         const Tri t = tri_coords(xyz + i * 3, centres + (size_t)v * 3, voxel_size);
         float acc[16];
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__(128) k_gather_bwd(long long M_host, const int3
                 const float ay = (k & 2) ? t.py : __fsub_rn(1.0f, t.py);
                 const float az = (k & 1) ? t.pz : __fsub_rn(1.0f, t.pz);
                 const float w = __fmul_rn(__fmul_rn(ax, ay), az);
+                if (rows[k] < 0) continue;
                 if (grad_emb) {
                     // d(emb row): grad_out * w, rounded to bf16 where autograd casts it for a bf16 table
                     float c[16];

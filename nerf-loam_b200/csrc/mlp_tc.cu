@@ -27,6 +27,8 @@ constexpr int STAGE_A = 2 * PANEL_A;  // hi + lo
 constexpr int STAGE_B = 2 * PANEL_B;
 constexpr int NSTAGE = 2;
 constexpr int STEPS_FWD = 9;          // layer 1 + 8 K-blocks of layer 2
+constexpr int STEPS_TRAIN = 25;       // + 8 K-blocks of backward layer 2 + 8 of backward layer 1
+constexpr int PANEL_B16 = 16 * 128;   // 2 KB: the 16-row panels of backward layer 1
 constexpr int SMEM_DATA = NSTAGE * (STAGE_A + STAGE_B);
 constexpr int SMEM_TOTAL = SMEM_DATA + 4096 + 1024;  // + biases/barriers + alignment slack
 constexpr int NTHREADS = 192;
@@ -104,20 +106,29 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 // ------------------------------------------------------------------------------------------------
 // Weight panels: the exact shared-memory image (K-major, 128B swizzle, tf32 hi then lo) of every weight
 // K-block, laid out contiguously in global memory so one bulk copy fills a ring stage.
-//   stage 0      : W0  [256 x 16]  (row j, k = e; only the first 64 B of each 128 B row are meaningful)
-//   stage 1 + kb : W1[:, 32kb : 32kb+32]
+//   stage 0       : W0  [256 x 16]  (row j, k = e; only the first 64 B of each 128 B row are meaningful)
+//   stage 1 + kb  : W1[:, 32kb : 32kb+32]              forward layer 2
+//   stage 9 + jb  : W1^T[:, 32jb : 32jb+32]            backward layer 2 (d h1 = d h2 . W1)
+//   stage 17 + kb : W0^T[:, 32kb : 32kb+32] (16 rows)  backward layer 1 (d x  = d h1 . W0)
 // ------------------------------------------------------------------------------------------------
 __global__ void k_tc_prepare(const float *__restrict__ W0, const float *__restrict__ W1, uint8_t *__restrict__ panels) {
-    const int stage = blockIdx.y;                         // 0..8
+    const int stage = blockIdx.y;                         // 0..24
     const int t = blockIdx.x * blockDim.x + threadIdx.x;  // (row, chunk)
     if (t >= WN * 8) return;
     const int r = t >> 3, c = t & 7;
     float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (stage == 0) {
+    if (stage == 0) {                                     // layer 1:   B[j][e] = W0[j][e]
         if (c < 4) for (int i = 0; i < 4; ++i) v[i] = W0[r * 16 + c * 4 + i];
-    } else {
+    } else if (stage <= 8) {                              // layer 2:   B[j][k] = W1[j][k],      k in K-block stage-1
         const int k0 = (stage - 1) * 32 + c * 4;
         for (int i = 0; i < 4; ++i) v[i] = W1[(size_t)r * WN + k0 + i];
+    } else if (stage <= 16) {                             // bwd layer 2: B[k][j] = W1[j][k],    j in K-block stage-9
+        const int j0 = (stage - 9) * 32 + c * 4;
+        for (int i = 0; i < 4; ++i) v[i] = W1[(size_t)(j0 + i) * WN + r];
+    } else {                                              // bwd layer 1: B[e][k] = W0[k][e],    k in K-block stage-17 (16 rows)
+        if (r >= 16) return;
+        const int k0 = (stage - 17) * 32 + c * 4;
+        for (int i = 0; i < 4; ++i) v[i] = W0[(size_t)(k0 + i) * 16 + r];
     }
     float hi[4], lo[4];
     for (int i = 0; i < 4; ++i) { hi[i] = tf32_rna(v[i]); lo[i] = tf32_rna(v[i] - hi[i]); }
@@ -304,13 +315,573 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_mlp_tc_fwd(FwdParams p) {
     }
 }
 
+
+// ================================================================================================
+// Training kernel: forward + loss + backward w.r.t. the input features in one pass per 128-sample tile.
+//   steps  0      layer 1            D1 = x . W0^T                      (TMEM cols 0..255)
+//          1..8   layer 2            D2 = relu(D1+b0) . W1^T            (TMEM cols 256..511)
+//                 epilogue: sdf = relu(D2+b1).w2 + b2, loss terms, d loss/d sdf (all thread-local: thread = sample)
+//          9..16  backward layer 2   D3 = dh2 . W1   (reuses D1's columns), dh2 = dsdf * w2 * relu'(h2) built in registers
+//          17..24 backward layer 1   D4 = (D3 * relu'(h1)) . W0  (N = 16, reuses D2's first 16 columns) = d loss / d x
+// ReLU masks are 2 x 256 bits per thread in registers.  With WGRAD the kernel also writes h1, dh2 and dh1 (masked)
+// to HBM in 16 KB "panel" blocks [(tile*8 + kblock)][row][32] (perfectly coalesced: a warp writes 4 KB) for the
+// weight-gradient GEMMs, and reduces gW2 / gb2 itself (32x32 register transpose-reduce per K-block).
+// ================================================================================================
+struct TrainParams {
+    long long M_host;
+    const int32_t *M_dev;
+    const float *feats;
+    const uint8_t *panels;     // 25 stages x 64 KB
+    const float *b0, *b1, *w2, *b2;
+    float *sdf, *dfeats;
+    const uint8_t *s_flag;
+    const float *s_depth;
+    const int32_t *s_ray;
+    const float *cosv, *gt_depth;
+    nl_render_stats *stats;
+    float truncation;
+    const float *dsdf_ext;
+    float *act_h1, *act_dh2, *act_dh1;   // WGRAD: panel-major [ntiles*8][128][32]
+    float *gW2, *gb2;                    // WGRAD
+};
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// split 32 fp32 values of one row into tf32 hi/lo and store them as one 128 B row of the swizzled A panels
+__device__ __forceinline__ void store_a_row(uint8_t *stage, int row, const float (&h)[32]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { hi[i] = tf32_rna(h[c * 4 + i]); lo[i] = tf32_rna(h[c * 4 + i] - hi[i]); }
+        *reinterpret_cast<float4 *>(stage + panel_off(row, c)) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4 *>(stage + PANEL_A + panel_off(row, c)) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+// one 128 B row of an HBM activation panel.  The panel is the exact shared-memory image the dW1 GEMM feeds to the tensor
+// core as an MN-major tf32 operand (K = sample row): the only layout tcgen05 accepts for that is SWIZZLE_128B_BASE32B
+// (cute Swizzle<2,5,2>, atoms of 4 rows x 128 B): 32-byte chunk c of row r is stored at position c ^ (r & 3).
+__device__ __forceinline__ void store_panel_row(float *dst, int row, const float (&h)[32]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float4 *d = reinterpret_cast<float4 *>(dst) + 2 * (c ^ (row & 3));
+        d[0] = make_float4(h[c * 8], h[c * 8 + 1], h[c * 8 + 2], h[c * 8 + 3]);
+        d[1] = make_float4(h[c * 8 + 4], h[c * 8 + 5], h[c * 8 + 6], h[c * 8 + 7]);
+    }
+}
+// float index of element k (0..31) of row r inside such a panel row
+__device__ __forceinline__ int panel_elem(int r, int k) { return ((((k >> 3) ^ (r & 3)) << 3) | (k & 7)); }
+// v[c] of lane l = element (row l, column c) of a 32x32 block; returns on lane l the sum over rows of column l
+__device__ __forceinline__ float colsum32(const float (&v)[32], int lane) {
+    float r16[16], r8[8], r4[4], r2[2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const bool up = lane & 16;
+        const float send = up ? v[i] : v[i + 16], keep = up ? v[i + 16] : v[i];
+        r16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const bool up = lane & 8;
+        const float send = up ? r16[i] : r16[i + 8], keep = up ? r16[i + 8] : r16[i];
+        r8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const bool up = lane & 4;
+        const float send = up ? r8[i] : r8[i + 4], keep = up ? r8[i + 4] : r8[i];
+        r4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const bool up = lane & 2;
+        const float send = up ? r4[i] : r4[i + 2], keep = up ? r4[i + 2] : r4[i];
+        r2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    const bool up = lane & 1;
+    const float send = up ? r2[0] : r2[1], keep = up ? r2[1] : r2[0];
+    return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+
+template <bool WGRAD>
+__global__ void __launch_bounds__(NTHREADS, 1) k_mlp_tc_train(TrainParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t *sm = smem_raw + (base - raw);
+    const uint32_t sB = base, sA = base + NSTAGE * STAGE_B;
+    uint8_t *A_gen = sm + NSTAGE * STAGE_B;
+    float *b0s = reinterpret_cast<float *>(sm + SMEM_DATA);
+    float *b1s = b0s + WN;
+    float *w2s = b1s + WN;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + SMEM_DATA + 3 * WN * 4);
+    // barriers: 0,1 b_full  2,3 b_empty  4,5 a_full  6,7 a_empty  8 d1_full  9 d2_full  10 d3_full  11 d4_full  12 d4_empty
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * i; };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 14);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long M = p.M_dev ? min((long long)*p.M_dev, p.M_host) : p.M_host;
+    const long long ntiles = (M + TM - 1) / TM;
+
+    for (int i = tid; i < WN; i += NTHREADS) { b0s[i] = p.b0[i]; b1s[i] = p.b1[i]; w2s[i] = p.w2[i]; }
+    if (tid == 0) {
+        mbar_init(BAR(0), 1); mbar_init(BAR(1), 1);
+        mbar_init(BAR(2), 1); mbar_init(BAR(3), 1);
+        mbar_init(BAR(4), 4); mbar_init(BAR(5), 4);
+        mbar_init(BAR(6), 1); mbar_init(BAR(7), 1);
+        mbar_init(BAR(8), 1); mbar_init(BAR(9), 1); mbar_init(BAR(10), 1); mbar_init(BAR(11), 1);
+        mbar_init(BAR(12), 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t D1 = tmem, D2 = tmem + 256;   // D3 aliases D1, D4 aliases D2[0:16]
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int step = 0; step < STEPS_TRAIN; ++step, ++it) {
+                    const uint32_t s = it & 1, ph = (it >> 1) & 1;
+                    const uint32_t bytes = (step < 17) ? PANEL_B : PANEL_B16;
+                    mbar_wait(BAR(2 + s), ph ^ 1);
+                    mbar_expect_tx(BAR(0 + s), 2 * bytes);
+                    const uint8_t *src = p.panels + (size_t)step * STAGE_B;
+                    bulk_g2s(sB + s * STAGE_B, src, bytes, BAR(0 + s));
+                    bulk_g2s(sB + s * STAGE_B + PANEL_B, src + PANEL_B, bytes, BAR(0 + s));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc256 = make_idesc(TM, WN), idesc16 = make_idesc(TM, 16);
+            uint32_t it = 0, tl = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
+                for (int step = 0; step < STEPS_TRAIN; ++step, ++it) {
+                    const uint32_t s = it & 1, ph = (it >> 1) & 1;
+                    if (step == 1) mbar_wait(BAR(12), (tl & 1) ^ 1);   // D4 (in D2's columns) of the previous tile fully read
+                    mbar_wait(BAR(0 + s), ph);
+                    mbar_wait(BAR(4 + s), ph);
+                    tc_fence_after();
+                    const uint32_t a_hi = sA + s * STAGE_A, a_lo = a_hi + PANEL_A;
+                    const uint32_t b_hi = sB + s * STAGE_B, b_lo = b_hi + PANEL_B;
+                    const uint32_t d = (step == 0 || (step >= 9 && step <= 16)) ? D1 : D2;
+                    const uint32_t idesc = (step >= 17) ? idesc16 : idesc256;
+                    const int nk = (step == 0) ? 2 : 4;
+                    uint32_t acc = (step == 0 || step == 1 || step == 9 || step == 17) ? 0u : 1u;
+#pragma unroll
+                    for (int term = 0; term < 3; ++term) {
+                        const uint64_t ad = make_desc(term == 2 ? a_lo : a_hi);
+                        const uint64_t bd = make_desc(term == 1 ? b_lo : b_hi);
+                        for (int ks = 0; ks < nk; ++ks) {
+                            mma_tf32(d, ad + 2 * ks, bd + 2 * ks, idesc, acc);
+                            acc = 1u;
+                        }
+                    }
+                    tc_commit(BAR(2 + s));
+                    tc_commit(BAR(6 + s));
+                    if (step == 0) tc_commit(BAR(8));
+                    if (step == 8) tc_commit(BAR(9));
+                    if (step == 16) tc_commit(BAR(10));
+                    if (step == 24) tc_commit(BAR(11));
+                }
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const float b2 = p.b2[0];
+        float g_fs = 0.f, g_sdf = 0.f;
+        if (!p.dsdf_ext) { g_fs = p.stats->g_fs; g_sdf = p.stats->g_sdf; }
+        double loss_fs = 0.0, loss_sdf = 0.0;
+        float gW2r[8], gb2r = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) gW2r[i] = 0.f;
+        uint32_t it = 0, tl = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
+            const long long m = tile * TM + row;
+            const bool live = m < M;
+            uint32_t mask1[8], mask2[8];
+            // ---- step 0: x -> A ----
+            {
+                const uint32_t s = it & 1, ph = (it >> 1) & 1;
+                mbar_wait(BAR(6 + s), ph ^ 1);
+                uint8_t *dst = A_gen + s * STAGE_A;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (live) v = *reinterpret_cast<const float4 *>(p.feats + (size_t)m * 16 + c * 4);
+                    const float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+                    const float4 lo = make_float4(tf32_rna(v.x - hi.x), tf32_rna(v.y - hi.y), tf32_rna(v.z - hi.z), tf32_rna(v.w - hi.w));
+                    *reinterpret_cast<float4 *>(dst + panel_off(row, c)) = hi;
+                    *reinterpret_cast<float4 *>(dst + PANEL_A + panel_off(row, c)) = lo;
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(4 + s));
+                ++it;
+            }
+            // ---- steps 1..8: h1 chunks ----
+            mbar_wait(BAR(8), tl & 1);
+            tc_fence_after();
+            for (int kb = 0; kb < 8; ++kb, ++it) {
+                const uint32_t s = it & 1, ph = (it >> 1) & 1;
+                uint32_t v[32];
+                tmem_ld32(D1 + lane_addr + kb * 32, v);
+                float h[32];
+                uint32_t mk = 0u;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float t = __uint_as_float(v[i]) + b0s[kb * 32 + i];
+                    const bool on = t > 0.f;
+                    h[i] = on ? t : 0.f;
+                    mk |= on ? (1u << i) : 0u;
+                }
+                mask1[kb] = mk;
+                if (WGRAD) store_panel_row(p.act_h1 + ((size_t)(tile * 8 + kb) * TM + row) * 32, row, h);
+                mbar_wait(BAR(6 + s), ph ^ 1);
+                store_a_row(A_gen + s * STAGE_A, row, h);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(4 + s));
+            }
+            // ---- output layer + loss ----
+            mbar_wait(BAR(9), tl & 1);
+            tc_fence_after();
+            float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int cb = 0; cb < 8; ++cb) {
+                uint32_t v[32];
+                tmem_ld32(D2 + lane_addr + cb * 32, v);
+                uint32_t mk = 0u;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float t = __uint_as_float(v[i]) + b1s[cb * 32 + i];
+                    const bool on = t > 0.f;
+                    mk |= on ? (1u << i) : 0u;
+                    acc4[i & 3] = fmaf(on ? t : 0.f, w2s[cb * 32 + i], acc4[i & 3]);
+                }
+                mask2[cb] = mk;
+            }
+            const float sdf = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]) + b2;
+            float dsdf = 0.f;
+            if (live) {
+                p.sdf[m] = sdf;
+                if (p.dsdf_ext) {
+                    dsdf = p.dsdf_ext[m];
+                } else {
+                    const uint32_t fl = p.s_flag[m];
+                    const int r = p.s_ray[m];
+                    const float cosr = p.cosv ? p.cosv[r] : 1.0f;
+                    const float z = __fmul_rn(p.s_depth[m], cosr);
+                    const float dgt = p.gt_depth[r];
+                    if (fl & 1u) {
+                        const float e = sdf - 1.0f;
+                        loss_fs += (double)e * (double)e;
+                        dsdf += 2.0f * g_fs * e;
+                    }
+                    if (fl & 2u) {
+                        const float e = __fsub_rn(__fadd_rn(z, __fmul_rn(sdf, p.truncation)), dgt);
+                        loss_sdf += (double)e * (double)e;
+                        dsdf += 2.0f * g_sdf * p.truncation * e;
+                    }
+                }
+            }
+            if (WGRAD) gb2r += dsdf;
+            // ---- steps 9..16: dh2 chunks (registers only; with WGRAD a second pass over D2 gives h2 for gW2) ----
+            for (int jb = 0; jb < 8; ++jb, ++it) {
+                const uint32_t s = it & 1, ph = (it >> 1) & 1;
+                float h[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) h[i] = ((mask2[jb] >> i) & 1u) ? dsdf * w2s[jb * 32 + i] : 0.f;
+                if (WGRAD) {
+                    store_panel_row(p.act_dh2 + ((size_t)(tile * 8 + jb) * TM + row) * 32, row, h);
+                    uint32_t v[32];
+                    tmem_ld32(D2 + lane_addr + jb * 32, v);
+                    float pr[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) pr[i] = ((mask2[jb] >> i) & 1u) ? (__uint_as_float(v[i]) + b1s[jb * 32 + i]) * dsdf : 0.f;
+                    gW2r[jb] += colsum32(pr, lane);
+                }
+                mbar_wait(BAR(6 + s), ph ^ 1);
+                store_a_row(A_gen + s * STAGE_A, row, h);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(4 + s));
+            }
+            // ---- steps 17..24: dh1 (masked) chunks from D3 ----
+            mbar_wait(BAR(10), tl & 1);
+            tc_fence_after();
+            for (int kb = 0; kb < 8; ++kb, ++it) {
+                const uint32_t s = it & 1, ph = (it >> 1) & 1;
+                uint32_t v[32];
+                tmem_ld32(D1 + lane_addr + kb * 32, v);
+                float h[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) h[i] = ((mask1[kb] >> i) & 1u) ? __uint_as_float(v[i]) : 0.f;
+                if (WGRAD) store_panel_row(p.act_dh1 + ((size_t)(tile * 8 + kb) * TM + row) * 32, row, h);
+                mbar_wait(BAR(6 + s), ph ^ 1);
+                store_a_row(A_gen + s * STAGE_A, row, h);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(4 + s));
+            }
+            // ---- d loss / d x ----
+            mbar_wait(BAR(11), tl & 1);
+            tc_fence_after();
+            {
+                uint32_t v[16];
+                tmem_ld16(D2 + lane_addr, v);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(12));
+                if (live) {
+                    float4 *o = reinterpret_cast<float4 *>(p.dfeats + (size_t)m * 16);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        o[c] = make_float4(__uint_as_float(v[c * 4]), __uint_as_float(v[c * 4 + 1]), __uint_as_float(v[c * 4 + 2]),
+                                           __uint_as_float(v[c * 4 + 3]));
+                }
+            }
+        }
+        if (!p.dsdf_ext) {
+            for (int off = 16; off > 0; off >>= 1) {
+                loss_fs += __shfl_down_sync(0xffffffffu, loss_fs, off);
+                loss_sdf += __shfl_down_sync(0xffffffffu, loss_sdf, off);
+            }
+            if (lane == 0) {
+                if (loss_fs != 0.0) atomicAdd(&p.stats->fs_sum, loss_fs);
+                if (loss_sdf != 0.0) atomicAdd(&p.stats->sdf_sum, loss_sdf);
+            }
+        }
+        if (WGRAD) {
+#pragma unroll
+            for (int jb = 0; jb < 8; ++jb) atomicAdd(p.gW2 + jb * 32 + lane, gW2r[jb]);
+            for (int off = 16; off > 0; off >>= 1) gb2r += __shfl_down_sync(0xffffffffu, gb2r, off);
+            if (lane == 0) atomicAdd(p.gb2, gb2r);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
+// ================================================================================================
+// Weight gradient of the hidden layer on tensor cores:  gW1[j][k] += sum_m dh2[m][j] * h1[m][k]
+//   D (256 x 256, fp32) lives in TMEM for the whole kernel: two M=128 accumulators x 256 columns = all 512 columns.
+//   K = samples, streamed in K-blocks of 16 rows.  Both operands are MN-major: the HBM panels written by
+//   k_mlp_tc_train<true> ([(tile*8+p)][row][32 floats], 128B-swizzled) are bulk-copied unchanged into shared memory
+//   (8 panels x 2 KB per operand and K-block).  fp32 bits are read by the tensor core as tf32 by truncation (= "hi");
+//   4 converter warps compute lo = tf32(x - trunc(x)) into sibling tiles; 3 MMAs terms (hi*hi + hi*lo + lo*hi).
+//   3-stage ring of 64 KB.  Every CTA finally adds its partial 256x256 into gW1 with float4 atomics.
+// ================================================================================================
+constexpr int DW_KROWS = 16;
+constexpr int DW_PANEL = DW_KROWS * 128;        // 2 KB: 16 sample rows x 128 B
+constexpr int DW_OPER = 8 * DW_PANEL;           // 16 KB: all 256 columns of one operand
+constexpr int DW_STAGE = 4 * DW_OPER;           // A raw | B raw | A lo | B lo
+constexpr int DW_NSTAGE = 3;
+constexpr int DW_SMEM = DW_NSTAGE * DW_STAGE + 1024 + 1024;
+
+// MN-major SWIZZLE_128B_BASE32B descriptor (layout type 1): LBO = byte stride between 32-element MN groups (= one 2 KB
+// panel), SBO = byte stride between groups of 4 K rows (512 B); one k-step (K = 8) spans two such groups
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(DW_PANEL >> 4) << 16) | (32ull << 32) | (1ull << 46) | (1ull << 61);
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) k_dw1_tc(long long M_host, const int32_t *__restrict__ M_dev, const float *__restrict__ act_dh2,
+                                                         const float *__restrict__ act_h1, float *__restrict__ gW1) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t *sm = smem_raw + (base - raw);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + DW_NSTAGE * DW_STAGE);
+    // barriers: 0..2 raw_full  3..5 conv_done  6..8 stage_empty  9 d_full
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * i; };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 12);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long M = M_dev ? min((long long)*M_dev, M_host) : M_host;
+    const long long nkb = ((M + TM - 1) / TM) * (TM / DW_KROWS);   // K-blocks of 16 rows (whole tiles: padded rows hold dh2 = 0)
+    if (tid == 0) {
+        for (int i = 0; i < 3; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), 4); mbar_init(BAR(6 + i), 1); }
+        mbar_init(BAR(9), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const bool has_work = (long long)blockIdx.x < nkb;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (long long kb = blockIdx.x; kb < nkb; kb += gridDim.x, ++it) {
+                const uint32_t s = it % DW_NSTAGE, ph = (it / DW_NSTAGE) & 1;
+                mbar_wait(BAR(6 + s), ph ^ 1);
+                mbar_expect_tx(BAR(0 + s), 2 * DW_OPER);
+                const long long tile = kb >> 3;
+                const int r0 = (int)(kb & 7) * DW_KROWS;
+                const uint32_t dst = base + s * DW_STAGE;
+                for (int pnl = 0; pnl < 8; ++pnl) {
+                    const size_t off = ((size_t)(tile * 8 + pnl) * TM + r0) * 32;
+                    bulk_g2s(dst + pnl * DW_PANEL, act_dh2 + off, DW_PANEL, BAR(0 + s));
+                    bulk_g2s(dst + DW_OPER + pnl * DW_PANEL, act_h1 + off, DW_PANEL, BAR(0 + s));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && has_work) {
+            // M = 128 (rows j), N = 256 (columns k), both operands MN-major (bits 15, 16)
+            constexpr uint32_t idesc = make_idesc(TM, WN) | (1u << 15) | (1u << 16);
+            uint32_t it = 0;
+            for (long long kb = blockIdx.x; kb < nkb; kb += gridDim.x, ++it) {
+                const uint32_t s = it % DW_NSTAGE, ph = (it / DW_NSTAGE) & 1;
+                mbar_wait(BAR(3 + s), ph);
+                tc_fence_after();
+                const uint32_t a_raw = base + s * DW_STAGE, b_raw = a_raw + DW_OPER, a_lo = a_raw + 2 * DW_OPER, b_lo = a_raw + 3 * DW_OPER;
+#pragma unroll
+                for (int jt = 0; jt < 2; ++jt) {
+                    uint32_t acc = it > 0 ? 1u : 0u;
+#pragma unroll
+                    for (int term = 0; term < 3; ++term) {
+                        const uint32_t a0 = (term == 2 ? a_lo : a_raw) + jt * 4 * DW_PANEL;
+                        const uint32_t b0 = (term == 1 ? b_lo : b_raw);
+#pragma unroll
+                        for (int ks = 0; ks < DW_KROWS / 8; ++ks) {
+                            mma_tf32(tmem + jt * 256, make_desc_mn(a0 + ks * 1024), make_desc_mn(b0 + ks * 1024), idesc, acc);
+                            acc = 1u;
+                        }
+                    }
+                }
+                tc_commit(BAR(6 + s));
+            }
+            tc_commit(BAR(9));
+        }
+    } else {
+        // converters: lo = tf32_rna(x - trunc_tf32(x)) for both operands of the stage (8192 floats, 128 threads)
+        const int ct = tid - 64;
+        uint32_t it = 0;
+        for (long long kb = blockIdx.x; kb < nkb; kb += gridDim.x, ++it) {
+            const uint32_t s = it % DW_NSTAGE, ph = (it / DW_NSTAGE) & 1;
+            mbar_wait(BAR(0 + s), ph);
+            float4 *src = reinterpret_cast<float4 *>(sm + s * DW_STAGE);
+            float4 *dst = reinterpret_cast<float4 *>(sm + s * DW_STAGE + 2 * DW_OPER);
+#pragma unroll 4
+            for (int f = ct; f < 2 * DW_OPER / 16; f += 128) {
+                const float4 v = src[f];
+                float4 l;
+                l.x = tf32_rna(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u));
+                l.y = tf32_rna(v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u));
+                l.z = tf32_rna(v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u));
+                l.w = tf32_rna(v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
+                dst[f] = l;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(3 + s));
+        }
+        // epilogue: thread = row j of each accumulator; add the CTA's partial sums into gW1
+        if (has_work) {
+            mbar_wait(BAR(9), 0);
+            tc_fence_after();
+            const int q = warp & 3;
+            const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+            for (int jt = 0; jt < 2; ++jt) {
+                const int j = jt * 128 + q * 32 + lane;
+                for (int cb = 0; cb < 8; ++cb) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem + lane_addr + jt * 256 + cb * 32, v);
+                    float4 *o = reinterpret_cast<float4 *>(gW1 + (size_t)j * WN + cb * 32);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        atomicAdd(o + c, make_float4(__uint_as_float(v[c * 4]), __uint_as_float(v[c * 4 + 1]), __uint_as_float(v[c * 4 + 2]),
+                                                     __uint_as_float(v[c * 4 + 3])));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
+// gW0[k][e] += sum_m dh1[m][k] x[m][e],  gb0[k] += sum_m dh1[m][k],  gb1[j] += sum_m dh2[m][j]   (fp32 CUDA cores: 2 KB/sample, HBM-bound)
+// thread = column k (256 threads); each CTA walks a strided set of samples
+__global__ void __launch_bounds__(256) k_dw0_panels(long long M_host, const int32_t *__restrict__ M_dev, const float *__restrict__ dh1,
+                                                     const float *__restrict__ dh2, const float *__restrict__ x, float *__restrict__ gW0,
+                                                     float *__restrict__ gb0, float *__restrict__ gb1) {
+    __shared__ float xs[32][16];
+    const long long M = M_dev ? min((long long)*M_dev, M_host) : M_host;
+    const int k = threadIdx.x;
+    float acc[16], sb0 = 0.f, sb1 = 0.f;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+    for (long long m0 = (long long)blockIdx.x * 32; m0 < M; m0 += (long long)gridDim.x * 32) {
+        for (int f = threadIdx.x; f < 32 * 16; f += 256) {
+            const long long m = m0 + (f >> 4);
+            xs[f >> 4][f & 15] = (m < M) ? x[(size_t)m * 16 + (f & 15)] : 0.f;
+        }
+        __syncthreads();
+        const int nr = (int)min((long long)32, M - m0);
+        for (int r8 = 0; r8 < nr; r8 += 8) {
+            float d1[8], d2[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {     // 16 independent loads in flight per thread
+                const long long m = m0 + r8 + u;
+                const int rr = (int)(m & 127);
+                const size_t off = (((size_t)(m >> 7) * 8 + (k >> 5)) * TM + rr) * 32 + panel_elem(rr, k & 31);
+                const bool ok = (r8 + u) < nr;
+                d1[u] = ok ? dh1[off] : 0.f;
+                d2[u] = ok ? dh2[off] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                sb0 += d1[u];
+                sb1 += d2[u];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) acc[e] = fmaf(d1[u], xs[(r8 + u) & 31][e], acc[e]);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int e = 0; e < 16; ++e) atomicAdd(gW0 + k * 16 + e, acc[e]);
+    atomicAdd(gb0 + k, sb0);
+    atomicAdd(gb1 + k, sb1);
+}
+
 }  // namespace tc
 
-extern "C" int64_t nl_mlp_tc_panel_bytes(void) { return (int64_t)tc::STEPS_FWD * tc::STAGE_B; }
+extern "C" int64_t nl_mlp_tc_panel_bytes(void) { return (int64_t)tc::STEPS_TRAIN * tc::STAGE_B; }
 
 extern "C" int nl_mlp_tc_prepare(const float *W0, const float *W1, void *panels, void *stream) {
     if (!W0 || !W1 || !panels) return nl_set_error("nl_mlp_tc_prepare: null pointer");
-    dim3 grid(nl_div_up(tc::WN * 8, 256), tc::STEPS_FWD);
+    dim3 grid(nl_div_up(tc::WN * 8, 256), tc::STEPS_TRAIN);
     tc::k_tc_prepare<<<grid, 256, 0, (cudaStream_t)stream>>>(W0, W1, (uint8_t *)panels);
     NL_CHECK_LAUNCH("nl_mlp_tc_prepare");
     return NL_OK;
@@ -334,5 +905,48 @@ extern "C" int nl_mlp_tc_forward(int64_t M, const int32_t *d_M_dev, const float 
     const int grid = (int)(ntiles < (long long)nl_num_sms() ? ntiles : (long long)nl_num_sms());
     tc::k_mlp_tc_fwd<<<grid, tc::NTHREADS, tc::SMEM_TOTAL, (cudaStream_t)stream>>>(p);
     NL_CHECK_LAUNCH("nl_mlp_tc_forward");
+    return NL_OK;
+}
+
+extern "C" int64_t nl_mlp_tc_act_floats(int64_t M) { return ((M + tc::TM - 1) / tc::TM) * 8 * tc::TM * 32; }
+
+extern "C" int nl_mlp_tc_train(int64_t M, const int32_t *d_M_dev, const float *feats, const void *panels, const float *b0,
+                               const float *b1, const float *w2, const float *b2, const uint8_t *s_flag, const float *s_depth,
+                               const int32_t *s_ray, const float *cosv, const float *gt_depth, nl_render_stats *stats,
+                               float truncation, float *sdf, float *dfeats, const nl_mlp_grads *grads, float *act_h1, float *act_dh2,
+                               float *act_dh1, const float *dsdf_ext, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (M < 0) return nl_set_error("nl_mlp_tc_train: negative M");
+    if (M == 0) return NL_OK;
+    if (!feats || !panels || !b0 || !b1 || !w2 || !b2 || !sdf || !dfeats) return nl_set_error("nl_mlp_tc_train: null pointer");
+    if (!dsdf_ext && (!s_flag || !s_depth || !s_ray || !gt_depth || !stats))
+        return nl_set_error("nl_mlp_tc_train: the loss needs s_flag, s_depth, s_ray, gt_depth and stats");
+    if (grads && (!grads->gW0 || !grads->gb0 || !grads->gW1 || !grads->gb1 || !grads->gW2 || !grads->gb2 || !act_h1 || !act_dh2 || !act_dh1))
+        return nl_set_error("nl_mlp_tc_train: decoder gradients requested but a buffer is null");
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc::k_mlp_tc_train<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::k_mlp_tc_train<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::k_dw1_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::DW_SMEM);
+        if (e != cudaSuccess) return nl_set_error_code(NL_ERR_CUDA, cudaGetErrorString(e));
+        configured = true;
+    }
+    tc::TrainParams p = {};
+    p.M_host = M; p.M_dev = d_M_dev; p.feats = feats; p.panels = (const uint8_t *)panels;
+    p.b0 = b0; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.sdf = sdf; p.dfeats = dfeats;
+    p.s_flag = s_flag; p.s_depth = s_depth; p.s_ray = s_ray; p.cosv = cosv; p.gt_depth = gt_depth; p.stats = stats;
+    p.truncation = truncation; p.dsdf_ext = dsdf_ext;
+    const long long ntiles = (M + tc::TM - 1) / tc::TM;
+    const int sms = nl_num_sms();
+    const int grid = (int)(ntiles < (long long)sms ? ntiles : (long long)sms);
+    if (grads) {
+        p.act_h1 = act_h1; p.act_dh2 = act_dh2; p.act_dh1 = act_dh1; p.gW2 = grads->gW2; p.gb2 = grads->gb2;
+        tc::k_mlp_tc_train<true><<<grid, tc::NTHREADS, tc::SMEM_TOTAL, stream>>>(p);
+        tc::k_dw1_tc<<<sms, tc::NTHREADS, tc::DW_SMEM, stream>>>(M, d_M_dev, act_dh2, act_h1, grads->gW1);
+        tc::k_dw0_panels<<<sms * 4, 256, 0, stream>>>(M, d_M_dev, act_dh1, act_dh2, feats, grads->gW0, grads->gb0, grads->gb1);
+    } else {
+        tc::k_mlp_tc_train<false><<<grid, tc::NTHREADS, tc::SMEM_TOTAL, stream>>>(p);
+    }
+    NL_CHECK_LAUNCH("nl_mlp_tc_train");
     return NL_OK;
 }

@@ -12,8 +12,62 @@ import torch
 from . import _capi
 from ._capi import MlpGrads, MlpWeights, RenderArgs, RenderStats
 
+import os
+
 STATS_BYTES = C.sizeof(RenderStats)
 N_SAMPLES_OFFSET = RenderStats.n_samples.offset
+
+
+def mlp_impl(width):
+    """'tc' = tcgen05 3xTF32 tensor-core kernels (width 256), 'simt' = fp32 CUDA-core kernels.  NL_MLP_IMPL overrides."""
+    want = os.environ.get("NL_MLP_IMPL", "tc")
+    return "tc" if (want == "tc" and width == 256) else "simt"
+
+
+def mlp_forward(bufs, M_cap, M_dev, feats, sdf):
+    """sdf[M] = decoder(feats[M,16]) through the selected kernel implementation."""
+    lib, st = _capi.lib(), _capi.stream_ptr()
+    if mlp_impl(bufs.width) == "tc":
+        p = bufs.params
+        _capi.check(lib.nl_mlp_tc_forward(M_cap, M_dev, _capi.ptr(feats), _capi.ptr(bufs.tc_panels), _capi.ptr(p[1]), _capi.ptr(p[3]),
+                                          _capi.ptr(p[4]), _capi.ptr(p[5]), _capi.ptr(sdf), st), "nl_mlp_tc_forward")
+    else:
+        w = bufs.weights_struct()
+        _capi.check(lib.nl_mlp_forward(M_cap, M_dev, _capi.ptr(feats), C.byref(w), _capi.ptr(sdf), st), "nl_mlp_forward")
+    _capi.LAUNCHES += 1
+
+
+def mlp_train(bufs, M_cap, M_dev, feats, sdf, dfeats, want_wgrad, act, s_flag=None, s_depth=None, s_ray=None, cos=None, gt_depth=None,
+              stats_ptr=None, truncation=0.0, dsdf_ext=None):
+    """Forward + (loss | external d sdf) + backward.  act: dict with scratch tensors for the weight gradients
+    ('h1','dh2' [cap,W] for simt; 'h1','dh2','dh1' panel buffers for tc).  Accumulates into bufs.grads when want_wgrad."""
+    lib, st = _capi.lib(), _capi.stream_ptr()
+    gs = bufs.grads_struct() if want_wgrad else None
+    gp = C.byref(gs) if want_wgrad else None
+    if mlp_impl(bufs.width) == "tc":
+        p = bufs.params
+        _capi.check(lib.nl_mlp_tc_train(M_cap, M_dev, _capi.ptr(feats), _capi.ptr(bufs.tc_panels), _capi.ptr(p[1]), _capi.ptr(p[3]),
+                                        _capi.ptr(p[4]), _capi.ptr(p[5]), _capi.ptr(s_flag), _capi.ptr(s_depth), _capi.ptr(s_ray),
+                                        _capi.ptr(cos), _capi.ptr(gt_depth), stats_ptr, float(truncation), _capi.ptr(sdf),
+                                        _capi.ptr(dfeats), gp, _capi.ptr(act["h1"]) if want_wgrad else None,
+                                        _capi.ptr(act["dh2"]) if want_wgrad else None, _capi.ptr(act["dh1"]) if want_wgrad else None,
+                                        _capi.ptr(dsdf_ext), st), "nl_mlp_tc_train")
+        _capi.LAUNCHES += 3 if want_wgrad else 1
+    else:
+        w = bufs.weights_struct()
+        _capi.check(lib.nl_mlp_train(M_cap, M_dev, _capi.ptr(feats), C.byref(w), _capi.ptr(s_flag), _capi.ptr(s_depth), _capi.ptr(s_ray),
+                                     _capi.ptr(cos), _capi.ptr(gt_depth), stats_ptr, float(truncation), _capi.ptr(sdf), _capi.ptr(dfeats),
+                                     gp, _capi.ptr(act["h1"]) if want_wgrad else None, _capi.ptr(act["dh2"]) if want_wgrad else None,
+                                     _capi.ptr(dsdf_ext), st), "nl_mlp_train")
+        _capi.LAUNCHES += 2 if want_wgrad else 1
+
+
+def alloc_act(width, M_cap, device):
+    """Scratch for the decoder weight gradients, sized for M_cap samples."""
+    if mlp_impl(width) == "tc":
+        n = int(_capi.lib().nl_mlp_tc_act_floats(int(M_cap)))
+        return {k: torch.empty(n, dtype=torch.float32, device=device) for k in ("h1", "dh2", "dh1")}
+    return {k: torch.empty((int(M_cap), width), dtype=torch.float32, device=device) for k in ("h1", "dh2")}
 
 
 class MapState:
@@ -76,6 +130,9 @@ class DecoderBuffers:
         self.W0t = torch.empty((16, W), device=device, dtype=torch.float32)
         self.W1t = torch.empty((W, W), device=device, dtype=torch.float32)
         self.grads = [torch.zeros_like(p) for p in self.params]
+        self.tc_panels = None
+        if mlp_impl(W) == "tc":
+            self.tc_panels = torch.empty(int(_capi.lib().nl_mlp_tc_panel_bytes()), dtype=torch.uint8, device=device)
 
     def weights_struct(self):
         p = self.params
@@ -86,9 +143,15 @@ class DecoderBuffers:
         return MlpGrads(*[C.c_void_p(g.data_ptr()) for g in self.grads])
 
     def refresh_transposes(self):
-        _capi.check(_capi.lib().nl_mlp_prepare(self.width, _capi.ptr(self.params[0]), _capi.ptr(self.params[2]), _capi.ptr(self.W0t),
-                                               _capi.ptr(self.W1t), _capi.stream_ptr()), "nl_mlp_prepare")
-        _capi.LAUNCHES += 2
+        """Re-derive the kernel-side weight images from the parameters (they change every optimiser step)."""
+        if self.tc_panels is not None:
+            _capi.check(_capi.lib().nl_mlp_tc_prepare(_capi.ptr(self.params[0]), _capi.ptr(self.params[2]), _capi.ptr(self.tc_panels),
+                                                      _capi.stream_ptr()), "nl_mlp_tc_prepare")
+            _capi.LAUNCHES += 1
+        else:
+            _capi.check(_capi.lib().nl_mlp_prepare(self.width, _capi.ptr(self.params[0]), _capi.ptr(self.params[2]), _capi.ptr(self.W0t),
+                                                   _capi.ptr(self.W1t), _capi.stream_ptr()), "nl_mlp_prepare")
+            _capi.LAUNCHES += 2
 
 
 class SDFEngine:
@@ -116,8 +179,8 @@ class SDFEngine:
         self.feats = torch.empty((M, 16), dtype=f32, device=d)
         self.dfeats = torch.empty((M, 16), dtype=f32, device=d)
         self.sdf = torch.empty(M, dtype=f32, device=d)
-        self.act_h1 = self.act_dh2 = None
-        self._act_width = 0
+        self.act = None
+        self._act_key = None
         self.want_decoder_grads = want_decoder_grads
         self.grad_emb = None          # fp32 [V,16]
         self.pose_acc = None          # fp32 [F,12]
@@ -144,10 +207,10 @@ class SDFEngine:
         return RenderStats.from_buffer_copy(self._stats_host.numpy().tobytes())
 
     def _ensure_act(self, width):
-        if self.act_h1 is None or self._act_width != width:
-            self.act_h1 = torch.empty((self.max_samples, width), dtype=torch.float32, device=self.device)
-            self.act_dh2 = torch.empty((self.max_samples, width), dtype=torch.float32, device=self.device)
-            self._act_width = width
+        key = (width, mlp_impl(width))
+        if self.act is None or self._act_key != key:
+            self.act = alloc_act(width, self.max_samples, self.device)
+            self._act_key = key
 
     # ------------------------------------------------------------------ stages
     def rays_from_poses(self, pose6, dir_local, ray_frame):
@@ -203,10 +266,7 @@ class SDFEngine:
         self.render_samples(m, R, cfg, ray_o, ray_d, None, None, noise, rng_seed, reference_compat)
         dec.refresh_transposes()
         self.gather_forward(m)
-        w = dec.weights_struct()
-        _capi.check(_capi.lib().nl_mlp_forward(self.max_samples, self.n_samples_dev, _capi.ptr(self.feats), C.byref(w),
-                                               _capi.ptr(self.sdf), _capi.stream_ptr()), "nl_mlp_forward")
-        _capi.LAUNCHES += 1
+        mlp_forward(dec, self.max_samples, self.n_samples_dev, self.feats, self.sdf)
 
     def forward_backward(self, m, dec, R, cfg, gt_depth, cos, dir_local=None, ray_frame=None, n_frames=1, ray_o=None,
                          ray_d=None, noise=None, rng_seed=0, reference_compat=True, update_decoder=True, update_emb=True,
@@ -228,20 +288,13 @@ class SDFEngine:
         dec.refresh_transposes()
         self.gather_forward(m)
         self._mark("t_gather_fwd")
-        grads_p = None
         if update_decoder:
             self._ensure_act(dec.width)
             for g in dec.grads:
                 g.zero_()
-            gs = dec.grads_struct()
-            grads_p = C.byref(gs)
-        w = dec.weights_struct()
-        _capi.check(lib.nl_mlp_train(self.max_samples, self.n_samples_dev, _capi.ptr(self.feats), C.byref(w), _capi.ptr(self.s_flag),
-                                     _capi.ptr(self.s_depth), _capi.ptr(self.s_ray), _capi.ptr(cos), _capi.ptr(gt_depth),
-                                     C.c_void_p(self.stats.data_ptr()), float(cfg["truncation"]), _capi.ptr(self.sdf),
-                                     _capi.ptr(self.dfeats), grads_p, _capi.ptr(self.act_h1) if update_decoder else None,
-                                     _capi.ptr(self.act_dh2) if update_decoder else None, None, st), "nl_mlp_train")
-        _capi.LAUNCHES += 2 if update_decoder else 1
+        mlp_train(dec, self.max_samples, self.n_samples_dev, self.feats, self.sdf, self.dfeats, update_decoder, self.act,
+                  s_flag=self.s_flag, s_depth=self.s_depth, s_ray=self.s_ray, cos=cos, gt_depth=gt_depth,
+                  stats_ptr=C.c_void_p(self.stats.data_ptr()), truncation=cfg["truncation"])
         self._mark("t_mlp")
         if update_emb:
             if self.grad_emb is None or self.grad_emb.shape[0] != m.emb.shape[0]:

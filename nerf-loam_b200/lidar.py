@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 
 from . import _capi
-from .engine import DecoderBuffers
+from .engine import DecoderBuffers, alloc_act, mlp_forward, mlp_train
 
 
 class Same(nn.Module):
@@ -32,9 +32,7 @@ class _DecoderFn(torch.autograd.Function):
         bufs.refresh_transposes()
         M = x.shape[0]
         sdf = torch.empty(M, dtype=torch.float32, device=x.device)
-        w = bufs.weights_struct()
-        _capi.check(_capi.lib().nl_mlp_forward(M, None, _capi.ptr(x), C.byref(w), _capi.ptr(sdf), _capi.stream_ptr()), "nl_mlp_forward")
-        _capi.LAUNCHES += 1
+        mlp_forward(bufs, M, None, x, sdf)
         ctx.save_for_backward(x)
         ctx.dec = dec
         return sdf.unsqueeze(-1)
@@ -49,18 +47,9 @@ class _DecoderFn(torch.autograd.Function):
         sdf = torch.empty(M, dtype=torch.float32, device=x.device)
         dx = torch.empty((M, 16), dtype=torch.float32, device=x.device)
         need_w = any(ctx.needs_input_grad[2:])
-        h1 = dh2 = None
-        gs = None
-        if need_w:
-            h1 = torch.empty((M, W), dtype=torch.float32, device=x.device)
-            dh2 = torch.empty((M, W), dtype=torch.float32, device=x.device)
-            gs = bufs.grads_struct()
-        w = bufs.weights_struct()
+        act = alloc_act(W, M, x.device) if need_w else None
         g = gout.reshape(-1).contiguous().float()
-        _capi.check(_capi.lib().nl_mlp_train(M, None, _capi.ptr(x), C.byref(w), None, None, None, None, None, None, 0.0,
-                                             _capi.ptr(sdf), _capi.ptr(dx), C.byref(gs) if need_w else None, _capi.ptr(h1),
-                                             _capi.ptr(dh2), _capi.ptr(g), _capi.stream_ptr()), "nl_mlp_train")
-        _capi.LAUNCHES += 2 if need_w else 1
+        mlp_train(bufs, M, None, x, sdf, dx, need_w, act, dsdf_ext=g)
         grads = bufs.grads if need_w else [None] * 6
         return (dx if ctx.needs_input_grad[0] else None, None, *grads)
 

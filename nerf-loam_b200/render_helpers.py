@@ -17,7 +17,7 @@ from copy import deepcopy
 import torch
 
 from . import _capi
-from .engine import DecoderBuffers, FusedAdam, MapState, SDFEngine
+from .engine import DecoderBuffers, FusedAdam, MapState, SDFEngine, alloc_act, mlp_forward, mlp_train
 
 MAX_DEPTH = 80.0
 
@@ -84,19 +84,10 @@ class _RenderSDF(torch.autograd.Function):
         W = bufs.width
         sdf = torch.empty(M, dtype=torch.float32, device=dev)
         dfeats = torch.empty((M, 16), dtype=torch.float32, device=dev)
-        h1 = dh2 = None
-        gs = None
-        if need_dec:
-            h1 = torch.empty((M, W), dtype=torch.float32, device=dev)
-            dh2 = torch.empty((M, W), dtype=torch.float32, device=dev)
-            gs = bufs.grads_struct()
-        w = bufs.weights_struct()
+        act = alloc_act(W, M, dev) if need_dec else None
         g = gsdf.contiguous().float()
         lib, st = _capi.lib(), _capi.stream_ptr()
-        _capi.check(lib.nl_mlp_train(M, None, _capi.ptr(s["feats"]), C.byref(w), None, None, None, None, None, None, 0.0,
-                                     _capi.ptr(sdf), _capi.ptr(dfeats), C.byref(gs) if need_dec else None, _capi.ptr(h1),
-                                     _capi.ptr(dh2), _capi.ptr(g), st), "nl_mlp_train")
-        _capi.LAUNCHES += 2 if need_dec else 1
+        mlp_train(bufs, M, None, s["feats"], sdf, dfeats, need_dec, act, dsdf_ext=g)
         need_emb = ctx.needs_input_grad[2]
         need_rays = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         grad_emb = torch.zeros((m.emb.shape[0], 16), dtype=torch.float32, device=dev) if need_emb else None
@@ -188,15 +179,13 @@ def get_scores(sdf_network, map_states, voxel_size, bits=8):
             continue
         feats = torch.empty((M, 16), dtype=torch.float32, device=dev)
         sdf = torch.empty(M, dtype=torch.float32, device=dev)
-        # voxels without embeddings (interior / FEATURE rows) have vox2row = -1: rows clamp to 0 there like any
-        # garbage the reference would read; they are never meshed (mesh_util only uses SURFACE voxels)
+        # voxels without embeddings (interior / FEATURE rows) have vox2row = -1: they are never meshed (mesh_util only
+        # uses SURFACE voxels); the gather treats a missing row as zeros
         _capi.check(_capi.lib().nl_gather_trilinear_fwd(M, None, _capi.ptr(xyz), _capi.ptr(vox), _capi.ptr(m.centres),
                                                         _capi.ptr(m.vox2row), _capi.ptr(m.emb), float(voxel_size), _capi.ptr(feats),
                                                         _capi.stream_ptr()), "nl_gather_trilinear_fwd")
-        w = bufs.weights_struct()
-        _capi.check(_capi.lib().nl_mlp_forward(M, None, _capi.ptr(feats), C.byref(w), _capi.ptr(sdf), _capi.stream_ptr()),
-                    "nl_mlp_forward")
-        _capi.LAUNCHES += 2
+        _capi.LAUNCHES += 1
+        mlp_forward(bufs, M, None, feats, sdf)
         out.append(sdf.reshape(-1, res ** 3, 1).cpu())
     return torch.cat(out, 0).view(-1, res, res, res, 1)
 
