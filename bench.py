@@ -116,10 +116,16 @@ def run_ours(args):
     emb = ms.emb
     state = {"opt": None}
 
-    def step(dirs, gt, cosv):
+    def step(dirs, gt, cosv, update_decoder=True):
         eng.rays_from_poses(pose6, dirs, None)
         eng.forward_backward(ms, bufs, R, CFG, gt, cosv, dir_local=dirs, ray_frame=None, n_frames=1, rng_seed=12345,
-                             update_decoder=True, update_emb=True, update_pose=True, pose6=pose6, group=group)
+                             update_decoder=update_decoder, update_emb=True, update_pose=True, pose6=pose6, group=group)
+        if not update_decoder:          # steady-state variant (decoder frozen after freeze_frame frames, mapping.py:196)
+            if "opt_frozen" not in state:
+                state["opt_frozen"] = nl.engine.FusedAdam([dict(param=emb, grad=eng.grad_emb, lr=LR[0]),
+                                                           dict(param=pose6[0], grad=eng.pose_grad[0], lr=LR[2])])
+            state["opt_frozen"].step()
+            return
         if state["opt"] is None:
             groups = [dict(param=emb, grad=eng.grad_emb, lr=LR[0])]
             groups += [dict(param=p.data, grad=g, lr=LR[1]) for p, g in zip(bufs.params, bufs.grads)]
@@ -157,6 +163,22 @@ def run_ours(args):
     t_gf = float(np.mean([a.elapsed_time(b) for a, b in zip(ev["t_samples"], ev["t_gather_fwd"])]))
     t_gb = float(np.mean([a.elapsed_time(b) for a, b in zip(ev["t_mlp"], ev["t_gather_bwd"])]))
     t_smp = float(np.mean([a.elapsed_time(b) for a, b in zip(ev["t0"], ev["t_samples"])]))
+
+    # ---------------- secondary: steady-state mapping iteration with the decoder frozen ----------------
+    for _ in range(3):
+        step(d_dirs, d_gt, d_cos, update_decoder=False)
+    sync_all()
+    eng.events = {}
+    z0, z1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    z0.record()
+    for _ in range(args.steps):
+        step(d_dirs, d_gt, d_cos, update_decoder=False)
+    z1.record()
+    sync_all()
+    ms_frozen = z0.elapsed_time(z1)
+    evf = eng.events
+    eng.events = None
+    t_mlp_frozen = float(np.mean([a.elapsed_time(b) for a, b in zip(evf["t_gather_fwd"], evf["t_mlp"])]))
 
     # ---------------- end-to-end through the public step with host buffers (e2e) ----------------
     loss_host = torch.empty(nl.engine.STATS_BYTES, dtype=torch.uint8).pin_memory()
@@ -214,6 +236,9 @@ def run_ours(args):
         "roofline_gather": {"bound": "hbm", "kernel": "k_gather_fwd + k_gather_bwd", "achieved": gather_gbs, "peak": pk["hbm"], "unit": "GB/s",
                             "frac": gather_gbs / pk["hbm"], "ms_fwd": t_gf, "ms_bwd": t_gb, "algorithmic_bytes_per_sample": BYTES_PER_SAMPLE_MAP},
         "stage_ms": {"traverse_sample": t_smp, "gather_fwd": t_gf, "mlp_fwd_bwd": t_mlp, "gather_bwd": t_gb},
+        "frozen_decoder": {"value": n_local * args.steps / (ms_frozen * 1e-3), "unit": "samples/s (this rank)", "ms_per_step": ms_frozen / args.steps,
+                           "mlp_fwd_bwd_ms": t_mlp_frozen,
+                           "note": "same iteration with update_decoder=False (steady state after freeze_frame frames, mapping.py:196)"},
         "clocks": clk,
     }
     if world == 1 and not os.environ.get("NL_BENCH_SKIP_CPU"):

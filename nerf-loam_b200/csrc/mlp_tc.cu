@@ -15,6 +15,8 @@
 //                       core reads; finally reduces relu(D2 + b1) . w2 + b2 per row.
 // Layer 1 (K = 16) runs through the same ring as one extra K-block with 2 k-steps.
 // Shared memory: 2 x 64 KB weight stages + 2 x 32 KB activation stages = 192 KB.
+#include <cstdlib>
+
 #include "nl_cuda.cuh"
 
 namespace tc {
@@ -30,7 +32,8 @@ constexpr int STEPS_FWD = 9;          // layer 1 + 8 K-blocks of layer 2
 constexpr int STEPS_TRAIN = 25;       // + 8 K-blocks of backward layer 2 + 8 of backward layer 1
 constexpr int PANEL_B16 = 16 * 128;   // 2 KB: the 16-row panels of backward layer 1
 constexpr int SMEM_DATA = NSTAGE * (STAGE_A + STAGE_B);
-constexpr int SMEM_TOTAL = SMEM_DATA + 4096 + 1024;  // + biases/barriers + alignment slack
+constexpr int SMEM_TOTAL = SMEM_DATA + 8192 + 1024;  // + biases/barriers/exchange + alignment slack
+constexpr int NTHREADS_TRAIN = 320;   // producer warp, MMA warp, 2 groups of 4 epilogue warps
 constexpr int NTHREADS = 192;
 
 // byte offset of 16-byte chunk c (0..7) of row r inside a K-major SWIZZLE_128B panel
@@ -341,8 +344,10 @@ struct TrainParams {
     nl_render_stats *stats;
     float truncation;
     const float *dsdf_ext;
-    float *act_h1, *act_dh2, *act_dh1;   // WGRAD: panel-major [ntiles*8][128][32]
+    float *act_h1, *act_dh2, *act_dh1, *act_h2;   // WGRAD: panel-major [ntiles*8][128][32]
+    float *act_dsdf;                     // WGRAD: d loss / d sdf per sample [ntiles*128]
     float *gW2, *gb2;                    // WGRAD
+    long long *dbg;                      // optional timeline stamps (NL_TC_TIMELINE=1), else nullptr
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
@@ -410,14 +415,33 @@ __device__ __forceinline__ float colsum32(const float (&v)[32], int lane) {
     return keep + __shfl_xor_sync(0xffffffffu, send, 1);
 }
 
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// One 128 B row (32 fp32) of an A-operand K-block: the raw fp32 bits are the "hi" operand (the tensor core reads the top
+// 19 bits = truncation to tf32), lo = x - trunc(x) is exact in fp32 and is itself truncated by the hardware (|error| <
+// 2^-20 |x|).  off[c] = swizzled byte offset of chunk c for this thread's row (loop invariant).
+__device__ __forceinline__ void store_a_row_fast(uint32_t stage, const uint32_t (&off)[8], const float (&h)[32]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) lo[i] = h[c * 4 + i] - __uint_as_float(__float_as_uint(h[c * 4 + i]) & 0xffffe000u);
+        st_shared_v4(stage + off[c], h[c * 4], h[c * 4 + 1], h[c * 4 + 2], h[c * 4 + 3]);
+        st_shared_v4(stage + PANEL_A + off[c], lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+// Warp roles (NTHREADS_TRAIN = 320): warps 0-7 epilogue (group g = warp >> 2, TMEM lane quarter q = warp & 3), warp 8
+// producer, warp 9 MMA issuer + TMEM owner.  The two single-thread roles get the HIGHEST warp ids: the per-SMSP arbiter
+// prefers the highest warp id, so the busy epilogue warps cannot starve the thread that feeds the tensor core.
 template <bool WGRAD>
-__global__ void __launch_bounds__(NTHREADS, 1) k_mlp_tc_train(TrainParams p) {
+__global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t *sm = smem_raw + (base - raw);
     const uint32_t sB = base, sA = base + NSTAGE * STAGE_B;
-    uint8_t *A_gen = sm + NSTAGE * STAGE_B;
     float *b0s = reinterpret_cast<float *>(sm + SMEM_DATA);
     float *b1s = b0s + WN;
     float *w2s = b1s + WN;
@@ -426,22 +450,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_mlp_tc_train(TrainParams p) {
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * i; };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 14);
+    float *sdf_part = reinterpret_cast<float *>(sm + SMEM_DATA + 4096);   // [tile parity][group][row]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    long long *dbg = (blockIdx.x == 0) ? p.dbg : nullptr;   // [role 0..3][step 0..24][4 stamps]
+#define NL_STAMP(role, step, k) do { if (dbg && tl == 1) dbg[((role) * 25 + (step)) * 8 + (k)] = clock64(); } while (0)
     const long long M = p.M_dev ? min((long long)*p.M_dev, p.M_host) : p.M_host;
     const long long ntiles = (M + TM - 1) / TM;
 
-    for (int i = tid; i < WN; i += NTHREADS) { b0s[i] = p.b0[i]; b1s[i] = p.b1[i]; w2s[i] = p.w2[i]; }
+    for (int i = tid; i < WN; i += NTHREADS_TRAIN) { b0s[i] = p.b0[i]; b1s[i] = p.b1[i]; w2s[i] = p.w2[i]; }
     if (tid == 0) {
         mbar_init(BAR(0), 1); mbar_init(BAR(1), 1);
         mbar_init(BAR(2), 1); mbar_init(BAR(3), 1);
-        mbar_init(BAR(4), 4); mbar_init(BAR(5), 4);
+        mbar_init(BAR(4), 4); mbar_init(BAR(5), 4);      // a_full: the 4 warps of the group that owns the chunk
         mbar_init(BAR(6), 1); mbar_init(BAR(7), 1);
         mbar_init(BAR(8), 1); mbar_init(BAR(9), 1); mbar_init(BAR(10), 1); mbar_init(BAR(11), 1);
         mbar_init(BAR(12), 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == 9) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -451,14 +478,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_mlp_tc_train(TrainParams p) {
     const uint32_t tmem = *tmem_slot;
     const uint32_t D1 = tmem, D2 = tmem + 256;   // D3 aliases D1, D4 aliases D2[0:16]
 
-    if (warp == 0) {
+    if (warp == 8) {
         if (lane == 0) {
-            uint32_t it = 0;
-            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            uint32_t it = 0, tl = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
                 for (int step = 0; step < STEPS_TRAIN; ++step, ++it) {
                     const uint32_t s = it & 1, ph = (it >> 1) & 1;
                     const uint32_t bytes = (step < 17) ? PANEL_B : PANEL_B16;
+                    NL_STAMP(0, step, 0);
                     mbar_wait(BAR(2 + s), ph ^ 1);
+                    NL_STAMP(0, step, 1);
                     mbar_expect_tx(BAR(0 + s), 2 * bytes);
                     const uint8_t *src = p.panels + (size_t)step * STAGE_B;
                     bulk_g2s(sB + s * STAGE_B, src, bytes, BAR(0 + s));
@@ -466,16 +495,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_mlp_tc_train(TrainParams p) {
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 9) {
         if (lane == 0) {
             constexpr uint32_t idesc256 = make_idesc(TM, WN), idesc16 = make_idesc(TM, 16);
             uint32_t it = 0, tl = 0;
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
                 for (int step = 0; step < STEPS_TRAIN; ++step, ++it) {
                     const uint32_t s = it & 1, ph = (it >> 1) & 1;
+                    NL_STAMP(1, step, 0);
                     if (step == 1) mbar_wait(BAR(12), (tl & 1) ^ 1);   // D4 (in D2's columns) of the previous tile fully read
                     mbar_wait(BAR(0 + s), ph);
+                    NL_STAMP(1, step, 1);
                     mbar_wait(BAR(4 + s), ph);
+                    NL_STAMP(1, step, 2);
                     tc_fence_after();
                     const uint32_t a_hi = sA + s * STAGE_A, a_lo = a_hi + PANEL_A;
                     const uint32_t b_hi = sB + s * STAGE_B, b_lo = b_hi + PANEL_B;
@@ -494,6 +526,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_mlp_tc_train(TrainParams p) {
                     }
                     tc_commit(BAR(2 + s));
                     tc_commit(BAR(6 + s));
+                    NL_STAMP(1, step, 3);
                     if (step == 0) tc_commit(BAR(8));
                     if (step == 8) tc_commit(BAR(9));
                     if (step == 16) tc_commit(BAR(10));
@@ -502,47 +535,79 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_mlp_tc_train(TrainParams p) {
             }
         }
     } else {
-        const int q = warp & 3;
+        // ===== epilogue: 2 groups x 4 warps; thread = (sample row, group); group g owns the K-blocks with (kb & 1) == g =====
+        const int q = warp & 3;                        // TMEM lane quarter this warp may access
+        const int g = warp >> 2;                       // 0: warps 0-3, 1: warps 4-7
         const int row = q * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        uint32_t offc[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) offc[c] = (uint32_t)panel_off(row, c);
         const float b2 = p.b2[0];
         float g_fs = 0.f, g_sdf = 0.f;
         if (!p.dsdf_ext) { g_fs = p.stats->g_fs; g_sdf = p.stats->g_sdf; }
         double loss_fs = 0.0, loss_sdf = 0.0;
-        float gW2r[8], gb2r = 0.f;
+        float gb2r = 0.f;
+        // per-sample inputs of the next tile are fetched one tile ahead (their latency hides behind a whole tile)
+        float4 xn[4];
+        uint32_t fl_n = 0u;
+        float z_n = 0.f, dgt_n = 0.f, dext_n = 0.f;
+        auto prefetch = [&](long long tile) {
+            const long long mm = tile * TM + row;
+            const bool lv = tile < ntiles && mm < M;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) gW2r[i] = 0.f;
-        uint32_t it = 0, tl = 0;
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
+            for (int c = 0; c < 4; ++c) xn[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            fl_n = 0u; z_n = 0.f; dgt_n = 0.f; dext_n = 0.f;
+            if (lv) {
+                if (g == 0) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) xn[c] = *reinterpret_cast<const float4 *>(p.feats + (size_t)mm * 16 + c * 4);
+                }
+                if (p.dsdf_ext) {
+                    dext_n = p.dsdf_ext[mm];
+                } else {
+                    fl_n = p.s_flag[mm];
+                    const int r = p.s_ray[mm];
+                    z_n = __fmul_rn(p.s_depth[mm], p.cosv ? p.cosv[r] : 1.0f);
+                    dgt_n = p.gt_depth[r];
+                }
+            }
+        };
+        prefetch(blockIdx.x);
+        uint32_t it0 = 0, tl = 0;                      // it0: ring step index of this tile's step 0
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl, it0 += STEPS_TRAIN) {
             const long long m = tile * TM + row;
             const bool live = m < M;
-            uint32_t mask1[8], mask2[8];
-            // ---- step 0: x -> A ----
-            {
-                const uint32_t s = it & 1, ph = (it >> 1) & 1;
+            const uint32_t fl = fl_n;
+            const float z = z_n, dgt = dgt_n, dext = dext_n;
+            uint32_t mask1[4], mask2[4];
+            // ---- step 0: x -> A (group 0) ----
+            if (g == 0) {
+                const uint32_t it = it0, s = it & 1, ph = (it >> 1) & 1;
                 mbar_wait(BAR(6 + s), ph ^ 1);
-                uint8_t *dst = A_gen + s * STAGE_A;
+                const uint32_t dst = sA + s * STAGE_A;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (live) v = *reinterpret_cast<const float4 *>(p.feats + (size_t)m * 16 + c * 4);
+                    const float4 v = xn[c];
                     const float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
-                    const float4 lo = make_float4(tf32_rna(v.x - hi.x), tf32_rna(v.y - hi.y), tf32_rna(v.z - hi.z), tf32_rna(v.w - hi.w));
-                    *reinterpret_cast<float4 *>(dst + panel_off(row, c)) = hi;
-                    *reinterpret_cast<float4 *>(dst + PANEL_A + panel_off(row, c)) = lo;
+                    st_shared_v4(dst + offc[c], hi.x, hi.y, hi.z, hi.w);
+                    st_shared_v4(dst + PANEL_A + offc[c], tf32_rna(v.x - hi.x), tf32_rna(v.y - hi.y), tf32_rna(v.z - hi.z), tf32_rna(v.w - hi.w));
                 }
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR(4 + s));
-                ++it;
             }
             // ---- steps 1..8: h1 chunks ----
             mbar_wait(BAR(8), tl & 1);
             tc_fence_after();
-            for (int kb = 0; kb < 8; ++kb, ++it) {
-                const uint32_t s = it & 1, ph = (it >> 1) & 1;
+#pragma unroll 1
+            for (int kk = 0; kk < 4; ++kk) {
+                const int kb = 2 * kk + g;
+                const uint32_t it = it0 + 1 + kb, s = it & 1, ph = (it >> 1) & 1;
+                if (q == 0 && lane == 0) NL_STAMP(2 + g, 1 + kb, 0);
                 uint32_t v[32];
                 tmem_ld32(D1 + lane_addr + kb * 32, v);
+                if (q == 0 && lane == 0) NL_STAMP(2 + g, 1 + kb, 4);
                 float h[32];
                 uint32_t mk = 0u;
 #pragma unroll
@@ -552,98 +617,120 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_mlp_tc_train(TrainParams p) {
                     h[i] = on ? t : 0.f;
                     mk |= on ? (1u << i) : 0u;
                 }
-                mask1[kb] = mk;
+                mask1[kk] = mk;
+                if (q == 0 && lane == 0) NL_STAMP(2 + g, 1 + kb, 5);
                 if (WGRAD) store_panel_row(p.act_h1 + ((size_t)(tile * 8 + kb) * TM + row) * 32, row, h);
+                if (q == 0 && lane == 0) NL_STAMP(2 + g, 1 + kb, 1);
                 mbar_wait(BAR(6 + s), ph ^ 1);
-                store_a_row(A_gen + s * STAGE_A, row, h);
+                if (q == 0 && lane == 0) NL_STAMP(2 + g, 1 + kb, 2);
+                store_a_row_fast(sA + s * STAGE_A, offc, h);
+                if (q == 0 && lane == 0) NL_STAMP(2 + g, 1 + kb, 6);
                 fence_proxy_async();
+                if (q == 0 && lane == 0) NL_STAMP(2 + g, 1 + kb, 7);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR(4 + s));
+                if (q == 0 && lane == 0) NL_STAMP(2 + g, 1 + kb, 3);
             }
-            // ---- output layer + loss ----
+            // ---- output layer + loss: each group reduces its 4 column blocks, partial sums exchanged through smem ----
+            if (q == 0 && lane == 0) NL_STAMP(2 + g, 0, 0);
             mbar_wait(BAR(9), tl & 1);
             tc_fence_after();
+            if (q == 0 && lane == 0) NL_STAMP(2 + g, 0, 1);
             float acc4[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int cb = 0; cb < 8; ++cb) {
+#pragma unroll 1
+            for (int kk = 0; kk < 4; ++kk) {
+                const int cb = 2 * kk + g;
+                if (q == 0 && lane == 0) NL_STAMP(2 + g, 0, 2 + kk);
                 uint32_t v[32];
                 tmem_ld32(D2 + lane_addr + cb * 32, v);
                 uint32_t mk = 0u;
+                float h[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     const float t = __uint_as_float(v[i]) + b1s[cb * 32 + i];
                     const bool on = t > 0.f;
                     mk |= on ? (1u << i) : 0u;
-                    acc4[i & 3] = fmaf(on ? t : 0.f, w2s[cb * 32 + i], acc4[i & 3]);
+                    h[i] = on ? t : 0.f;
+                    acc4[i & 3] = fmaf(h[i], w2s[cb * 32 + i], acc4[i & 3]);
                 }
-                mask2[cb] = mk;
+                mask2[kk] = mk;
+                if (WGRAD) store_panel_row(p.act_h2 + ((size_t)(tile * 8 + cb) * TM + row) * 32, row, h);   // for gW2 = sum h2 * dsdf
             }
-            const float sdf = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]) + b2;
+            float *part = sdf_part + (tl & 1) * 256;
+            part[g * 128 + row] = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
+            if (q == 0 && lane == 0) NL_STAMP(2 + g, 0, 6);
+            asm volatile("bar.sync 1, 256;" ::: "memory");          // the 8 epilogue warps
+            if (q == 0 && lane == 0) NL_STAMP(2 + g, 0, 7);
+            const float sdf = (part[row] + part[128 + row]) + b2;
             float dsdf = 0.f;
             if (live) {
-                p.sdf[m] = sdf;
+                if (g == 0) p.sdf[m] = sdf;
                 if (p.dsdf_ext) {
-                    dsdf = p.dsdf_ext[m];
+                    dsdf = dext;
                 } else {
-                    const uint32_t fl = p.s_flag[m];
-                    const int r = p.s_ray[m];
-                    const float cosr = p.cosv ? p.cosv[r] : 1.0f;
-                    const float z = __fmul_rn(p.s_depth[m], cosr);
-                    const float dgt = p.gt_depth[r];
                     if (fl & 1u) {
                         const float e = sdf - 1.0f;
-                        loss_fs += (double)e * (double)e;
+                        if (g == 0) loss_fs += (double)e * (double)e;
                         dsdf += 2.0f * g_fs * e;
                     }
                     if (fl & 2u) {
                         const float e = __fsub_rn(__fadd_rn(z, __fmul_rn(sdf, p.truncation)), dgt);
-                        loss_sdf += (double)e * (double)e;
+                        if (g == 0) loss_sdf += (double)e * (double)e;
                         dsdf += 2.0f * g_sdf * p.truncation * e;
                     }
                 }
             }
-            if (WGRAD) gb2r += dsdf;
-            // ---- steps 9..16: dh2 chunks (registers only; with WGRAD a second pass over D2 gives h2 for gW2) ----
-            for (int jb = 0; jb < 8; ++jb, ++it) {
-                const uint32_t s = it & 1, ph = (it >> 1) & 1;
+            if (WGRAD && g == 0) {
+                gb2r += dsdf;
+                p.act_dsdf[tile * TM + row] = dsdf;
+            }
+            // ---- steps 9..16: dh2 chunks, built from registers ----
+#pragma unroll 1
+            for (int kk = 0; kk < 4; ++kk) {
+                const int jb = 2 * kk + g;
+                const uint32_t it = it0 + 9 + jb, s = it & 1, ph = (it >> 1) & 1;
+                if (q == 0 && lane == 0) NL_STAMP(2 + g, 9 + jb, 0);
                 float h[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) h[i] = ((mask2[jb] >> i) & 1u) ? dsdf * w2s[jb * 32 + i] : 0.f;
-                if (WGRAD) {
-                    store_panel_row(p.act_dh2 + ((size_t)(tile * 8 + jb) * TM + row) * 32, row, h);
-                    uint32_t v[32];
-                    tmem_ld32(D2 + lane_addr + jb * 32, v);
-                    float pr[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) pr[i] = ((mask2[jb] >> i) & 1u) ? (__uint_as_float(v[i]) + b1s[jb * 32 + i]) * dsdf : 0.f;
-                    gW2r[jb] += colsum32(pr, lane);
-                }
+                for (int i = 0; i < 32; ++i) h[i] = ((mask2[kk] >> i) & 1u) ? dsdf * w2s[jb * 32 + i] : 0.f;
+                if (WGRAD) store_panel_row(p.act_dh2 + ((size_t)(tile * 8 + jb) * TM + row) * 32, row, h);
+                if (q == 0 && lane == 0) NL_STAMP(2 + g, 9 + jb, 1);
                 mbar_wait(BAR(6 + s), ph ^ 1);
-                store_a_row(A_gen + s * STAGE_A, row, h);
+                if (q == 0 && lane == 0) NL_STAMP(2 + g, 9 + jb, 2);
+                store_a_row_fast(sA + s * STAGE_A, offc, h);
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR(4 + s));
+                if (q == 0 && lane == 0) NL_STAMP(2 + g, 9 + jb, 3);
             }
+            prefetch(tile + gridDim.x);                 // next tile's x / loss inputs: a whole backward pass to arrive
             // ---- steps 17..24: dh1 (masked) chunks from D3 ----
             mbar_wait(BAR(10), tl & 1);
             tc_fence_after();
-            for (int kb = 0; kb < 8; ++kb, ++it) {
-                const uint32_t s = it & 1, ph = (it >> 1) & 1;
+#pragma unroll 1
+            for (int kk = 0; kk < 4; ++kk) {
+                const int kb = 2 * kk + g;
+                const uint32_t it = it0 + 17 + kb, s = it & 1, ph = (it >> 1) & 1;
+                if (q == 0 && lane == 0) NL_STAMP(2 + g, 17 + kb, 0);
                 uint32_t v[32];
                 tmem_ld32(D1 + lane_addr + kb * 32, v);
                 float h[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) h[i] = ((mask1[kb] >> i) & 1u) ? __uint_as_float(v[i]) : 0.f;
+                for (int i = 0; i < 32; ++i) h[i] = ((mask1[kk] >> i) & 1u) ? __uint_as_float(v[i]) : 0.f;
                 if (WGRAD) store_panel_row(p.act_dh1 + ((size_t)(tile * 8 + kb) * TM + row) * 32, row, h);
+                if (q == 0 && lane == 0) NL_STAMP(2 + g, 17 + kb, 1);
                 mbar_wait(BAR(6 + s), ph ^ 1);
-                store_a_row(A_gen + s * STAGE_A, row, h);
+                if (q == 0 && lane == 0) NL_STAMP(2 + g, 17 + kb, 2);
+                store_a_row_fast(sA + s * STAGE_A, offc, h);
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR(4 + s));
+                if (q == 0 && lane == 0) NL_STAMP(2 + g, 17 + kb, 3);
             }
-            // ---- d loss / d x ----
-            mbar_wait(BAR(11), tl & 1);
-            tc_fence_after();
-            {
+            // ---- d loss / d x (group 0) ----
+            if (g == 0) {
+                mbar_wait(BAR(11), tl & 1);
+                tc_fence_after();
                 uint32_t v[16];
                 tmem_ld16(D2 + lane_addr, v);
                 tc_fence_before();
@@ -658,7 +745,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_mlp_tc_train(TrainParams p) {
                 }
             }
         }
-        if (!p.dsdf_ext) {
+        if (!p.dsdf_ext && g == 0) {
             for (int off = 16; off > 0; off >>= 1) {
                 loss_fs += __shfl_down_sync(0xffffffffu, loss_fs, off);
                 loss_sdf += __shfl_down_sync(0xffffffffu, loss_sdf, off);
@@ -668,16 +755,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_mlp_tc_train(TrainParams p) {
                 if (loss_sdf != 0.0) atomicAdd(&p.stats->sdf_sum, loss_sdf);
             }
         }
-        if (WGRAD) {
-#pragma unroll
-            for (int jb = 0; jb < 8; ++jb) atomicAdd(p.gW2 + jb * 32 + lane, gW2r[jb]);
+        if (WGRAD && g == 0) {
             for (int off = 16; off > 0; off >>= 1) gb2r += __shfl_down_sync(0xffffffffu, gb2r, off);
             if (lane == 0) atomicAdd(p.gb2, gb2r);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 9) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
     }
@@ -830,15 +915,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dw1_tc(long long M_host, const 
     }
 }
 
-// gW0[k][e] += sum_m dh1[m][k] x[m][e],  gb0[k] += sum_m dh1[m][k],  gb1[j] += sum_m dh2[m][j]   (fp32 CUDA cores: 2 KB/sample, HBM-bound)
+// gW0[k][e] += sum_m dh1[m][k] x[m][e],  gb0[k] += sum_m dh1[m][k],  gb1[j] += sum_m dh2[m][j],  gW2[j] += sum_m h2[m][j] dsdf[m]
+// (fp32 CUDA cores: 3 KB/sample, HBM-bound)
 // thread = column k (256 threads); each CTA walks a strided set of samples
 __global__ void __launch_bounds__(256) k_dw0_panels(long long M_host, const int32_t *__restrict__ M_dev, const float *__restrict__ dh1,
-                                                     const float *__restrict__ dh2, const float *__restrict__ x, float *__restrict__ gW0,
-                                                     float *__restrict__ gb0, float *__restrict__ gb1) {
+                                                     const float *__restrict__ dh2, const float *__restrict__ h2, const float *__restrict__ dsdf,
+                                                     const float *__restrict__ x, float *__restrict__ gW0, float *__restrict__ gb0,
+                                                     float *__restrict__ gb1, float *__restrict__ gW2) {
     __shared__ float xs[32][16];
+    __shared__ float ds[32];
     const long long M = M_dev ? min((long long)*M_dev, M_host) : M_host;
     const int k = threadIdx.x;
-    float acc[16], sb0 = 0.f, sb1 = 0.f;
+    float acc[16], sb0 = 0.f, sb1 = 0.f, sw2 = 0.f;
 #pragma unroll
     for (int e = 0; e < 16; ++e) acc[e] = 0.f;
     for (long long m0 = (long long)blockIdx.x * 32; m0 < M; m0 += (long long)gridDim.x * 32) {
@@ -846,23 +934,26 @@ __global__ void __launch_bounds__(256) k_dw0_panels(long long M_host, const int3
             const long long m = m0 + (f >> 4);
             xs[f >> 4][f & 15] = (m < M) ? x[(size_t)m * 16 + (f & 15)] : 0.f;
         }
+        if (threadIdx.x < 32) ds[threadIdx.x] = (m0 + threadIdx.x < M) ? dsdf[m0 + threadIdx.x] : 0.f;
         __syncthreads();
         const int nr = (int)min((long long)32, M - m0);
         for (int r8 = 0; r8 < nr; r8 += 8) {
-            float d1[8], d2[8];
+            float d1[8], d2[8], hh[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {     // 16 independent loads in flight per thread
+            for (int u = 0; u < 8; ++u) {     // 24 independent loads in flight per thread
                 const long long m = m0 + r8 + u;
                 const int rr = (int)(m & 127);
                 const size_t off = (((size_t)(m >> 7) * 8 + (k >> 5)) * TM + rr) * 32 + panel_elem(rr, k & 31);
                 const bool ok = (r8 + u) < nr;
                 d1[u] = ok ? dh1[off] : 0.f;
                 d2[u] = ok ? dh2[off] : 0.f;
+                hh[u] = ok ? h2[off] : 0.f;
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 sb0 += d1[u];
                 sb1 += d2[u];
+                sw2 = fmaf(hh[u], ds[(r8 + u) & 31], sw2);
 #pragma unroll
                 for (int e = 0; e < 16; ++e) acc[e] = fmaf(d1[u], xs[(r8 + u) & 31][e], acc[e]);
             }
@@ -873,6 +964,7 @@ __global__ void __launch_bounds__(256) k_dw0_panels(long long M_host, const int3
     for (int e = 0; e < 16; ++e) atomicAdd(gW0 + k * 16 + e, acc[e]);
     atomicAdd(gb0 + k, sb0);
     atomicAdd(gb1 + k, sb1);
+    atomicAdd(gW2 + k, sw2);
 }
 
 }  // namespace tc
@@ -908,20 +1000,20 @@ extern "C" int nl_mlp_tc_forward(int64_t M, const int32_t *d_M_dev, const float 
     return NL_OK;
 }
 
-extern "C" int64_t nl_mlp_tc_act_floats(int64_t M) { return ((M + tc::TM - 1) / tc::TM) * 8 * tc::TM * 32; }
+extern "C" int64_t nl_mlp_tc_act_floats(int64_t M) { return ((M + tc::TM - 1) / tc::TM) * (4 * 8 * tc::TM * 32 + tc::TM); }
 
 extern "C" int nl_mlp_tc_train(int64_t M, const int32_t *d_M_dev, const float *feats, const void *panels, const float *b0,
                                const float *b1, const float *w2, const float *b2, const uint8_t *s_flag, const float *s_depth,
                                const int32_t *s_ray, const float *cosv, const float *gt_depth, nl_render_stats *stats,
-                               float truncation, float *sdf, float *dfeats, const nl_mlp_grads *grads, float *act_h1, float *act_dh2,
-                               float *act_dh1, const float *dsdf_ext, void *stream_) {
+                               float truncation, float *sdf, float *dfeats, const nl_mlp_grads *grads, float *act,
+                               const float *dsdf_ext, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (M < 0) return nl_set_error("nl_mlp_tc_train: negative M");
     if (M == 0) return NL_OK;
     if (!feats || !panels || !b0 || !b1 || !w2 || !b2 || !sdf || !dfeats) return nl_set_error("nl_mlp_tc_train: null pointer");
     if (!dsdf_ext && (!s_flag || !s_depth || !s_ray || !gt_depth || !stats))
         return nl_set_error("nl_mlp_tc_train: the loss needs s_flag, s_depth, s_ray, gt_depth and stats");
-    if (grads && (!grads->gW0 || !grads->gb0 || !grads->gW1 || !grads->gb1 || !grads->gW2 || !grads->gb2 || !act_h1 || !act_dh2 || !act_dh1))
+    if (grads && (!grads->gW0 || !grads->gb0 || !grads->gW1 || !grads->gb1 || !grads->gW2 || !grads->gb2 || !act))
         return nl_set_error("nl_mlp_tc_train: decoder gradients requested but a buffer is null");
     static bool configured = false;
     if (!configured) {
@@ -939,14 +1031,39 @@ extern "C" int nl_mlp_tc_train(int64_t M, const int32_t *d_M_dev, const float *f
     const long long ntiles = (M + tc::TM - 1) / tc::TM;
     const int sms = nl_num_sms();
     const int grid = (int)(ntiles < (long long)sms ? ntiles : (long long)sms);
+    static long long *dbg_dev = nullptr;
+    static int dbg_calls = 0;
+    const bool want_dbg = getenv("NL_TC_TIMELINE") != nullptr;
+    if (want_dbg && !dbg_dev) { cudaMalloc(&dbg_dev, 4 * 25 * 8 * sizeof(long long)); cudaMemset(dbg_dev, 0, 4 * 25 * 8 * sizeof(long long)); }
+    p.dbg = want_dbg ? dbg_dev : nullptr;
     if (grads) {
-        p.act_h1 = act_h1; p.act_dh2 = act_dh2; p.act_dh1 = act_dh1; p.gW2 = grads->gW2; p.gb2 = grads->gb2;
-        tc::k_mlp_tc_train<true><<<grid, tc::NTHREADS, tc::SMEM_TOTAL, stream>>>(p);
-        tc::k_dw1_tc<<<sms, tc::NTHREADS, tc::DW_SMEM, stream>>>(M, d_M_dev, act_dh2, act_h1, grads->gW1);
-        tc::k_dw0_panels<<<sms * 4, 256, 0, stream>>>(M, d_M_dev, act_dh1, act_dh2, feats, grads->gW0, grads->gb0, grads->gb1);
+        const size_t panel = (size_t)ntiles * 8 * tc::TM * 32;   // capacity-based carve (M is the host-side bound)
+        p.act_h1 = act; p.act_dh2 = act + panel; p.act_dh1 = act + 2 * panel; p.act_h2 = act + 3 * panel; p.act_dsdf = act + 4 * panel;
+        p.gW2 = grads->gW2; p.gb2 = grads->gb2;
+        tc::k_mlp_tc_train<true><<<grid, tc::NTHREADS_TRAIN, tc::SMEM_TOTAL, stream>>>(p);
+        tc::k_dw1_tc<<<sms, tc::NTHREADS, tc::DW_SMEM, stream>>>(M, d_M_dev, p.act_dh2, p.act_h1, grads->gW1);
+        tc::k_dw0_panels<<<sms * 4, 256, 0, stream>>>(M, d_M_dev, p.act_dh1, p.act_dh2, p.act_h2, p.act_dsdf, feats, grads->gW0, grads->gb0,
+                                                      grads->gb1, grads->gW2);
     } else {
-        tc::k_mlp_tc_train<false><<<grid, tc::NTHREADS, tc::SMEM_TOTAL, stream>>>(p);
+        tc::k_mlp_tc_train<false><<<grid, tc::NTHREADS_TRAIN, tc::SMEM_TOTAL, stream>>>(p);
     }
     NL_CHECK_LAUNCH("nl_mlp_tc_train");
+    if (want_dbg && ++dbg_calls == 8) {   // debug only: dump one steady-state tile timeline of CTA 0 (synchronises)
+        long long h[800];
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
+        long long t0 = h[0];
+        for (int i = 0; i < 800; ++i) if (h[i] && h[i] < t0) t0 = h[i];
+        const char *roles[4] = {"producer", "mma", "epi_g0", "epi_g1"};
+        for (int r = 0; r < 4; ++r)
+            for (int st = 0; st < 25; ++st) {
+                long long *q = h + (r * 25 + st) * 8;
+                if (q[0] || q[1] || q[2] || q[3]) {
+                    fprintf(stderr, "TL %-8s step %2d :", roles[r], st);
+                    for (int k = 0; k < 8; ++k) fprintf(stderr, " %7lld", q[k] ? q[k] - t0 : -1);
+                    fprintf(stderr, "\n");
+                }
+            }
+    }
     return NL_OK;
 }

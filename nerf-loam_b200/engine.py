@@ -40,7 +40,7 @@ def mlp_forward(bufs, M_cap, M_dev, feats, sdf):
 def mlp_train(bufs, M_cap, M_dev, feats, sdf, dfeats, want_wgrad, act, s_flag=None, s_depth=None, s_ray=None, cos=None, gt_depth=None,
               stats_ptr=None, truncation=0.0, dsdf_ext=None):
     """Forward + (loss | external d sdf) + backward.  act: dict with scratch tensors for the weight gradients
-    ('h1','dh2' [cap,W] for simt; 'h1','dh2','dh1' panel buffers for tc).  Accumulates into bufs.grads when want_wgrad."""
+    ('h1','dh2' [cap,W] for simt; one 'buf' of nl_mlp_tc_act_floats(cap) floats for tc).  Accumulates into bufs.grads when want_wgrad."""
     lib, st = _capi.lib(), _capi.stream_ptr()
     gs = bufs.grads_struct() if want_wgrad else None
     gp = C.byref(gs) if want_wgrad else None
@@ -49,9 +49,8 @@ def mlp_train(bufs, M_cap, M_dev, feats, sdf, dfeats, want_wgrad, act, s_flag=No
         _capi.check(lib.nl_mlp_tc_train(M_cap, M_dev, _capi.ptr(feats), _capi.ptr(bufs.tc_panels), _capi.ptr(p[1]), _capi.ptr(p[3]),
                                         _capi.ptr(p[4]), _capi.ptr(p[5]), _capi.ptr(s_flag), _capi.ptr(s_depth), _capi.ptr(s_ray),
                                         _capi.ptr(cos), _capi.ptr(gt_depth), stats_ptr, float(truncation), _capi.ptr(sdf),
-                                        _capi.ptr(dfeats), gp, _capi.ptr(act["h1"]) if want_wgrad else None,
-                                        _capi.ptr(act["dh2"]) if want_wgrad else None, _capi.ptr(act["dh1"]) if want_wgrad else None,
-                                        _capi.ptr(dsdf_ext), st), "nl_mlp_tc_train")
+                                        _capi.ptr(dfeats), gp, _capi.ptr(act["buf"]) if want_wgrad else None, _capi.ptr(dsdf_ext), st),
+                    "nl_mlp_tc_train")
         _capi.LAUNCHES += 3 if want_wgrad else 1
     else:
         w = bufs.weights_struct()
@@ -66,7 +65,7 @@ def alloc_act(width, M_cap, device):
     """Scratch for the decoder weight gradients, sized for M_cap samples."""
     if mlp_impl(width) == "tc":
         n = int(_capi.lib().nl_mlp_tc_act_floats(int(M_cap)))
-        return {k: torch.empty(n, dtype=torch.float32, device=device) for k in ("h1", "dh2", "dh1")}
+        return {"buf": torch.empty(n, dtype=torch.float32, device=device)}
     return {k: torch.empty((int(M_cap), width), dtype=torch.float32, device=device) for k in ("h1", "dh2")}
 
 
