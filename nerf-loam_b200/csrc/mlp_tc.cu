@@ -382,7 +382,7 @@ __device__ __forceinline__ void store_panel_row(float *dst, int row, const float
     }
 }
 // float index of element k (0..31) of row r inside such a panel row
-__device__ __forceinline__ int panel_elem(int r, int k) { return ((((k >> 3) ^ (r & 3)) << 3) | (k & 7)); }
+__device__ __forceinline__ int panel_elem(int r, int k) { return ((((k >> 2) ^ (r & 7)) << 2) | (k & 3)); }
 // v[c] of lane l = element (row l, column c) of a 32x32 block; returns on lane l the sum over rows of column l
 __device__ __forceinline__ float colsum32(const float (&v)[32], int lane) {
     float r16[16], r8[8], r4[4], r2[2];
@@ -414,6 +414,14 @@ __device__ __forceinline__ float colsum32(const float (&v)[32], int lane) {
     const float send = up ? r2[0] : r2[1], keep = up ? r2[1] : r2[0];
     return keep + __shfl_xor_sync(0xffffffffu, send, 1);
 }
+
+// smem -> global bulk copy (1-D TMA store) of this warp's rows of an activation panel; one instruction per warp and
+// chunk instead of 8 partially-coalesced STG.128 per thread
+__device__ __forceinline__ void bulk_s2g(void *gdst, uint32_t ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -584,6 +592,7 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
             // ---- step 0: x -> A (group 0) ----
             if (g == 0) {
                 const uint32_t it = it0, s = it & 1, ph = (it >> 1) & 1;
+                if (WGRAD) { if (lane == 0) bulk_wait_read(); __syncwarp(); }
                 mbar_wait(BAR(6 + s), ph ^ 1);
                 const uint32_t dst = sA + s * STAGE_A;
 #pragma unroll
@@ -619,7 +628,7 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
                 }
                 mask1[kk] = mk;
                 if (q == 0 && lane == 0) NL_STAMP(2 + g, 1 + kb, 5);
-                if (WGRAD) store_panel_row(p.act_h1 + ((size_t)(tile * 8 + kb) * TM + row) * 32, row, h);
+                if (WGRAD) { if (lane == 0) bulk_wait_read(); __syncwarp(); }   // previous panel store of this warp left the stage
                 if (q == 0 && lane == 0) NL_STAMP(2 + g, 1 + kb, 1);
                 mbar_wait(BAR(6 + s), ph ^ 1);
                 if (q == 0 && lane == 0) NL_STAMP(2 + g, 1 + kb, 2);
@@ -628,6 +637,7 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
                 fence_proxy_async();
                 if (q == 0 && lane == 0) NL_STAMP(2 + g, 1 + kb, 7);
                 __syncwarp();
+                if (WGRAD && lane == 0) bulk_s2g(p.act_h1 + ((size_t)(tile * 8 + kb) * TM + q * 32) * 32, sA + s * STAGE_A + q * 4096, 4096);
                 if (lane == 0) mbar_arrive(BAR(4 + s));
                 if (q == 0 && lane == 0) NL_STAMP(2 + g, 1 + kb, 3);
             }
@@ -654,7 +664,16 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
                     acc4[i & 3] = fmaf(h[i], w2s[cb * 32 + i], acc4[i & 3]);
                 }
                 mask2[kk] = mk;
-                if (WGRAD) store_panel_row(p.act_h2 + ((size_t)(tile * 8 + cb) * TM + row) * 32, row, h);   // for gW2 = sum h2 * dsdf
+                if (WGRAD) {   // h2 panel (for gW2 = sum h2 * dsdf): staged through this group's idle activation stage
+                    const uint32_t sg = sA + ((it0 + 9 + g) & 1) * STAGE_A;
+                    if (lane == 0) bulk_wait_read();
+                    __syncwarp();
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) st_shared_v4(sg + offc[c], h[c * 4], h[c * 4 + 1], h[c * 4 + 2], h[c * 4 + 3]);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) bulk_s2g(p.act_h2 + ((size_t)(tile * 8 + cb) * TM + q * 32) * 32, sg + q * 4096, 4096);
+                }
             }
             float *part = sdf_part + (tl & 1) * 256;
             part[g * 128 + row] = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
@@ -693,13 +712,14 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
                 float h[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) h[i] = ((mask2[kk] >> i) & 1u) ? dsdf * w2s[jb * 32 + i] : 0.f;
-                if (WGRAD) store_panel_row(p.act_dh2 + ((size_t)(tile * 8 + jb) * TM + row) * 32, row, h);
+                if (WGRAD) { if (lane == 0) bulk_wait_read(); __syncwarp(); }
                 if (q == 0 && lane == 0) NL_STAMP(2 + g, 9 + jb, 1);
                 mbar_wait(BAR(6 + s), ph ^ 1);
                 if (q == 0 && lane == 0) NL_STAMP(2 + g, 9 + jb, 2);
                 store_a_row_fast(sA + s * STAGE_A, offc, h);
                 fence_proxy_async();
                 __syncwarp();
+                if (WGRAD && lane == 0) bulk_s2g(p.act_dh2 + ((size_t)(tile * 8 + jb) * TM + q * 32) * 32, sA + s * STAGE_A + q * 4096, 4096);
                 if (lane == 0) mbar_arrive(BAR(4 + s));
                 if (q == 0 && lane == 0) NL_STAMP(2 + g, 9 + jb, 3);
             }
@@ -717,15 +737,20 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
                 float h[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) h[i] = ((mask1[kk] >> i) & 1u) ? __uint_as_float(v[i]) : 0.f;
-                if (WGRAD) store_panel_row(p.act_dh1 + ((size_t)(tile * 8 + kb) * TM + row) * 32, row, h);
+                if (WGRAD) { if (lane == 0) bulk_wait_read(); __syncwarp(); }
                 if (q == 0 && lane == 0) NL_STAMP(2 + g, 17 + kb, 1);
                 mbar_wait(BAR(6 + s), ph ^ 1);
                 if (q == 0 && lane == 0) NL_STAMP(2 + g, 17 + kb, 2);
                 store_a_row_fast(sA + s * STAGE_A, offc, h);
                 fence_proxy_async();
                 __syncwarp();
+                if (WGRAD && lane == 0) bulk_s2g(p.act_dh1 + ((size_t)(tile * 8 + kb) * TM + q * 32) * 32, sA + s * STAGE_A + q * 4096, 4096);
                 if (lane == 0) mbar_arrive(BAR(4 + s));
                 if (q == 0 && lane == 0) NL_STAMP(2 + g, 17 + kb, 3);
+            }
+            if (WGRAD) {   // stages change hands between the groups at the tile boundary: all panel stores must have left smem
+                if (lane == 0) bulk_wait_read();
+                asm volatile("bar.sync 2, 256;" ::: "memory");
             }
             // ---- d loss / d x (group 0) ----
             if (g == 0) {
@@ -759,6 +784,7 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
             for (int off = 16; off > 0; off >>= 1) gb2r += __shfl_down_sync(0xffffffffu, gb2r, off);
             if (lane == 0) atomicAdd(p.gb2, gb2r);
         }
+        if (WGRAD && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // panel stores complete before exit
     }
     tc_fence_before();
     __syncthreads();
@@ -780,8 +806,8 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
 constexpr int DW_KROWS = 16;
 constexpr int DW_PANEL = DW_KROWS * 128;        // 2 KB: 16 sample rows x 128 B
 constexpr int DW_OPER = 8 * DW_PANEL;           // 16 KB: all 256 columns of one operand
-constexpr int DW_STAGE = 4 * DW_OPER;           // A raw | B raw | A lo | B lo
-constexpr int DW_NSTAGE = 3;
+constexpr int DW_STAGE = 6 * DW_OPER;           // A raw | B raw (SW128 K-major images as stored) | A hi | B hi | A lo | B lo (BASE32B MN-major)
+constexpr int DW_NSTAGE = 2;
 constexpr int DW_SMEM = DW_NSTAGE * DW_STAGE + 1024 + 1024;
 
 // MN-major SWIZZLE_128B_BASE32B descriptor (layout type 1): LBO = byte stride between 32-element MN groups (= one 2 KB
@@ -797,7 +823,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dw1_tc(long long M_host, const 
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t *sm = smem_raw + (base - raw);
     uint64_t *bars = reinterpret_cast<uint64_t *>(sm + DW_NSTAGE * DW_STAGE);
-    // barriers: 0..2 raw_full  3..5 conv_done  6..8 stage_empty  9 d_full
+    // barriers: 0..1 raw_full  3..4 conv_done  6..7 stage_empty  9 d_full
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * i; };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 12);
@@ -845,7 +871,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dw1_tc(long long M_host, const 
                 const uint32_t s = it % DW_NSTAGE, ph = (it / DW_NSTAGE) & 1;
                 mbar_wait(BAR(3 + s), ph);
                 tc_fence_after();
-                const uint32_t a_raw = base + s * DW_STAGE, b_raw = a_raw + DW_OPER, a_lo = a_raw + 2 * DW_OPER, b_lo = a_raw + 3 * DW_OPER;
+                const uint32_t a_raw = base + s * DW_STAGE + 2 * DW_OPER, b_raw = a_raw + DW_OPER, a_lo = a_raw + 2 * DW_OPER, b_lo = a_raw + 3 * DW_OPER;
 #pragma unroll
                 for (int jt = 0; jt < 2; ++jt) {
                     uint32_t acc = it > 0 ? 1u : 0u;
@@ -865,23 +891,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dw1_tc(long long M_host, const 
             tc_commit(BAR(9));
         }
     } else {
-        // converters: lo = tf32_rna(x - trunc_tf32(x)) for both operands of the stage (8192 floats, 128 threads)
+        // converters (128 threads): re-swizzle the stored K-major SWIZZLE_128B images (16 B chunk c of row r at c ^ (r & 7))
+        // into the MN-major SWIZZLE_128B_BASE32B tiles the tensor core needs for tf32 (32 B chunk c of row r at c ^ (r & 3)):
+        // hi = the fp32 bits (truncated to tf32 by the hardware), lo = tf32(x - trunc(x))
         const int ct = tid - 64;
         uint32_t it = 0;
         for (long long kb = blockIdx.x; kb < nkb; kb += gridDim.x, ++it) {
             const uint32_t s = it % DW_NSTAGE, ph = (it / DW_NSTAGE) & 1;
             mbar_wait(BAR(0 + s), ph);
-            float4 *src = reinterpret_cast<float4 *>(sm + s * DW_STAGE);
-            float4 *dst = reinterpret_cast<float4 *>(sm + s * DW_STAGE + 2 * DW_OPER);
+            const float4 *src = reinterpret_cast<const float4 *>(sm + s * DW_STAGE);
+            float4 *hi = reinterpret_cast<float4 *>(sm + s * DW_STAGE + 2 * DW_OPER);
+            float4 *lo = reinterpret_cast<float4 *>(sm + s * DW_STAGE + 4 * DW_OPER);
+            const int r0 = (int)(kb & 7) * DW_KROWS;             // first sample row (inside its 128-row tile) of this K-block
 #pragma unroll 4
-            for (int f = ct; f < 2 * DW_OPER / 16; f += 128) {
+            for (int f = ct; f < 2 * DW_OPER / 16; f += 128) {   // f: float4 index = (operand*8 + panel, local row, stored chunk)
+                const int pnl = f >> 7, lr = (f >> 3) & 15, p16 = f & 7;
+                const int r = r0 + lr;
+                const int c16 = p16 ^ (r & 7);                   // logical 16 B chunk
+                const int d16 = (((c16 >> 1) ^ (r & 3)) << 1) | (c16 & 1);
                 const float4 v = src[f];
                 float4 l;
                 l.x = tf32_rna(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u));
                 l.y = tf32_rna(v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u));
                 l.z = tf32_rna(v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u));
                 l.w = tf32_rna(v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
-                dst[f] = l;
+                const int o = (pnl << 7) | (lr << 3) | d16;
+                hi[o] = v;
+                lo[o] = l;
             }
             fence_proxy_async();
             __syncwarp();
@@ -917,18 +953,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dw1_tc(long long M_host, const 
 
 // gW0[k][e] += sum_m dh1[m][k] x[m][e],  gb0[k] += sum_m dh1[m][k],  gb1[j] += sum_m dh2[m][j],  gW2[j] += sum_m h2[m][j] dsdf[m]
 // (fp32 CUDA cores: 3 KB/sample, HBM-bound)
-// thread = column k (256 threads); each CTA walks a strided set of samples
-__global__ void __launch_bounds__(256) k_dw0_panels(long long M_host, const int32_t *__restrict__ M_dev, const float *__restrict__ dh1,
+// thread = (4 consecutive columns cg = tid & 63, row lane rl = tid >> 6); 16-byte loads, 4 rows (12 loads) in flight per thread, 2 CTAs per SM
+__global__ void __launch_bounds__(256, 2) k_dw0_panels(long long M_host, const int32_t *__restrict__ M_dev, const float *__restrict__ dh1,
                                                      const float *__restrict__ dh2, const float *__restrict__ h2, const float *__restrict__ dsdf,
                                                      const float *__restrict__ x, float *__restrict__ gW0, float *__restrict__ gb0,
                                                      float *__restrict__ gb1, float *__restrict__ gW2) {
     __shared__ float xs[32][16];
     __shared__ float ds[32];
     const long long M = M_dev ? min((long long)*M_dev, M_host) : M_host;
-    const int k = threadIdx.x;
-    float acc[16], sb0 = 0.f, sb1 = 0.f, sw2 = 0.f;
+    const int cg = threadIdx.x & 63, rl = threadIdx.x >> 6;      // columns 4cg..4cg+3; rows rl, rl+4, ...
+    const int pnl = cg >> 3, c16 = cg & 7;
+    float acc[4][16], sb0[4] = {0.f, 0.f, 0.f, 0.f}, sb1[4] = {0.f, 0.f, 0.f, 0.f}, sw2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int e = 0; e < 16; ++e) acc[c][e] = 0.f;
     for (long long m0 = (long long)blockIdx.x * 32; m0 < M; m0 += (long long)gridDim.x * 32) {
         for (int f = threadIdx.x; f < 32 * 16; f += 256) {
             const long long m = m0 + (f >> 4);
@@ -936,35 +975,49 @@ __global__ void __launch_bounds__(256) k_dw0_panels(long long M_host, const int3
         }
         if (threadIdx.x < 32) ds[threadIdx.x] = (m0 + threadIdx.x < M) ? dsdf[m0 + threadIdx.x] : 0.f;
         __syncthreads();
-        const int nr = (int)min((long long)32, M - m0);
-        for (int r8 = 0; r8 < nr; r8 += 8) {
-            float d1[8], d2[8], hh[8];
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+        float4 d1[4], d2[4], hh[4];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {     // 24 independent loads in flight per thread
-                const long long m = m0 + r8 + u;
-                const int rr = (int)(m & 127);
-                const size_t off = (((size_t)(m >> 7) * 8 + (k >> 5)) * TM + rr) * 32 + panel_elem(rr, k & 31);
-                const bool ok = (r8 + u) < nr;
-                d1[u] = ok ? dh1[off] : 0.f;
-                d2[u] = ok ? dh2[off] : 0.f;
-                hh[u] = ok ? h2[off] : 0.f;
+        for (int u = 0; u < 4; ++u) {     // 12 independent 16-byte loads in flight per thread
+            const int r = rl + 4 * (u + 4 * half);
+            const long long m = m0 + r;
+            const int rr = (int)(m & 127);
+            const size_t off = (((size_t)(m >> 7) * 8 + pnl) * TM + rr) * 32 + ((c16 ^ (rr & 7)) << 2);
+            const bool ok = m < M;
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            d1[u] = ok ? *reinterpret_cast<const float4 *>(dh1 + off) : z4;
+            d2[u] = ok ? *reinterpret_cast<const float4 *>(dh2 + off) : z4;
+            hh[u] = ok ? *reinterpret_cast<const float4 *>(h2 + off) : z4;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int r = rl + 4 * (u + 4 * half);
+            const float a[4] = {d1[u].x, d1[u].y, d1[u].z, d1[u].w};
+            const float b[4] = {d2[u].x, d2[u].y, d2[u].z, d2[u].w};
+            const float hv[4] = {hh[u].x, hh[u].y, hh[u].z, hh[u].w};
+            const float dv = ds[r];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                sb0[c] += a[c];
+                sb1[c] += b[c];
+                sw2[c] = fmaf(hv[c], dv, sw2[c]);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) acc[c][e] = fmaf(a[c], xs[r][e], acc[c][e]);
             }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                sb0 += d1[u];
-                sb1 += d2[u];
-                sw2 = fmaf(hh[u], ds[(r8 + u) & 31], sw2);
-#pragma unroll
-                for (int e = 0; e < 16; ++e) acc[e] = fmaf(d1[u], xs[(r8 + u) & 31][e], acc[e]);
-            }
+        }
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int e = 0; e < 16; ++e) atomicAdd(gW0 + k * 16 + e, acc[e]);
-    atomicAdd(gb0 + k, sb0);
-    atomicAdd(gb1 + k, sb1);
-    atomicAdd(gW2 + k, sw2);
+    for (int c = 0; c < 4; ++c) {
+        const int k = cg * 4 + c;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) atomicAdd(gW0 + k * 16 + e, acc[c][e]);
+        atomicAdd(gb0 + k, sb0[c]);
+        atomicAdd(gb1 + k, sb1[c]);
+        atomicAdd(gW2 + k, sw2[c]);
+    }
 }
 
 }  // namespace tc
@@ -1042,7 +1095,7 @@ extern "C" int nl_mlp_tc_train(int64_t M, const int32_t *d_M_dev, const float *f
         p.gW2 = grads->gW2; p.gb2 = grads->gb2;
         tc::k_mlp_tc_train<true><<<grid, tc::NTHREADS_TRAIN, tc::SMEM_TOTAL, stream>>>(p);
         tc::k_dw1_tc<<<sms, tc::NTHREADS, tc::DW_SMEM, stream>>>(M, d_M_dev, p.act_dh2, p.act_h1, grads->gW1);
-        tc::k_dw0_panels<<<sms * 4, 256, 0, stream>>>(M, d_M_dev, p.act_dh1, p.act_dh2, p.act_h2, p.act_dsdf, feats, grads->gW0, grads->gb0,
+        tc::k_dw0_panels<<<sms * 6, 256, 0, stream>>>(M, d_M_dev, p.act_dh1, p.act_dh2, p.act_h2, p.act_dsdf, feats, grads->gW0, grads->gb0,
                                                       grads->gb1, grads->gW2);
     } else {
         tc::k_mlp_tc_train<false><<<grid, tc::NTHREADS_TRAIN, tc::SMEM_TOTAL, stream>>>(p);

@@ -92,37 +92,65 @@ enum { SCAN_HITS = 0, SCAN_SAMPLES = 1 };
 template <int MODE>
 __global__ void __launch_bounds__(1024) k_scan(int n, const int32_t *__restrict__ in, int32_t *__restrict__ out,
                                                 int32_t *__restrict__ hitray, nl_render_stats *stats, int sample_capacity) {
-    __shared__ int part[1024];
-    const int t = threadIdx.x;
-    const int per = (n + 1023) / 1024;
-    const int lo = min(n, t * per), hi = min(n, lo + per);
-    int s = 0;
-    for (int i = lo; i < hi; ++i) s += (MODE == SCAN_HITS) ? (in[i] > 0) : in[i];
-    part[t] = s;
+    // tiles of 4096 elements: every thread owns 4 consecutive ones (coalesced 16-byte accesses), warp shuffle scan,
+    // 32 warp totals scanned by warp 0, running carry across tiles
+    __shared__ int wsum[32];
+    __shared__ int carry_s;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (t == 0) carry_s = 0;
     __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {  // Hillis-Steele inclusive scan
-        int v = (t >= off) ? part[t - off] : 0;
-        __syncthreads();
-        part[t] += v;
-        __syncthreads();
-    }
-    int run = part[t] - s;
-    for (int i = lo; i < hi; ++i) {
-        if (MODE == SCAN_HITS) {
-            const bool h = in[i] > 0;
-            out[i] = h ? run : -1;
-            if (h) { hitray[run] = i; ++run; }
-        } else {
-            out[i] = run;
-            run += in[i];
+    for (int base = 0; base < n; base += 4096) {
+        const int i0 = base + t * 4;
+        int v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int x = (i0 + k < n) ? in[i0 + k] : 0;
+            v[k] = (MODE == SCAN_HITS) ? (x > 0) : x;
         }
+        const int mine = v[0] + v[1] + v[2] + v[3];
+        int incl = mine;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += y;
+        }
+        if (lane == 31) wsum[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+            int ws = wsum[lane], wi = ws;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, wi, off);
+                if (lane >= off) wi += y;
+            }
+            wsum[lane] = wi - ws;   // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        int run = carry + wsum[w] + incl - mine;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i0 + k < n) {
+                if (MODE == SCAN_HITS) {
+                    out[i0 + k] = v[k] ? run : -1;
+                    if (v[k]) hitray[run] = i0 + k;
+                } else {
+                    out[i0 + k] = run;
+                }
+            }
+            run += v[k];
+        }
+        __syncthreads();
+        if (t == 1023) carry_s = run;   // thread 1023's running value = carry + tile total
+        __syncthreads();
     }
-    if (t == 1023) {
+    if (t == 0) {
+        const int total = carry_s;
         if (MODE == SCAN_HITS) {
-            stats->n_hit_rays = part[1023];
+            stats->n_hit_rays = total;
         } else {
-            stats->n_samples = part[1023];
-            if (part[1023] > sample_capacity) atomicOr(&stats->error, 2);
+            stats->n_samples = total;
+            if (total > sample_capacity) atomicOr(&stats->error, 2);
         }
     }
 }
