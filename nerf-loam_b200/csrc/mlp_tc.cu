@@ -929,9 +929,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dw1_tc(long long M_host, const 
             tc_fence_after();
             const int q = warp & 3;
             const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-            for (int jt = 0; jt < 2; ++jt) {
+            // all CTAs finish at about the same time: start each one at a different (accumulator, column block) so the
+            // 148 partial sums do not hammer the same L2 lines simultaneously
+            for (int jj = 0; jj < 2; ++jj) {
+                const int jt = (jj + (blockIdx.x >> 3)) & 1;
                 const int j = jt * 128 + q * 32 + lane;
-                for (int cb = 0; cb < 8; ++cb) {
+                for (int cc = 0; cc < 8; ++cc) {
+                    const int cb = (cc + blockIdx.x) & 7;
                     uint32_t v[32];
                     tmem_ld32(tmem + lane_addr + jt * 256 + cb * 32, v);
                     float4 *o = reinterpret_cast<float4 *>(gW1 + (size_t)j * WN + cb * 32);
@@ -1009,14 +1013,38 @@ __global__ void __launch_bounds__(256, 2) k_dw0_panels(long long M_host, const i
         }
         __syncthreads();
     }
+    // reduce the 4 row lanes of every column group in shared memory, then one atomic per output element and CTA
+    __shared__ float red[64][4 * 19 + 1];
+    for (int pass = 1; pass < 4; ++pass) {
+        __syncthreads();
+        if (rl == pass) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        const int k = cg * 4 + c;
+            for (int c = 0; c < 4; ++c) {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) atomicAdd(gW0 + k * 16 + e, acc[c][e]);
-        atomicAdd(gb0 + k, sb0[c]);
-        atomicAdd(gb1 + k, sb1[c]);
-        atomicAdd(gW2 + k, sw2[c]);
+                for (int e = 0; e < 16; ++e) red[cg][c * 19 + e] = acc[c][e];
+                red[cg][c * 19 + 16] = sb0[c]; red[cg][c * 19 + 17] = sb1[c]; red[cg][c * 19 + 18] = sw2[c];
+            }
+        }
+        __syncthreads();
+        if (rl == 0) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) acc[c][e] += red[cg][c * 19 + e];
+                sb0[c] += red[cg][c * 19 + 16]; sb1[c] += red[cg][c * 19 + 17]; sw2[c] += red[cg][c * 19 + 18];
+            }
+        }
+    }
+    if (rl == 0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int k = cg * 4 + c;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) atomicAdd(gW0 + k * 16 + e, acc[c][e]);
+            atomicAdd(gb0 + k, sb0[c]);
+            atomicAdd(gb1 + k, sb1[c]);
+            atomicAdd(gW2 + k, sw2[c]);
+        }
     }
 }
 
@@ -1095,7 +1123,7 @@ extern "C" int nl_mlp_tc_train(int64_t M, const int32_t *d_M_dev, const float *f
         p.gW2 = grads->gW2; p.gb2 = grads->gb2;
         tc::k_mlp_tc_train<true><<<grid, tc::NTHREADS_TRAIN, tc::SMEM_TOTAL, stream>>>(p);
         tc::k_dw1_tc<<<sms, tc::NTHREADS, tc::DW_SMEM, stream>>>(M, d_M_dev, p.act_dh2, p.act_h1, grads->gW1);
-        tc::k_dw0_panels<<<sms * 6, 256, 0, stream>>>(M, d_M_dev, p.act_dh1, p.act_dh2, p.act_h2, p.act_dsdf, feats, grads->gW0, grads->gb0,
+        tc::k_dw0_panels<<<sms * 2, 256, 0, stream>>>(M, d_M_dev, p.act_dh1, p.act_dh2, p.act_h2, p.act_dsdf, feats, grads->gW0, grads->gb0,
                                                       grads->gb1, grads->gW2);
     } else {
         tc::k_mlp_tc_train<false><<<grid, tc::NTHREADS_TRAIN, tc::SMEM_TOTAL, stream>>>(p);

@@ -44,7 +44,7 @@ __device__ __forceinline__ int warp_max(int v) { return __reduce_max_sync(0xffff
 // ------------------------------------------------------------------------------------------------
 // k_traverse_sort: svo_intersect + ray_intersect (voxel_helpers.py:530-567) for one ray per thread.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_traverse_sort(int R, float voxel_size, float max_distance,
+__global__ void __launch_bounds__(64) k_traverse_sort(int R, float voxel_size, float max_distance,
                                                         const float *__restrict__ centres,
                                                         const int32_t *__restrict__ structure,
                                                         const float *__restrict__ ray_o, const float *__restrict__ ray_d,
@@ -382,7 +382,7 @@ extern "C" int nl_render_samples(const nl_render_args *a, void *stream_) {
     Workspace ws = carve(a->d_workspace, R);
     cudaMemsetAsync(a->d_stats, 0, sizeof(nl_render_stats), stream);
     const int blocks = nl_div_up(R, 128);
-    k_traverse_sort<<<blocks, 128, 0, stream>>>(R, a->voxel_size, a->max_distance, a->d_centres, a->d_structure, a->d_ray_o,
+    k_traverse_sort<<<nl_div_up(R, 64), 64, 0, stream>>>(R, a->voxel_size, a->max_distance, a->d_centres, a->d_structure, a->d_ray_o,
                                                 a->d_ray_d, ws, a->d_ray_nsamp, a->d_stats);
     k_scan<SCAN_HITS><<<1, 1024, 0, stream>>>(R, ws.nvalid, a->d_hit_rank, ws.hitray, a->d_stats, 0);
     SampleParams p;
