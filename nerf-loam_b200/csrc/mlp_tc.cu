@@ -806,9 +806,10 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
 constexpr int DW_KROWS = 16;
 constexpr int DW_PANEL = DW_KROWS * 128;        // 2 KB: 16 sample rows x 128 B
 constexpr int DW_OPER = 8 * DW_PANEL;           // 16 KB: all 256 columns of one operand
-constexpr int DW_STAGE = 6 * DW_OPER;           // A raw | B raw (SW128 K-major images as stored) | A hi | B hi | A lo | B lo (BASE32B MN-major)
-constexpr int DW_NSTAGE = 2;
-constexpr int DW_SMEM = DW_NSTAGE * DW_STAGE + 1024 + 1024;
+constexpr int DW_RAW = 2 * DW_OPER;             // 32 KB: A raw | B raw (K-major SWIZZLE_128B images exactly as stored in HBM)
+constexpr int DW_CONV = 4 * DW_OPER;            // 64 KB: A hi | B hi | A lo | B lo (MN-major SWIZZLE_128B_BASE32B)
+constexpr int DW_NRAW = 3, DW_NCONV = 2;        // the loads run 3 K-blocks ahead of the converters, those 2 ahead of the MMAs
+constexpr int DW_SMEM = DW_NRAW * DW_RAW + DW_NCONV * DW_CONV + 1024 + 1024;
 
 // MN-major SWIZZLE_128B_BASE32B descriptor (layout type 1): LBO = byte stride between 32-element MN groups (= one 2 KB
 // panel), SBO = byte stride between groups of 4 K rows (512 B); one k-step (K = 8) spans two such groups
@@ -822,8 +823,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dw1_tc(long long M_host, const 
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t *sm = smem_raw + (base - raw);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + DW_NSTAGE * DW_STAGE);
-    // barriers: 0..1 raw_full  3..4 conv_done  6..7 stage_empty  9 d_full
+    const uint32_t sRaw = base, sConv = base + DW_NRAW * DW_RAW;
+    uint8_t *raw_gen = sm, *conv_gen = sm + DW_NRAW * DW_RAW;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + DW_NRAW * DW_RAW + DW_NCONV * DW_CONV);
+    // barriers: 0..2 raw_full  3..5 raw_empty  6..7 conv_full  8..9 conv_empty  10 d_full
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * i; };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 12);
@@ -831,8 +834,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dw1_tc(long long M_host, const 
     const long long M = M_dev ? min((long long)*M_dev, M_host) : M_host;
     const long long nkb = ((M + TM - 1) / TM) * (TM / DW_KROWS);   // K-blocks of 16 rows (whole tiles: padded rows hold dh2 = 0)
     if (tid == 0) {
-        for (int i = 0; i < 3; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), 4); mbar_init(BAR(6 + i), 1); }
-        mbar_init(BAR(9), 1);
+        for (int i = 0; i < 3; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(BAR(6 + i), 4); mbar_init(BAR(8 + i), 1); }
+        mbar_init(BAR(10), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -849,12 +853,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dw1_tc(long long M_host, const 
         if (lane == 0) {
             uint32_t it = 0;
             for (long long kb = blockIdx.x; kb < nkb; kb += gridDim.x, ++it) {
-                const uint32_t s = it % DW_NSTAGE, ph = (it / DW_NSTAGE) & 1;
-                mbar_wait(BAR(6 + s), ph ^ 1);
-                mbar_expect_tx(BAR(0 + s), 2 * DW_OPER);
+                const uint32_t s = it % DW_NRAW, ph = (it / DW_NRAW) & 1;
+                mbar_wait(BAR(3 + s), ph ^ 1);
+                mbar_expect_tx(BAR(0 + s), DW_RAW);
                 const long long tile = kb >> 3;
                 const int r0 = (int)(kb & 7) * DW_KROWS;
-                const uint32_t dst = base + s * DW_STAGE;
+                const uint32_t dst = sRaw + s * DW_RAW;
                 for (int pnl = 0; pnl < 8; ++pnl) {
                     const size_t off = ((size_t)(tile * 8 + pnl) * TM + r0) * 32;
                     bulk_g2s(dst + pnl * DW_PANEL, act_dh2 + off, DW_PANEL, BAR(0 + s));
@@ -868,17 +872,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dw1_tc(long long M_host, const 
             constexpr uint32_t idesc = make_idesc(TM, WN) | (1u << 15) | (1u << 16);
             uint32_t it = 0;
             for (long long kb = blockIdx.x; kb < nkb; kb += gridDim.x, ++it) {
-                const uint32_t s = it % DW_NSTAGE, ph = (it / DW_NSTAGE) & 1;
-                mbar_wait(BAR(3 + s), ph);
+                const uint32_t s = it % DW_NCONV, ph = (it / DW_NCONV) & 1;
+                mbar_wait(BAR(6 + s), ph);
                 tc_fence_after();
-                const uint32_t a_raw = base + s * DW_STAGE + 2 * DW_OPER, b_raw = a_raw + DW_OPER, a_lo = a_raw + 2 * DW_OPER, b_lo = a_raw + 3 * DW_OPER;
+                const uint32_t a_hi = sConv + s * DW_CONV, b_hi = a_hi + DW_OPER, a_lo = a_hi + 2 * DW_OPER, b_lo = a_hi + 3 * DW_OPER;
 #pragma unroll
                 for (int jt = 0; jt < 2; ++jt) {
                     uint32_t acc = it > 0 ? 1u : 0u;
 #pragma unroll
                     for (int term = 0; term < 3; ++term) {
-                        const uint32_t a0 = (term == 2 ? a_lo : a_raw) + jt * 4 * DW_PANEL;
-                        const uint32_t b0 = (term == 1 ? b_lo : b_raw);
+                        const uint32_t a0 = (term == 2 ? a_lo : a_hi) + jt * 4 * DW_PANEL;
+                        const uint32_t b0 = (term == 1 ? b_lo : b_hi);
 #pragma unroll
                         for (int ks = 0; ks < DW_KROWS / 8; ++ks) {
                             mma_tf32(tmem + jt * 256, make_desc_mn(a0 + ks * 1024), make_desc_mn(b0 + ks * 1024), idesc, acc);
@@ -886,9 +890,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dw1_tc(long long M_host, const 
                         }
                     }
                 }
-                tc_commit(BAR(6 + s));
+                tc_commit(BAR(8 + s));
             }
-            tc_commit(BAR(9));
+            tc_commit(BAR(10));
         }
     } else {
         // converters (128 threads): re-swizzle the stored K-major SWIZZLE_128B images (16 B chunk c of row r at c ^ (r & 7))
@@ -897,14 +901,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dw1_tc(long long M_host, const 
         const int ct = tid - 64;
         uint32_t it = 0;
         for (long long kb = blockIdx.x; kb < nkb; kb += gridDim.x, ++it) {
-            const uint32_t s = it % DW_NSTAGE, ph = (it / DW_NSTAGE) & 1;
-            mbar_wait(BAR(0 + s), ph);
-            const float4 *src = reinterpret_cast<const float4 *>(sm + s * DW_STAGE);
-            float4 *hi = reinterpret_cast<float4 *>(sm + s * DW_STAGE + 2 * DW_OPER);
-            float4 *lo = reinterpret_cast<float4 *>(sm + s * DW_STAGE + 4 * DW_OPER);
+            const uint32_t rs = it % DW_NRAW, rph = (it / DW_NRAW) & 1;
+            const uint32_t cs = it % DW_NCONV, cph = (it / DW_NCONV) & 1;
+            mbar_wait(BAR(0 + rs), rph);          // raw tiles landed
+            mbar_wait(BAR(8 + cs), cph ^ 1);      // converted stage free (its MMAs retired)
+            const float4 *src = reinterpret_cast<const float4 *>(raw_gen + rs * DW_RAW);
+            float4 *hi = reinterpret_cast<float4 *>(conv_gen + cs * DW_CONV);
+            float4 *lo = reinterpret_cast<float4 *>(conv_gen + cs * DW_CONV + 2 * DW_OPER);
             const int r0 = (int)(kb & 7) * DW_KROWS;             // first sample row (inside its 128-row tile) of this K-block
 #pragma unroll 4
-            for (int f = ct; f < 2 * DW_OPER / 16; f += 128) {   // f: float4 index = (operand*8 + panel, local row, stored chunk)
+            for (int f = ct; f < DW_RAW / 16; f += 128) {        // f: float4 index = (operand*8 + panel, local row, stored chunk)
                 const int pnl = f >> 7, lr = (f >> 3) & 15, p16 = f & 7;
                 const int r = r0 + lr;
                 const int c16 = p16 ^ (r & 7);                   // logical 16 B chunk
@@ -921,11 +927,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dw1_tc(long long M_host, const 
             }
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(3 + s));
+            if (lane == 0) { mbar_arrive(BAR(6 + cs)); mbar_arrive(BAR(3 + rs)); }
         }
         // epilogue: thread = row j of each accumulator; add the CTA's partial sums into gW1
         if (has_work) {
-            mbar_wait(BAR(9), 0);
+            mbar_wait(BAR(10), 0);
             tc_fence_after();
             const int q = warp & 3;
             const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
