@@ -204,14 +204,15 @@ NL_API int nl_mlp_train(int64_t M, const int32_t *d_M_dev, const float *d_feats,
 /* Tensor-core (tcgen05 3xTF32) forward for width 256: weights are pre-split into tf32 hi/lo and pre-swizzled
  * into shared-memory panel images by nl_mlp_tc_prepare (nl_mlp_tc_panel_bytes() bytes of device memory). */
 NL_API int64_t nl_mlp_tc_panel_bytes(void);
-NL_API int nl_mlp_tc_prepare(const float *d_W0, const float *d_W1, void *d_panels, void *stream);
+NL_API int nl_mlp_tc_prepare(const float *d_W0, const float *d_W1, const float *d_w2, void *d_panels, void *stream);
 NL_API int nl_mlp_tc_forward(int64_t M, const int32_t *d_M_dev, const float *d_feats, const void *d_panels, const float *d_b0,
                       const float *d_b1, const float *d_w2, const float *d_b2, float *d_sdf, void *stream);
 /* Tensor-core forward + loss + backward (same contract as nl_mlp_train, width 256 only).  With grads != NULL d_act is a
- * scratch buffer of nl_mlp_tc_act_floats(M) floats (internal panel-major activations for the weight-gradient GEMMs). */
+ * scratch buffer of nl_mlp_tc_act_floats(M) floats (internal panel-major activations for the weight-gradient GEMMs).
+ * The panels must have been prepared from the same W0 / W1 / w2 (the backward panels hold diag(w2) W1). */
 NL_API int64_t nl_mlp_tc_act_floats(int64_t M);
-NL_API int nl_mlp_tc_train(int64_t M, const int32_t *d_M_dev, const float *d_feats, const void *d_panels, const float *d_b0,
-                    const float *d_b1, const float *d_w2, const float *d_b2, const uint8_t *d_s_flag, const float *d_s_depth,
+NL_API int nl_mlp_tc_train(int64_t M, const int32_t *d_M_dev, const float *d_feats, const void *d_panels, const float *d_W1,
+                    const float *d_b0, const float *d_b1, const float *d_w2, const float *d_b2, const uint8_t *d_s_flag, const float *d_s_depth,
                     const int32_t *d_s_ray, const float *d_cos, const float *d_gt_depth, nl_render_stats *d_stats, float truncation,
                     float *d_sdf, float *d_dfeats, const nl_mlp_grads *grads, float *d_act, const float *d_dsdf_ext, void *stream);
 /* loss constants from the sample statistics (criterion.py:84-88, 97-100); call after nl_render_samples */

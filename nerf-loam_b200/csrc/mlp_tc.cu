@@ -111,10 +111,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 // K-block, laid out contiguously in global memory so one bulk copy fills a ring stage.
 //   stage 0       : W0  [256 x 16]  (row j, k = e; only the first 64 B of each 128 B row are meaningful)
 //   stage 1 + kb  : W1[:, 32kb : 32kb+32]              forward layer 2
-//   stage 9 + jb  : W1^T[:, 32jb : 32jb+32]            backward layer 2 (d h1 = d h2 . W1)
+//   stage 9 + jb  : (diag(w2) W1)^T[:, 32jb : 32jb+32] backward layer 2 (d h1 = dsdf * relu'(h2) . diag(w2) W1, see k_mlp_tc_train)
 //   stage 17 + kb : W0^T[:, 32kb : 32kb+32] (16 rows)  backward layer 1 (d x  = d h1 . W0)
 // ------------------------------------------------------------------------------------------------
-__global__ void k_tc_prepare(const float *__restrict__ W0, const float *__restrict__ W1, uint8_t *__restrict__ panels) {
+__global__ void k_tc_prepare(const float *__restrict__ W0, const float *__restrict__ W1, const float *__restrict__ w2,
+                             uint8_t *__restrict__ panels) {
     const int stage = blockIdx.y;                         // 0..24
     const int t = blockIdx.x * blockDim.x + threadIdx.x;  // (row, chunk)
     if (t >= WN * 8) return;
@@ -125,9 +126,9 @@ __global__ void k_tc_prepare(const float *__restrict__ W0, const float *__restri
     } else if (stage <= 8) {                              // layer 2:   B[j][k] = W1[j][k],      k in K-block stage-1
         const int k0 = (stage - 1) * 32 + c * 4;
         for (int i = 0; i < 4; ++i) v[i] = W1[(size_t)r * WN + k0 + i];
-    } else if (stage <= 16) {                             // bwd layer 2: B[k][j] = W1[j][k],    j in K-block stage-9
+    } else if (stage <= 16) {                             // bwd layer 2: B[k][j] = w2[j] W1[j][k], j in K-block stage-9
         const int j0 = (stage - 9) * 32 + c * 4;
-        for (int i = 0; i < 4; ++i) v[i] = W1[(size_t)(j0 + i) * WN + r];
+        for (int i = 0; i < 4; ++i) v[i] = __fmul_rn(w2[j0 + i], W1[(size_t)(j0 + i) * WN + r]);
     } else {                                              // bwd layer 1: B[e][k] = W0[k][e],    k in K-block stage-17 (16 rows)
         if (r >= 16) return;
         const int k0 = (stage - 17) * 32 + c * 4;
@@ -324,11 +325,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_mlp_tc_fwd(FwdParams p) {
 //   steps  0      layer 1            D1 = x . W0^T                      (TMEM cols 0..255)
 //          1..8   layer 2            D2 = relu(D1+b0) . W1^T            (TMEM cols 256..511)
 //                 epilogue: sdf = relu(D2+b1).w2 + b2, loss terms, d loss/d sdf (all thread-local: thread = sample)
-//          9..16  backward layer 2   D3 = dh2 . W1   (reuses D1's columns), dh2 = dsdf * w2 * relu'(h2) built in registers
-//          17..24 backward layer 1   D4 = (D3 * relu'(h1)) . W0  (N = 16, reuses D2's first 16 columns) = d loss / d x
-// ReLU masks are 2 x 256 bits per thread in registers.  With WGRAD the kernel also writes h1, dh2 and dh1 (masked)
-// to HBM in 16 KB "panel" blocks [(tile*8 + kblock)][row][32] (perfectly coalesced: a warp writes 4 KB) for the
-// weight-gradient GEMMs, and reduces gW2 / gb2 itself (32x32 register transpose-reduce per K-block).
+//          9..16  backward layer 2   D3 = relu'(h2) . (diag(w2) W1)     (reuses D1's columns)
+//          17..24 backward layer 1   D4 = (dsdf * D3 * relu'(h1)) . W0  (N = 16, reuses D2's first 16 columns) = d loss / d x
+// The output layer has ONE unit, so d h2 = dsdf (per sample) x w2 (per column) x relu'(h2) is rank-1 up to the mask:
+// the per-sample factor is pulled out of the GEMM (applied when D3 is read back), the per-column factor is folded into
+// the weight panels, and the A operand of backward layer 2 is the 0/1 mask itself -- exact in tf32, so that GEMM needs
+// two terms (mask x hi, mask x lo) instead of three and no lo panel.  ReLU masks are 2 x 256 bits per thread in registers.
+// With WGRAD the kernel writes h1 and dh1 to HBM in 16 KB "panel" blocks [(tile*8 + kblock)][row][32] (bulk copies of the
+// A stages) plus the relu'(h2) bits (32 B/sample) and dsdf; the same factorisation lets k_dw1_tc / k_dw0_panels rebuild
+// everything that used to need dh2 and h2 panels (see there).
 // ================================================================================================
 struct TrainParams {
     long long M_host;
@@ -344,9 +349,10 @@ struct TrainParams {
     nl_render_stats *stats;
     float truncation;
     const float *dsdf_ext;
-    float *act_h1, *act_dh2, *act_dh1, *act_h2;   // WGRAD: panel-major [ntiles*8][128][32]
+    float *act_h1, *act_dh1;             // WGRAD: panel-major [ntiles*8][128][32]
     float *act_dsdf;                     // WGRAD: d loss / d sdf per sample [ntiles*128]
-    float *gW2, *gb2;                    // WGRAD
+    uint32_t *act_mask2;                 // WGRAD: relu'(h2) bits per sample [ntiles*128][8], word g*4+kk = columns 32(2kk+g)..+31
+    float *gb2;                          // WGRAD
     long long *dbg;                      // optional timeline stamps (NL_TC_TIMELINE=1), else nullptr
 };
 
@@ -523,8 +529,10 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
                     const uint32_t idesc = (step >= 17) ? idesc16 : idesc256;
                     const int nk = (step == 0) ? 2 : 4;
                     uint32_t acc = (step == 0 || step == 1 || step == 9 || step == 17) ? 0u : 1u;
+                    const int nterm = (step >= 9 && step <= 16) ? 2 : 3;   // the 0/1 mask operand of backward layer 2 has no lo part
 #pragma unroll
                     for (int term = 0; term < 3; ++term) {
+                        if (term >= nterm) break;
                         const uint64_t ad = make_desc(term == 2 ? a_lo : a_hi);
                         const uint64_t bd = make_desc(term == 1 ? b_lo : b_hi);
                         for (int ks = 0; ks < nk; ++ks) {
@@ -654,26 +662,14 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
                 uint32_t v[32];
                 tmem_ld32(D2 + lane_addr + cb * 32, v);
                 uint32_t mk = 0u;
-                float h[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     const float t = __uint_as_float(v[i]) + b1s[cb * 32 + i];
                     const bool on = t > 0.f;
                     mk |= on ? (1u << i) : 0u;
-                    h[i] = on ? t : 0.f;
-                    acc4[i & 3] = fmaf(h[i], w2s[cb * 32 + i], acc4[i & 3]);
+                    acc4[i & 3] = fmaf(on ? t : 0.f, w2s[cb * 32 + i], acc4[i & 3]);
                 }
                 mask2[kk] = mk;
-                if (WGRAD) {   // h2 panel (for gW2 = sum h2 * dsdf): staged through this group's idle activation stage
-                    const uint32_t sg = sA + ((it0 + 9 + g) & 1) * STAGE_A;
-                    if (lane == 0) bulk_wait_read();
-                    __syncwarp();
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) st_shared_v4(sg + offc[c], h[c * 4], h[c * 4 + 1], h[c * 4 + 2], h[c * 4 + 3]);
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) bulk_s2g(p.act_h2 + ((size_t)(tile * 8 + cb) * TM + q * 32) * 32, sg + q * 4096, 4096);
-                }
             }
             float *part = sdf_part + (tl & 1) * 256;
             part[g * 128 + row] = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
@@ -699,9 +695,12 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
                     }
                 }
             }
-            if (WGRAD && g == 0) {
-                gb2r += dsdf;
-                p.act_dsdf[tile * TM + row] = dsdf;
+            if (WGRAD) {
+                if (g == 0) {
+                    gb2r += dsdf;
+                    p.act_dsdf[tile * TM + row] = dsdf;
+                }
+                *reinterpret_cast<uint4 *>(p.act_mask2 + (size_t)(tile * TM + row) * 8 + g * 4) = make_uint4(mask2[0], mask2[1], mask2[2], mask2[3]);
             }
             // ---- steps 9..16: dh2 chunks, built from registers ----
 #pragma unroll 1
@@ -709,17 +708,19 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
                 const int jb = 2 * kk + g;
                 const uint32_t it = it0 + 9 + jb, s = it & 1, ph = (it >> 1) & 1;
                 if (q == 0 && lane == 0) NL_STAMP(2 + g, 9 + jb, 0);
-                float h[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) h[i] = ((mask2[kk] >> i) & 1u) ? dsdf * w2s[jb * 32 + i] : 0.f;
                 if (WGRAD) { if (lane == 0) bulk_wait_read(); __syncwarp(); }
                 if (q == 0 && lane == 0) NL_STAMP(2 + g, 9 + jb, 1);
                 mbar_wait(BAR(6 + s), ph ^ 1);
                 if (q == 0 && lane == 0) NL_STAMP(2 + g, 9 + jb, 2);
-                store_a_row_fast(sA + s * STAGE_A, offc, h);
+                {   // A = relu'(h2) as exact 0/1 tf32 values; dsdf and w2 are folded into the epilogue / the weight panels
+                    const uint32_t mk = mask2[kk], dst = sA + s * STAGE_A;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        st_shared_v4(dst + offc[c], (mk >> (4 * c)) & 1u ? 1.f : 0.f, (mk >> (4 * c + 1)) & 1u ? 1.f : 0.f,
+                                     (mk >> (4 * c + 2)) & 1u ? 1.f : 0.f, (mk >> (4 * c + 3)) & 1u ? 1.f : 0.f);
+                }
                 fence_proxy_async();
                 __syncwarp();
-                if (WGRAD && lane == 0) bulk_s2g(p.act_dh2 + ((size_t)(tile * 8 + jb) * TM + q * 32) * 32, sA + s * STAGE_A + q * 4096, 4096);
                 if (lane == 0) mbar_arrive(BAR(4 + s));
                 if (q == 0 && lane == 0) NL_STAMP(2 + g, 9 + jb, 3);
             }
@@ -736,7 +737,7 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
                 tmem_ld32(D1 + lane_addr + kb * 32, v);
                 float h[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) h[i] = ((mask1[kk] >> i) & 1u) ? __uint_as_float(v[i]) : 0.f;
+                for (int i = 0; i < 32; ++i) h[i] = ((mask1[kk] >> i) & 1u) ? dsdf * __uint_as_float(v[i]) : 0.f;
                 if (WGRAD) { if (lane == 0) bulk_wait_read(); __syncwarp(); }
                 if (q == 0 && lane == 0) NL_STAMP(2 + g, 17 + kb, 1);
                 mbar_wait(BAR(6 + s), ph ^ 1);
@@ -795,20 +796,24 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
 }
 
 // ================================================================================================
-// Weight gradient of the hidden layer on tensor cores:  gW1[j][k] += sum_m dh2[m][j] * h1[m][k]
-//   D (256 x 256, fp32) lives in TMEM for the whole kernel: two M=128 accumulators x 256 columns = all 512 columns.
-//   K = samples, streamed in K-blocks of 16 rows.  Both operands are MN-major: the HBM panels written by
-//   k_mlp_tc_train<true> ([(tile*8+p)][row][32 floats], 128B-swizzled) are bulk-copied unchanged into shared memory
-//   (8 panels x 2 KB per operand and K-block).  fp32 bits are read by the tensor core as tf32 by truncation (= "hi");
-//   4 converter warps compute lo = tf32(x - trunc(x)) into sibling tiles; 3 MMAs terms (hi*hi + hi*lo + lo*hi).
-//   3-stage ring of 64 KB.  Every CTA finally adds its partial 256x256 into gW1 with float4 atomics.
+// Weight gradients of the hidden and output layers on tensor cores.  With m2 = relu'(h2) (0/1) and d = dsdf:
+//   G[j][k]  = sum_s m2[s][j] * (d[s] h1[s][k])                 (256 x 256, fp32 in TMEM: 2 accumulators x 256 columns)
+//   gW1[j][k] += w2[j] G[j][k]                                   (= sum_s dh2[s][j] h1[s][k])
+//   gW2[j]    += sum_k W1[j][k] G[j][k]   (+ b1[j] c[j], added by k_dw0_panels;  = sum_s d[s] h2[s][j] because
+//                                            h2 = m2 * (h1 . W1^T + b1), c[j] = sum_s m2[s][j] d[s])
+//   K = samples, streamed in K-blocks of 16 rows.  Both operands are MN-major (SWIZZLE_128B_BASE32B, the only layout
+//   tcgen05 takes for MN-major tf32).  Per K-block the producer bulk-copies the 16 rows of the h1 panels (16 KB, the
+//   K-major image k_mlp_tc_train stored), 512 B of mask bits and 64 B of dsdf; 4 converter warps expand the bits into
+//   the 0/1 A operand (exact in tf32: one term fewer than 3xTF32) and write hi/lo of d*h1 as the B operand.
+//   4-deep raw ring (17 KB) + 3-deep converted ring (48 KB).  Every CTA finally adds its partial sums with atomics.
 // ================================================================================================
 constexpr int DW_KROWS = 16;
 constexpr int DW_PANEL = DW_KROWS * 128;        // 2 KB: 16 sample rows x 128 B
 constexpr int DW_OPER = 8 * DW_PANEL;           // 16 KB: all 256 columns of one operand
-constexpr int DW_RAW = 2 * DW_OPER;             // 32 KB: A raw | B raw (K-major SWIZZLE_128B images exactly as stored in HBM)
-constexpr int DW_CONV = 4 * DW_OPER;            // 64 KB: A hi | B hi | A lo | B lo (MN-major SWIZZLE_128B_BASE32B)
-constexpr int DW_NRAW = 3, DW_NCONV = 2;        // the loads run 3 K-blocks ahead of the converters, those 2 ahead of the MMAs
+constexpr int DW_BITS = DW_KROWS * 32;          // 512 B of relu'(h2) bits
+constexpr int DW_RAW = DW_OPER + 1024;          // h1 raw (K-major SWIZZLE_128B image as stored in HBM) | bits | dsdf
+constexpr int DW_CONV = 3 * DW_OPER;            // 48 KB: A mask | B hi | B lo (MN-major SWIZZLE_128B_BASE32B)
+constexpr int DW_NRAW = 4, DW_NCONV = 3;
 constexpr int DW_SMEM = DW_NRAW * DW_RAW + DW_NCONV * DW_CONV + 1024 + 1024;
 
 // MN-major SWIZZLE_128B_BASE32B descriptor (layout type 1): LBO = byte stride between 32-element MN groups (= one 2 KB
@@ -817,26 +822,29 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(DW_PANEL >> 4) << 16) | (32ull << 32) | (1ull << 46) | (1ull << 61);
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) k_dw1_tc(long long M_host, const int32_t *__restrict__ M_dev, const float *__restrict__ act_dh2,
-                                                         const float *__restrict__ act_h1, float *__restrict__ gW1) {
+__global__ void __launch_bounds__(NTHREADS, 1) k_dw1_tc(long long M_host, const int32_t *__restrict__ M_dev, const uint32_t *__restrict__ act_mask2,
+                                                         const float *__restrict__ act_dsdf, const float *__restrict__ act_h1,
+                                                         const float *__restrict__ W1, const float *__restrict__ w2, float *__restrict__ gW1,
+                                                         float *__restrict__ gW2) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t *sm = smem_raw + (base - raw);
-    const uint32_t sRaw = base, sConv = base + DW_NRAW * DW_RAW;
-    uint8_t *raw_gen = sm, *conv_gen = sm + DW_NRAW * DW_RAW;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + DW_NRAW * DW_RAW + DW_NCONV * DW_CONV);
-    // barriers: 0..2 raw_full  3..5 raw_empty  6..7 conv_full  8..9 conv_empty  10 d_full
+    // converted stages first: their operand tiles need 1024-byte alignment, the raw stages only 16
+    const uint32_t sConv = base, sRaw = base + DW_NCONV * DW_CONV;
+    uint8_t *conv_gen = sm, *raw_gen = sm + DW_NCONV * DW_CONV;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + DW_NCONV * DW_CONV + DW_NRAW * DW_RAW);
+    // barriers: 0..3 raw_full  4..7 raw_empty  8..10 conv_full  11..13 conv_empty  14 d_full
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * i; };
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 12);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long M = M_dev ? min((long long)*M_dev, M_host) : M_host;
-    const long long nkb = ((M + TM - 1) / TM) * (TM / DW_KROWS);   // K-blocks of 16 rows (whole tiles: padded rows hold dh2 = 0)
+    const long long nkb = ((M + TM - 1) / TM) * (TM / DW_KROWS);   // K-blocks of 16 rows (whole tiles: padded rows have dsdf = 0)
     if (tid == 0) {
-        for (int i = 0; i < 3; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), 4); }
-        for (int i = 0; i < 2; ++i) { mbar_init(BAR(6 + i), 4); mbar_init(BAR(8 + i), 1); }
-        mbar_init(BAR(10), 1);
+        for (int i = 0; i < DW_NRAW; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(4 + i), 4); }
+        for (int i = 0; i < DW_NCONV; ++i) { mbar_init(BAR(8 + i), 4); mbar_init(BAR(11 + i), 1); }
+        mbar_init(BAR(14), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -854,16 +862,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dw1_tc(long long M_host, const 
             uint32_t it = 0;
             for (long long kb = blockIdx.x; kb < nkb; kb += gridDim.x, ++it) {
                 const uint32_t s = it % DW_NRAW, ph = (it / DW_NRAW) & 1;
-                mbar_wait(BAR(3 + s), ph ^ 1);
-                mbar_expect_tx(BAR(0 + s), DW_RAW);
+                mbar_wait(BAR(4 + s), ph ^ 1);
+                mbar_expect_tx(BAR(0 + s), DW_OPER + DW_BITS + DW_KROWS * 4);
                 const long long tile = kb >> 3;
                 const int r0 = (int)(kb & 7) * DW_KROWS;
                 const uint32_t dst = sRaw + s * DW_RAW;
-                for (int pnl = 0; pnl < 8; ++pnl) {
-                    const size_t off = ((size_t)(tile * 8 + pnl) * TM + r0) * 32;
-                    bulk_g2s(dst + pnl * DW_PANEL, act_dh2 + off, DW_PANEL, BAR(0 + s));
-                    bulk_g2s(dst + DW_OPER + pnl * DW_PANEL, act_h1 + off, DW_PANEL, BAR(0 + s));
-                }
+                for (int pnl = 0; pnl < 8; ++pnl)
+                    bulk_g2s(dst + pnl * DW_PANEL, act_h1 + ((size_t)(tile * 8 + pnl) * TM + r0) * 32, DW_PANEL, BAR(0 + s));
+                bulk_g2s(dst + DW_OPER, act_mask2 + (size_t)(tile * TM + r0) * 8, DW_BITS, BAR(0 + s));
+                bulk_g2s(dst + DW_OPER + DW_BITS, act_dsdf + tile * TM + r0, DW_KROWS * 4, BAR(0 + s));
             }
         }
     } else if (warp == 1) {
@@ -873,15 +880,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dw1_tc(long long M_host, const 
             uint32_t it = 0;
             for (long long kb = blockIdx.x; kb < nkb; kb += gridDim.x, ++it) {
                 const uint32_t s = it % DW_NCONV, ph = (it / DW_NCONV) & 1;
-                mbar_wait(BAR(6 + s), ph);
+                mbar_wait(BAR(8 + s), ph);
                 tc_fence_after();
-                const uint32_t a_hi = sConv + s * DW_CONV, b_hi = a_hi + DW_OPER, a_lo = a_hi + 2 * DW_OPER, b_lo = a_hi + 3 * DW_OPER;
+                const uint32_t a_m = sConv + s * DW_CONV, b_hi = a_m + DW_OPER, b_lo = a_m + 2 * DW_OPER;
 #pragma unroll
                 for (int jt = 0; jt < 2; ++jt) {
                     uint32_t acc = it > 0 ? 1u : 0u;
 #pragma unroll
-                    for (int term = 0; term < 3; ++term) {
-                        const uint32_t a0 = (term == 2 ? a_lo : a_hi) + jt * 4 * DW_PANEL;
+                    for (int term = 0; term < 2; ++term) {
+                        const uint32_t a0 = a_m + jt * 4 * DW_PANEL;
                         const uint32_t b0 = (term == 1 ? b_lo : b_hi);
 #pragma unroll
                         for (int ks = 0; ks < DW_KROWS / 8; ++ks) {
@@ -890,32 +897,48 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dw1_tc(long long M_host, const 
                         }
                     }
                 }
-                tc_commit(BAR(8 + s));
+                tc_commit(BAR(11 + s));
             }
-            tc_commit(BAR(10));
+            tc_commit(BAR(14));
         }
     } else {
-        // converters (128 threads): re-swizzle the stored K-major SWIZZLE_128B images (16 B chunk c of row r at c ^ (r & 7))
-        // into the MN-major SWIZZLE_128B_BASE32B tiles the tensor core needs for tf32 (32 B chunk c of row r at c ^ (r & 3)):
-        // hi = the fp32 bits (truncated to tf32 by the hardware), lo = tf32(x - trunc(x))
+        // converters (128 threads).  Stored h1 image: K-major SWIZZLE_128B (16 B chunk c of row r at c ^ (r & 7)); operand
+        // tiles: MN-major SWIZZLE_128B_BASE32B (32 B chunk c of row r at c ^ (r & 3)).  hi = the fp32 bits of d*h1
+        // (truncated to tf32 by the hardware), lo = tf32(x - trunc(x)).
         const int ct = tid - 64;
+        const int m_pnl = ct >> 4, m_lr = ct & 15;                 // mask expansion: one (column block, sample row) per thread
+        const int m_word = (m_pnl & 1) * 4 + (m_pnl >> 1);         // storage order of k_mlp_tc_train: [group][kk]
         uint32_t it = 0;
         for (long long kb = blockIdx.x; kb < nkb; kb += gridDim.x, ++it) {
             const uint32_t rs = it % DW_NRAW, rph = (it / DW_NRAW) & 1;
             const uint32_t cs = it % DW_NCONV, cph = (it / DW_NCONV) & 1;
             mbar_wait(BAR(0 + rs), rph);          // raw tiles landed
-            mbar_wait(BAR(8 + cs), cph ^ 1);      // converted stage free (its MMAs retired)
-            const float4 *src = reinterpret_cast<const float4 *>(raw_gen + rs * DW_RAW);
-            float4 *hi = reinterpret_cast<float4 *>(conv_gen + cs * DW_CONV);
+            mbar_wait(BAR(11 + cs), cph ^ 1);     // converted stage free (its MMAs retired)
+            const uint8_t *rawp = raw_gen + rs * DW_RAW;
+            const float4 *src = reinterpret_cast<const float4 *>(rawp);
+            const uint32_t *bits = reinterpret_cast<const uint32_t *>(rawp + DW_OPER);
+            const float *dsd = reinterpret_cast<const float *>(rawp + DW_OPER + DW_BITS);
+            float4 *am = reinterpret_cast<float4 *>(conv_gen + cs * DW_CONV);
+            float4 *hi = reinterpret_cast<float4 *>(conv_gen + cs * DW_CONV + DW_OPER);
             float4 *lo = reinterpret_cast<float4 *>(conv_gen + cs * DW_CONV + 2 * DW_OPER);
-            const int r0 = (int)(kb & 7) * DW_KROWS;             // first sample row (inside its 128-row tile) of this K-block
+            {
+                const uint32_t mk = bits[m_lr * 8 + m_word];
+#pragma unroll
+                for (int c16 = 0; c16 < 8; ++c16) {
+                    const int d16 = (((c16 >> 1) ^ (m_lr & 3)) << 1) | (c16 & 1);
+                    am[(m_pnl << 7) | (m_lr << 3) | d16] =
+                        make_float4((mk >> (4 * c16)) & 1u ? 1.f : 0.f, (mk >> (4 * c16 + 1)) & 1u ? 1.f : 0.f,
+                                    (mk >> (4 * c16 + 2)) & 1u ? 1.f : 0.f, (mk >> (4 * c16 + 3)) & 1u ? 1.f : 0.f);
+                }
+            }
 #pragma unroll 4
-            for (int f = ct; f < DW_RAW / 16; f += 128) {        // f: float4 index = (operand*8 + panel, local row, stored chunk)
+            for (int f = ct; f < DW_OPER / 16; f += 128) {        // f: float4 index = (panel, local row, stored chunk)
                 const int pnl = f >> 7, lr = (f >> 3) & 15, p16 = f & 7;
-                const int r = r0 + lr;
-                const int c16 = p16 ^ (r & 7);                   // logical 16 B chunk
-                const int d16 = (((c16 >> 1) ^ (r & 3)) << 1) | (c16 & 1);
-                const float4 v = src[f];
+                const int c16 = p16 ^ (lr & 7);                   // logical 16 B chunk (r0 is a multiple of 16: r & 7 == lr & 7)
+                const int d16 = (((c16 >> 1) ^ (lr & 3)) << 1) | (c16 & 1);
+                const float d = dsd[lr];
+                float4 v = src[f];
+                v.x *= d; v.y *= d; v.z *= d; v.w *= d;
                 float4 l;
                 l.x = tf32_rna(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u));
                 l.y = tf32_rna(v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u));
@@ -927,11 +950,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dw1_tc(long long M_host, const 
             }
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) { mbar_arrive(BAR(6 + cs)); mbar_arrive(BAR(3 + rs)); }
+            if (lane == 0) { mbar_arrive(BAR(8 + cs)); mbar_arrive(BAR(4 + rs)); }
         }
-        // epilogue: thread = row j of each accumulator; add the CTA's partial sums into gW1
+        // epilogue: thread = row j of each accumulator; add the CTA's partial sums into gW1 (scaled by w2[j]) and gW2
         if (has_work) {
-            mbar_wait(BAR(10), 0);
+            mbar_wait(BAR(14), 0);
             tc_fence_after();
             const int q = warp & 3;
             const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
@@ -940,16 +963,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dw1_tc(long long M_host, const 
             for (int jj = 0; jj < 2; ++jj) {
                 const int jt = (jj + (blockIdx.x >> 3)) & 1;
                 const int j = jt * 128 + q * 32 + lane;
+                const float w2j = w2[j];
+                float dot = 0.f;
                 for (int cc = 0; cc < 8; ++cc) {
                     const int cb = (cc + blockIdx.x) & 7;
                     uint32_t v[32];
                     tmem_ld32(tmem + lane_addr + jt * 256 + cb * 32, v);
                     float4 *o = reinterpret_cast<float4 *>(gW1 + (size_t)j * WN + cb * 32);
+                    const float4 *wr = reinterpret_cast<const float4 *>(W1 + (size_t)j * WN + cb * 32);
 #pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        atomicAdd(o + c, make_float4(__uint_as_float(v[c * 4]), __uint_as_float(v[c * 4 + 1]), __uint_as_float(v[c * 4 + 2]),
-                                                     __uint_as_float(v[c * 4 + 3])));
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 w = wr[c];
+                        const float g0 = __uint_as_float(v[c * 4]), g1 = __uint_as_float(v[c * 4 + 1]), g2 = __uint_as_float(v[c * 4 + 2]),
+                                    g3 = __uint_as_float(v[c * 4 + 3]);
+                        dot = fmaf(w.x, g0, fmaf(w.y, g1, fmaf(w.z, g2, fmaf(w.w, g3, dot))));
+                        atomicAdd(o + c, make_float4(w2j * g0, w2j * g1, w2j * g2, w2j * g3));
+                    }
                 }
+                atomicAdd(gW2 + j, dot);
             }
         }
     }
@@ -961,19 +992,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dw1_tc(long long M_host, const 
     }
 }
 
-// gW0[k][e] += sum_m dh1[m][k] x[m][e],  gb0[k] += sum_m dh1[m][k],  gb1[j] += sum_m dh2[m][j],  gW2[j] += sum_m h2[m][j] dsdf[m]
-// (fp32 CUDA cores: 3 KB/sample, HBM-bound)
-// thread = (4 consecutive columns cg = tid & 63, row lane rl = tid >> 6); 16-byte loads, 4 rows (12 loads) in flight per thread, 2 CTAs per SM
+// gW0[k][e] += sum_m dh1[m][k] x[m][e],  gb0[k] += sum_m dh1[m][k],  and with c[j] = sum_m relu'(h2)[m][j] dsdf[m]:
+// gb1[j] += w2[j] c[j],  gW2[j] += b1[j] c[j]  (the other part of gW2 comes from k_dw1_tc).  fp32 CUDA cores, HBM-bound
+// (1 KB/sample).  thread = (4 consecutive columns cg = tid & 63, row lane rl = tid >> 6); 8 independent 16-byte loads in
+// flight per thread, 2 CTAs per SM
 __global__ void __launch_bounds__(256, 2) k_dw0_panels(long long M_host, const int32_t *__restrict__ M_dev, const float *__restrict__ dh1,
-                                                     const float *__restrict__ dh2, const float *__restrict__ h2, const float *__restrict__ dsdf,
-                                                     const float *__restrict__ x, float *__restrict__ gW0, float *__restrict__ gb0,
-                                                     float *__restrict__ gb1, float *__restrict__ gW2) {
+                                                     const uint32_t *__restrict__ mask2, const float *__restrict__ dsdf,
+                                                     const float *__restrict__ x, const float *__restrict__ b1, const float *__restrict__ w2,
+                                                     float *__restrict__ gW0, float *__restrict__ gb0, float *__restrict__ gb1,
+                                                     float *__restrict__ gW2) {
     __shared__ float xs[32][16];
     __shared__ float ds[32];
     const long long M = M_dev ? min((long long)*M_dev, M_host) : M_host;
     const int cg = threadIdx.x & 63, rl = threadIdx.x >> 6;      // columns 4cg..4cg+3; rows rl, rl+4, ...
     const int pnl = cg >> 3, c16 = cg & 7;
-    float acc[4][16], sb0[4] = {0.f, 0.f, 0.f, 0.f}, sb1[4] = {0.f, 0.f, 0.f, 0.f}, sw2[4] = {0.f, 0.f, 0.f, 0.f};
+    const int word = (pnl & 1) * 4 + (pnl >> 1), shift = c16 * 4;
+    float acc[4][16], sb0[4] = {0.f, 0.f, 0.f, 0.f}, sc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int c = 0; c < 4; ++c)
 #pragma unroll
@@ -985,50 +1019,44 @@ __global__ void __launch_bounds__(256, 2) k_dw0_panels(long long M_host, const i
         }
         if (threadIdx.x < 32) ds[threadIdx.x] = (m0 + threadIdx.x < M) ? dsdf[m0 + threadIdx.x] : 0.f;
         __syncthreads();
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-        float4 d1[4], d2[4], hh[4];
+        float4 d1[8];
+        uint32_t mk[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {     // 12 independent 16-byte loads in flight per thread
-            const int r = rl + 4 * (u + 4 * half);
+        for (int u = 0; u < 8; ++u) {
+            const int r = rl + 4 * u;
             const long long m = m0 + r;
             const int rr = (int)(m & 127);
             const size_t off = (((size_t)(m >> 7) * 8 + pnl) * TM + rr) * 32 + ((c16 ^ (rr & 7)) << 2);
             const bool ok = m < M;
-            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            d1[u] = ok ? *reinterpret_cast<const float4 *>(dh1 + off) : z4;
-            d2[u] = ok ? *reinterpret_cast<const float4 *>(dh2 + off) : z4;
-            hh[u] = ok ? *reinterpret_cast<const float4 *>(h2 + off) : z4;
+            d1[u] = ok ? *reinterpret_cast<const float4 *>(dh1 + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+            mk[u] = ok ? mask2[(size_t)m * 8 + word] : 0u;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int r = rl + 4 * (u + 4 * half);
+        for (int u = 0; u < 8; ++u) {
+            const int r = rl + 4 * u;
             const float a[4] = {d1[u].x, d1[u].y, d1[u].z, d1[u].w};
-            const float b[4] = {d2[u].x, d2[u].y, d2[u].z, d2[u].w};
-            const float hv[4] = {hh[u].x, hh[u].y, hh[u].z, hh[u].w};
             const float dv = ds[r];
+            const uint32_t mb = mk[u] >> shift;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 sb0[c] += a[c];
-                sb1[c] += b[c];
-                sw2[c] = fmaf(hv[c], dv, sw2[c]);
+                sc[c] += (mb >> c) & 1u ? dv : 0.f;
 #pragma unroll
                 for (int e = 0; e < 16; ++e) acc[c][e] = fmaf(a[c], xs[r][e], acc[c][e]);
             }
         }
-        }
         __syncthreads();
     }
     // reduce the 4 row lanes of every column group in shared memory, then one atomic per output element and CTA
-    __shared__ float red[64][4 * 19 + 1];
+    __shared__ float red[64][4 * 18 + 1];
     for (int pass = 1; pass < 4; ++pass) {
         __syncthreads();
         if (rl == pass) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
 #pragma unroll
-                for (int e = 0; e < 16; ++e) red[cg][c * 19 + e] = acc[c][e];
-                red[cg][c * 19 + 16] = sb0[c]; red[cg][c * 19 + 17] = sb1[c]; red[cg][c * 19 + 18] = sw2[c];
+                for (int e = 0; e < 16; ++e) red[cg][c * 18 + e] = acc[c][e];
+                red[cg][c * 18 + 16] = sb0[c]; red[cg][c * 18 + 17] = sc[c];
             }
         }
         __syncthreads();
@@ -1036,8 +1064,8 @@ __global__ void __launch_bounds__(256, 2) k_dw0_panels(long long M_host, const i
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
 #pragma unroll
-                for (int e = 0; e < 16; ++e) acc[c][e] += red[cg][c * 19 + e];
-                sb0[c] += red[cg][c * 19 + 16]; sb1[c] += red[cg][c * 19 + 17]; sw2[c] += red[cg][c * 19 + 18];
+                for (int e = 0; e < 16; ++e) acc[c][e] += red[cg][c * 18 + e];
+                sb0[c] += red[cg][c * 18 + 16]; sc[c] += red[cg][c * 18 + 17];
             }
         }
     }
@@ -1048,8 +1076,8 @@ __global__ void __launch_bounds__(256, 2) k_dw0_panels(long long M_host, const i
 #pragma unroll
             for (int e = 0; e < 16; ++e) atomicAdd(gW0 + k * 16 + e, acc[c][e]);
             atomicAdd(gb0 + k, sb0[c]);
-            atomicAdd(gb1 + k, sb1[c]);
-            atomicAdd(gW2 + k, sw2[c]);
+            atomicAdd(gb1 + k, w2[k] * sc[c]);
+            atomicAdd(gW2 + k, b1[k] * sc[c]);
         }
     }
 }
@@ -1058,10 +1086,10 @@ __global__ void __launch_bounds__(256, 2) k_dw0_panels(long long M_host, const i
 
 extern "C" int64_t nl_mlp_tc_panel_bytes(void) { return (int64_t)tc::STEPS_TRAIN * tc::STAGE_B; }
 
-extern "C" int nl_mlp_tc_prepare(const float *W0, const float *W1, void *panels, void *stream) {
-    if (!W0 || !W1 || !panels) return nl_set_error("nl_mlp_tc_prepare: null pointer");
+extern "C" int nl_mlp_tc_prepare(const float *W0, const float *W1, const float *w2, void *panels, void *stream) {
+    if (!W0 || !W1 || !w2 || !panels) return nl_set_error("nl_mlp_tc_prepare: null pointer");
     dim3 grid(nl_div_up(tc::WN * 8, 256), tc::STEPS_TRAIN);
-    tc::k_tc_prepare<<<grid, 256, 0, (cudaStream_t)stream>>>(W0, W1, (uint8_t *)panels);
+    tc::k_tc_prepare<<<grid, 256, 0, (cudaStream_t)stream>>>(W0, W1, w2, (uint8_t *)panels);
     NL_CHECK_LAUNCH("nl_mlp_tc_prepare");
     return NL_OK;
 }
@@ -1087,9 +1115,10 @@ extern "C" int nl_mlp_tc_forward(int64_t M, const int32_t *d_M_dev, const float 
     return NL_OK;
 }
 
-extern "C" int64_t nl_mlp_tc_act_floats(int64_t M) { return ((M + tc::TM - 1) / tc::TM) * (4 * 8 * tc::TM * 32 + tc::TM); }
+// per 128-sample tile: h1 and dh1 panels (2 x 128 KB), dsdf (512 B), relu'(h2) bits (4 KB)
+extern "C" int64_t nl_mlp_tc_act_floats(int64_t M) { return ((M + tc::TM - 1) / tc::TM) * (2 * 8 * tc::TM * 32 + tc::TM + tc::TM * 8); }
 
-extern "C" int nl_mlp_tc_train(int64_t M, const int32_t *d_M_dev, const float *feats, const void *panels, const float *b0,
+extern "C" int nl_mlp_tc_train(int64_t M, const int32_t *d_M_dev, const float *feats, const void *panels, const float *W1, const float *b0,
                                const float *b1, const float *w2, const float *b2, const uint8_t *s_flag, const float *s_depth,
                                const int32_t *s_ray, const float *cosv, const float *gt_depth, nl_render_stats *stats,
                                float truncation, float *sdf, float *dfeats, const nl_mlp_grads *grads, float *act,
@@ -1097,7 +1126,7 @@ extern "C" int nl_mlp_tc_train(int64_t M, const int32_t *d_M_dev, const float *f
     cudaStream_t stream = (cudaStream_t)stream_;
     if (M < 0) return nl_set_error("nl_mlp_tc_train: negative M");
     if (M == 0) return NL_OK;
-    if (!feats || !panels || !b0 || !b1 || !w2 || !b2 || !sdf || !dfeats) return nl_set_error("nl_mlp_tc_train: null pointer");
+    if (!feats || !panels || !W1 || !b0 || !b1 || !w2 || !b2 || !sdf || !dfeats) return nl_set_error("nl_mlp_tc_train: null pointer");
     if (!dsdf_ext && (!s_flag || !s_depth || !s_ray || !gt_depth || !stats))
         return nl_set_error("nl_mlp_tc_train: the loss needs s_flag, s_depth, s_ray, gt_depth and stats");
     if (grads && (!grads->gW0 || !grads->gb0 || !grads->gW1 || !grads->gb1 || !grads->gW2 || !grads->gb2 || !act))
@@ -1125,11 +1154,12 @@ extern "C" int nl_mlp_tc_train(int64_t M, const int32_t *d_M_dev, const float *f
     p.dbg = want_dbg ? dbg_dev : nullptr;
     if (grads) {
         const size_t panel = (size_t)ntiles * 8 * tc::TM * 32;   // capacity-based carve (M is the host-side bound)
-        p.act_h1 = act; p.act_dh2 = act + panel; p.act_dh1 = act + 2 * panel; p.act_h2 = act + 3 * panel; p.act_dsdf = act + 4 * panel;
-        p.gW2 = grads->gW2; p.gb2 = grads->gb2;
+        p.act_h1 = act; p.act_dh1 = act + panel; p.act_dsdf = act + 2 * panel;
+        p.act_mask2 = reinterpret_cast<uint32_t *>(act + 2 * panel + (size_t)ntiles * tc::TM);
+        p.gb2 = grads->gb2;
         tc::k_mlp_tc_train<true><<<grid, tc::NTHREADS_TRAIN, tc::SMEM_TOTAL, stream>>>(p);
-        tc::k_dw1_tc<<<sms, tc::NTHREADS, tc::DW_SMEM, stream>>>(M, d_M_dev, p.act_dh2, p.act_h1, grads->gW1);
-        tc::k_dw0_panels<<<sms * 2, 256, 0, stream>>>(M, d_M_dev, p.act_dh1, p.act_dh2, p.act_h2, p.act_dsdf, feats, grads->gW0, grads->gb0,
+        tc::k_dw1_tc<<<sms, tc::NTHREADS, tc::DW_SMEM, stream>>>(M, d_M_dev, p.act_mask2, p.act_dsdf, p.act_h1, W1, w2, grads->gW1, grads->gW2);
+        tc::k_dw0_panels<<<sms * 2, 256, 0, stream>>>(M, d_M_dev, p.act_dh1, p.act_mask2, p.act_dsdf, feats, b1, w2, grads->gW0, grads->gb0,
                                                       grads->gb1, grads->gW2);
     } else {
         tc::k_mlp_tc_train<false><<<grid, tc::NTHREADS_TRAIN, tc::SMEM_TOTAL, stream>>>(p);

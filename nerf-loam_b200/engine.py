@@ -46,7 +46,7 @@ def mlp_train(bufs, M_cap, M_dev, feats, sdf, dfeats, want_wgrad, act, s_flag=No
     gp = C.byref(gs) if want_wgrad else None
     if mlp_impl(bufs.width) == "tc":
         p = bufs.params
-        _capi.check(lib.nl_mlp_tc_train(M_cap, M_dev, _capi.ptr(feats), _capi.ptr(bufs.tc_panels), _capi.ptr(p[1]), _capi.ptr(p[3]),
+        _capi.check(lib.nl_mlp_tc_train(M_cap, M_dev, _capi.ptr(feats), _capi.ptr(bufs.tc_panels), _capi.ptr(p[2]), _capi.ptr(p[1]), _capi.ptr(p[3]),
                                         _capi.ptr(p[4]), _capi.ptr(p[5]), _capi.ptr(s_flag), _capi.ptr(s_depth), _capi.ptr(s_ray),
                                         _capi.ptr(cos), _capi.ptr(gt_depth), stats_ptr, float(truncation), _capi.ptr(sdf),
                                         _capi.ptr(dfeats), gp, _capi.ptr(act["buf"]) if want_wgrad else None, _capi.ptr(dsdf_ext), st),
@@ -144,7 +144,7 @@ class DecoderBuffers:
     def refresh_transposes(self):
         """Re-derive the kernel-side weight images from the parameters (they change every optimiser step)."""
         if self.tc_panels is not None:
-            _capi.check(_capi.lib().nl_mlp_tc_prepare(_capi.ptr(self.params[0]), _capi.ptr(self.params[2]), _capi.ptr(self.tc_panels),
+            _capi.check(_capi.lib().nl_mlp_tc_prepare(_capi.ptr(self.params[0]), _capi.ptr(self.params[2]), _capi.ptr(self.params[4]), _capi.ptr(self.tc_panels),
                                                       _capi.stream_ptr()), "nl_mlp_tc_prepare")
             _capi.LAUNCHES += 1
         else:
