@@ -94,6 +94,31 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc),
         "r"(accumulate) : "memory");
 }
+// One lane of a converged warp.  The single-thread roles (MMA issue, bulk copies) run their loops warp-uniformly and
+// predicate only the issuing instruction: every operand then lives in uniform registers and the compiler emits a plain
+// UTCHMMA / UBLKCP instead of a per-thread serialisation loop (R2UR + ELECT + BRA.U.ANY, ~100 cycles per MMA).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// all MMAs of one K-block: NTERM tf32 terms (hi*hi, hi*lo, lo*hi) x NK k-steps of 8, fully unrolled
+template <int NK, int NTERM>
+__device__ __forceinline__ void issue_kblock(uint32_t d, uint32_t a_hi, uint32_t b_hi, uint32_t idesc, uint32_t acc) {
+    const uint64_t adh = make_desc(a_hi), adl = make_desc(a_hi + PANEL_A), bdh = make_desc(b_hi), bdl = make_desc(b_hi + PANEL_B);
+#pragma unroll
+    for (int term = 0; term < NTERM; ++term) {
+        const uint64_t ad = (term == 2) ? adl : adh, bd = (term == 1) ? bdl : bdh;
+#pragma unroll
+        for (int ks = 0; ks < NK; ++ks) {
+            mma_tf32(d, ad + 2 * ks, bd + 2 * ks, idesc, acc);
+            acc = 1u;
+        }
+    }
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
@@ -192,50 +217,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_mlp_tc_fwd(FwdParams p) {
 
     if (warp == 0) {
         // ===================== producer: weight panels -> ring =====================
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                for (int step = 0; step < STEPS_FWD; ++step, ++it) {
-                    const uint32_t s = it & 1, ph = (it >> 1) & 1;
-                    mbar_wait(BAR(2 + s), ph ^ 1);
+        uint32_t it = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int step = 0; step < STEPS_FWD; ++step, ++it) {
+                const uint32_t s = it & 1, ph = (it >> 1) & 1;
+                mbar_wait(BAR(2 + s), ph ^ 1);
+                if (elect_one()) {
                     mbar_expect_tx(BAR(0 + s), STAGE_B);
                     const uint8_t *src = p.panels + (size_t)step * STAGE_B;
                     bulk_g2s(sB + s * STAGE_B, src, PANEL_B, BAR(0 + s));
                     bulk_g2s(sB + s * STAGE_B + PANEL_B, src + PANEL_B, PANEL_B, BAR(0 + s));
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(TM, WN);
-            uint32_t it = 0, tl = 0;
-            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
-                for (int step = 0; step < STEPS_FWD; ++step, ++it) {
-                    const uint32_t s = it & 1, ph = (it >> 1) & 1;
-                    if (step == 1) mbar_wait(BAR(10), (tl & 1) ^ 1);   // D2 of the previous tile fully read
-                    mbar_wait(BAR(0 + s), ph);                          // weights landed
-                    mbar_wait(BAR(4 + s), ph);                          // activations written
-                    tc_fence_after();
-                    const uint32_t a_hi = sA + s * STAGE_A, a_lo = a_hi + PANEL_A;
-                    const uint32_t b_hi = sB + s * STAGE_B, b_lo = b_hi + PANEL_B;
-                    const uint32_t d = (step == 0) ? D1 : D2;
-                    const int nk = (step == 0) ? 2 : 4;                 // k-steps of 8 (32 B) in this K-block
-                    uint32_t acc = (step <= 1) ? 0u : 1u;               // first MMA of a layer overwrites
-#pragma unroll
-                    for (int term = 0; term < 3; ++term) {
-                        const uint64_t ad = make_desc(term == 2 ? a_lo : a_hi);
-                        const uint64_t bd = make_desc(term == 1 ? b_lo : b_hi);
-                        for (int ks = 0; ks < nk; ++ks) {
-                            mma_tf32(d, ad + 2 * ks, bd + 2 * ks, idesc, acc);
-                            acc = 1u;
-                        }
-                    }
+        // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+        constexpr uint32_t idesc = make_idesc(TM, WN);
+        uint32_t it = 0, tl = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
+            for (int step = 0; step < STEPS_FWD; ++step, ++it) {
+                const uint32_t s = it & 1, ph = (it >> 1) & 1;
+                if (step == 1) mbar_wait(BAR(10), (tl & 1) ^ 1);   // D2 of the previous tile fully read
+                mbar_wait(BAR(0 + s), ph);                          // weights landed
+                mbar_wait(BAR(4 + s), ph);                          // activations written
+                tc_fence_after();
+                const uint32_t a_hi = sA + s * STAGE_A, b_hi = sB + s * STAGE_B;
+                if (elect_one()) {
+                    if (step == 0) issue_kblock<2, 3>(D1, a_hi, b_hi, idesc, 0u);          // K = 16: 2 k-steps of 8
+                    else issue_kblock<4, 3>(D2, a_hi, b_hi, idesc, step == 1 ? 0u : 1u);   // first MMA of a layer overwrites
                     tc_commit(BAR(2 + s));                              // ring stages free once these MMAs retire
                     tc_commit(BAR(6 + s));
                     if (step == 0) tc_commit(BAR(8));                   // D1 complete
                     if (step == STEPS_FWD - 1) tc_commit(BAR(9));       // D2 complete
                 }
+                __syncwarp();
             }
         }
     } else {
@@ -468,7 +484,7 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     long long *dbg = (blockIdx.x == 0) ? p.dbg : nullptr;   // [role 0..3][step 0..24][4 stamps]
-#define NL_STAMP(role, step, k) do { if (dbg && tl == 1) dbg[((role) * 25 + (step)) * 8 + (k)] = clock64(); } while (0)
+#define NL_STAMP(role, step, k) do { if (dbg && tl == 1 && (threadIdx.x & 31) == 0) dbg[((role) * 25 + (step)) * 8 + (k)] = clock64(); } while (0)
     const long long M = p.M_dev ? min((long long)*p.M_dev, p.M_host) : p.M_host;
     const long long ntiles = (M + TM - 1) / TM;
 
@@ -493,61 +509,54 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
     const uint32_t D1 = tmem, D2 = tmem + 256;   // D3 aliases D1, D4 aliases D2[0:16]
 
     if (warp == 8) {
-        if (lane == 0) {
-            uint32_t it = 0, tl = 0;
-            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
-                for (int step = 0; step < STEPS_TRAIN; ++step, ++it) {
-                    const uint32_t s = it & 1, ph = (it >> 1) & 1;
-                    const uint32_t bytes = (step < 17) ? PANEL_B : PANEL_B16;
-                    NL_STAMP(0, step, 0);
-                    mbar_wait(BAR(2 + s), ph ^ 1);
-                    NL_STAMP(0, step, 1);
+        // ===== producer (warp-uniform loop, one elected lane issues the copies) =====
+        uint32_t it = 0, tl = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
+            for (int step = 0; step < STEPS_TRAIN; ++step, ++it) {
+                const uint32_t s = it & 1, ph = (it >> 1) & 1;
+                const uint32_t bytes = (step < 17) ? PANEL_B : PANEL_B16;
+                NL_STAMP(0, step, 0);
+                mbar_wait(BAR(2 + s), ph ^ 1);
+                NL_STAMP(0, step, 1);
+                if (elect_one()) {
                     mbar_expect_tx(BAR(0 + s), 2 * bytes);
                     const uint8_t *src = p.panels + (size_t)step * STAGE_B;
                     bulk_g2s(sB + s * STAGE_B, src, bytes, BAR(0 + s));
                     bulk_g2s(sB + s * STAGE_B + PANEL_B, src + PANEL_B, bytes, BAR(0 + s));
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 9) {
-        if (lane == 0) {
-            constexpr uint32_t idesc256 = make_idesc(TM, WN), idesc16 = make_idesc(TM, 16);
-            uint32_t it = 0, tl = 0;
-            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
-                for (int step = 0; step < STEPS_TRAIN; ++step, ++it) {
-                    const uint32_t s = it & 1, ph = (it >> 1) & 1;
-                    NL_STAMP(1, step, 0);
-                    if (step == 1) mbar_wait(BAR(12), (tl & 1) ^ 1);   // D4 (in D2's columns) of the previous tile fully read
-                    mbar_wait(BAR(0 + s), ph);
-                    NL_STAMP(1, step, 1);
-                    mbar_wait(BAR(4 + s), ph);
-                    NL_STAMP(1, step, 2);
-                    tc_fence_after();
-                    const uint32_t a_hi = sA + s * STAGE_A, a_lo = a_hi + PANEL_A;
-                    const uint32_t b_hi = sB + s * STAGE_B, b_lo = b_hi + PANEL_B;
-                    const uint32_t d = (step == 0 || (step >= 9 && step <= 16)) ? D1 : D2;
-                    const uint32_t idesc = (step >= 17) ? idesc16 : idesc256;
-                    const int nk = (step == 0) ? 2 : 4;
-                    uint32_t acc = (step == 0 || step == 1 || step == 9 || step == 17) ? 0u : 1u;
-                    const int nterm = (step >= 9 && step <= 16) ? 2 : 3;   // the 0/1 mask operand of backward layer 2 has no lo part
-#pragma unroll
-                    for (int term = 0; term < 3; ++term) {
-                        if (term >= nterm) break;
-                        const uint64_t ad = make_desc(term == 2 ? a_lo : a_hi);
-                        const uint64_t bd = make_desc(term == 1 ? b_lo : b_hi);
-                        for (int ks = 0; ks < nk; ++ks) {
-                            mma_tf32(d, ad + 2 * ks, bd + 2 * ks, idesc, acc);
-                            acc = 1u;
-                        }
-                    }
+        // ===== MMA issuer (warp-uniform loop, one elected lane issues) =====
+        constexpr uint32_t idesc256 = make_idesc(TM, WN), idesc16 = make_idesc(TM, 16);
+        uint32_t it = 0, tl = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
+            for (int step = 0; step < STEPS_TRAIN; ++step, ++it) {
+                const uint32_t s = it & 1, ph = (it >> 1) & 1;
+                NL_STAMP(1, step, 0);
+                if (step == 1) mbar_wait(BAR(12), (tl & 1) ^ 1);   // D4 (in D2's columns) of the previous tile fully read
+                mbar_wait(BAR(0 + s), ph);
+                NL_STAMP(1, step, 1);
+                mbar_wait(BAR(4 + s), ph);
+                NL_STAMP(1, step, 2);
+                tc_fence_after();
+                const uint32_t a_hi = sA + s * STAGE_A, b_hi = sB + s * STAGE_B;
+                if (elect_one()) {
+                    if (step == 0) issue_kblock<2, 3>(D1, a_hi, b_hi, idesc256, 0u);                      // layer 1 (K = 16)
+                    else if (step <= 8) issue_kblock<4, 3>(D2, a_hi, b_hi, idesc256, step == 1 ? 0u : 1u);    // layer 2
+                    else if (step <= 16) issue_kblock<4, 2>(D1, a_hi, b_hi, idesc256, step == 9 ? 0u : 1u);   // backward layer 2: the 0/1
+                                                                                                              // mask operand has no lo part
+                    else issue_kblock<4, 3>(D2, a_hi, b_hi, idesc16, step == 17 ? 0u : 1u);                   // backward layer 1 (N = 16)
                     tc_commit(BAR(2 + s));
                     tc_commit(BAR(6 + s));
-                    NL_STAMP(1, step, 3);
                     if (step == 0) tc_commit(BAR(8));
                     if (step == 8) tc_commit(BAR(9));
                     if (step == 16) tc_commit(BAR(10));
                     if (step == 24) tc_commit(BAR(11));
                 }
+                __syncwarp();
+                NL_STAMP(1, step, 3);
             }
         }
     } else {
@@ -858,23 +867,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dw1_tc(long long M_host, const 
     const bool has_work = (long long)blockIdx.x < nkb;
 
     if (warp == 0) {
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (long long kb = blockIdx.x; kb < nkb; kb += gridDim.x, ++it) {
-                const uint32_t s = it % DW_NRAW, ph = (it / DW_NRAW) & 1;
-                mbar_wait(BAR(4 + s), ph ^ 1);
+        uint32_t it = 0;
+        for (long long kb = blockIdx.x; kb < nkb; kb += gridDim.x, ++it) {
+            const uint32_t s = it % DW_NRAW, ph = (it / DW_NRAW) & 1;
+            mbar_wait(BAR(4 + s), ph ^ 1);
+            if (elect_one()) {
                 mbar_expect_tx(BAR(0 + s), DW_OPER + DW_BITS + DW_KROWS * 4);
                 const long long tile = kb >> 3;
                 const int r0 = (int)(kb & 7) * DW_KROWS;
                 const uint32_t dst = sRaw + s * DW_RAW;
+#pragma unroll
                 for (int pnl = 0; pnl < 8; ++pnl)
                     bulk_g2s(dst + pnl * DW_PANEL, act_h1 + ((size_t)(tile * 8 + pnl) * TM + r0) * 32, DW_PANEL, BAR(0 + s));
                 bulk_g2s(dst + DW_OPER, act_mask2 + (size_t)(tile * TM + r0) * 8, DW_BITS, BAR(0 + s));
                 bulk_g2s(dst + DW_OPER + DW_BITS, act_dsdf + tile * TM + r0, DW_KROWS * 4, BAR(0 + s));
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        if (lane == 0 && has_work) {
+        if (has_work) {
             // M = 128 (rows j), N = 256 (columns k), both operands MN-major (bits 15, 16)
             constexpr uint32_t idesc = make_idesc(TM, WN) | (1u << 15) | (1u << 16);
             uint32_t it = 0;
@@ -883,23 +894,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dw1_tc(long long M_host, const 
                 mbar_wait(BAR(8 + s), ph);
                 tc_fence_after();
                 const uint32_t a_m = sConv + s * DW_CONV, b_hi = a_m + DW_OPER, b_lo = a_m + 2 * DW_OPER;
+                if (elect_one()) {
 #pragma unroll
-                for (int jt = 0; jt < 2; ++jt) {
-                    uint32_t acc = it > 0 ? 1u : 0u;
+                    for (int jt = 0; jt < 2; ++jt) {
+                        uint32_t acc = it > 0 ? 1u : 0u;
 #pragma unroll
-                    for (int term = 0; term < 2; ++term) {
-                        const uint32_t a0 = a_m + jt * 4 * DW_PANEL;
-                        const uint32_t b0 = (term == 1 ? b_lo : b_hi);
+                        for (int term = 0; term < 2; ++term) {
+                            const uint32_t a0 = a_m + jt * 4 * DW_PANEL;
+                            const uint32_t b0 = (term == 1 ? b_lo : b_hi);
 #pragma unroll
-                        for (int ks = 0; ks < DW_KROWS / 8; ++ks) {
-                            mma_tf32(tmem + jt * 256, make_desc_mn(a0 + ks * 1024), make_desc_mn(b0 + ks * 1024), idesc, acc);
-                            acc = 1u;
+                            for (int ks = 0; ks < DW_KROWS / 8; ++ks) {
+                                mma_tf32(tmem + jt * 256, make_desc_mn(a0 + ks * 1024), make_desc_mn(b0 + ks * 1024), idesc, acc);
+                                acc = 1u;
+                            }
                         }
                     }
+                    tc_commit(BAR(11 + s));
                 }
-                tc_commit(BAR(11 + s));
+                __syncwarp();
             }
-            tc_commit(BAR(14));
+            if (elect_one()) tc_commit(BAR(14));
+            __syncwarp();
         }
     } else {
         // converters (128 threads).  Stored h1 image: K-major SWIZZLE_128B (16 B chunk c of row r at c ^ (r & 7)); operand

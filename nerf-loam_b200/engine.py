@@ -269,7 +269,7 @@ class SDFEngine:
 
     def forward_backward(self, m, dec, R, cfg, gt_depth, cos, dir_local=None, ray_frame=None, n_frames=1, ray_o=None,
                          ray_d=None, noise=None, rng_seed=0, reference_compat=True, update_decoder=True, update_emb=True,
-                         update_pose=True, pose6=None, group=None):
+                         update_pose=True, pose6=None, group=None, refresh_weights=True):
         """One optimisation iteration without the optimiser step.  Gradients land in
         self.grad_emb (fp32 [V,16]), dec.grads (fp32), self.pose_grad (fp32 [F,6]); the loss in stats."""
         lib = _capi.lib()
@@ -284,7 +284,8 @@ class SDFEngine:
                         "nl_loss_prepare")
             _capi.LAUNCHES += 1
         self._mark("t_samples")
-        dec.refresh_transposes()
+        if refresh_weights:
+            dec.refresh_transposes()
         self.gather_forward(m)
         self._mark("t_gather_fwd")
         if update_decoder:

@@ -202,12 +202,19 @@ class _FrameBatch:
         self.cos = [f.pointsCos.float().view(-1).to(dev) for f in frames]
         self.gt = [torch.norm(f.points.float().to(dev), 2, -1) * c for f, c in zip(frames, self.cos)]  # criterion.py:30-32
 
-    def select(self, N_rays, dev, track=False):
-        """Host ray selection like the reference (frame.sample_rays -> boolean mask, CPU RNG), gathered on the device."""
+    def select(self, N_rays, dev, track=False, mode="host"):
+        """mode "host": ray selection like the reference (frame.sample_rays -> boolean mask, CPU torch RNG: the same seed
+        picks the same rays as the reference), gathered on the device.  mode "device": the same distribution (uniform
+        without replacement = top-k of iid keys, sample_util.py:4-19 with a constant mask) drawn with the CUDA generator,
+        no host round trip; frame.sample_mask is not updated."""
         d, g, c, fid = [], [], [], []
         for i, f in enumerate(self.frames):
-            f.sample_rays(N_rays, track=True) if track else f.sample_rays(N_rays)
-            idx = f.sample_mask.view(-1).nonzero().view(-1).to(dev, non_blocking=True)
+            if mode == "device":
+                n = self.dirs[i].shape[0]
+                idx = torch.rand(n, device=dev).topk(min(N_rays, n)).indices.sort().values
+            else:
+                f.sample_rays(N_rays, track=True) if track else f.sample_rays(N_rays)
+                idx = f.sample_mask.view(-1).nonzero().view(-1).to(dev, non_blocking=True)
             d.append(self.dirs[i][idx]); g.append(self.gt[i][idx]); c.append(self.cos[i][idx])
             fid.append(torch.full((idx.shape[0],), i, dtype=torch.int32, device=dev))
         return torch.cat(d).contiguous(), torch.cat(g).contiguous(), torch.cat(c).contiguous(), torch.cat(fid).contiguous()
@@ -216,9 +223,11 @@ class _FrameBatch:
 def bundle_adjust_frames(keyframe_graph, embeddings, map_states, sdf_network, loss_criteria, voxel_size, step_size,
                          N_rays=512, num_iterations=10, truncation=0.1, max_voxel_hit=10, max_distance=10,
                          learning_rate=[1e-2, 1e-2, 5e-3], update_pose=True, update_decoder=True, profiler=None,
-                         deterministic=False, noise_per_iter=None, loss_log=None):
+                         deterministic=False, noise_per_iter=None, loss_log=None, ray_selection="host"):
     """render_helpers.py:321-425.  Mutates `embeddings` (bf16 CUDA table), the decoder parameters and the
-    frame poses in place, like the reference.  Returns None."""
+    frame poses in place, like the reference.  Returns None.  ray_selection: see _FrameBatch.select."""
+    if ray_selection not in ("host", "device"):
+        raise ValueError("ray_selection must be 'host' or 'device'")
     dev = embeddings.device
     if dev.type != "cuda":
         raise RuntimeError("bundle_adjust_frames runs on the GPU only (no CPU fallback)")
@@ -246,7 +255,7 @@ def bundle_adjust_frames(keyframe_graph, embeddings, map_states, sdf_network, lo
     pose_params = [pose6[i] for i in pose_rows]                    # views into pose6 (contiguous rows)
     opt = None
     for it in range(num_iterations):
-        dirs, gt, cos, fid = batch.select(N_rays, dev)
+        dirs, gt, cos, fid = batch.select(N_rays, dev, mode=ray_selection)
         eng.rays_from_poses(pose6, dirs, fid)
         noise = noise_per_iter[it] if noise_per_iter is not None else None
         seed = 0 if (deterministic or noise is not None) else _seed_from_torch()
@@ -272,9 +281,12 @@ def bundle_adjust_frames(keyframe_graph, embeddings, map_states, sdf_network, lo
 
 def track_frame(frame_pose, curr_frame, map_states, sdf_network, loss_criteria, voxel_size, N_rays=512, step_size=0.05,
                 num_iterations=10, truncation=0.1, learning_rate=1e-3, max_voxel_hit=10, max_distance=10, profiler=None,
-                depth_variance=False, deterministic=False, noise_per_iter=None, loss_log=None):
+                depth_variance=False, deterministic=False, noise_per_iter=None, loss_log=None, ray_selection="host"):
     """render_helpers.py:428-514: optimise the 6-vector pose of one scan against a frozen map.
-    Returns (OptimizablePose on the GPU, hit_mask bool[N_rays]) or (pose, None) if nothing was hit."""
+    Returns (OptimizablePose on the GPU, hit_mask bool[N_rays]) or (pose, None) if nothing was hit.
+    ray_selection: see _FrameBatch.select."""
+    if ray_selection not in ("host", "device"):
+        raise ValueError("ray_selection must be 'host' or 'device'")
     dev = torch.device("cuda")
     m = map_states if isinstance(map_states, MapState) else MapState.from_map_states(map_states, dev)
     cfg = _cfg(step_size, voxel_size, max_distance, loss_criteria)
@@ -287,22 +299,27 @@ def track_frame(frame_pose, curr_frame, map_states, sdf_network, loss_criteria, 
     batch = _FrameBatch([curr_frame], dev)
     opt = None
     hit_mask = None
+    n_last = 0
+    bufs.refresh_transposes()           # the decoder is frozen while tracking: derive the kernel-side weight images once
     for it in range(num_iterations):
-        dirs, gt, cos, fid = batch.select(N_rays, dev, track=True)
+        dirs, gt, cos, fid = batch.select(N_rays, dev, track=True, mode=ray_selection)
         eng.rays_from_poses(pose6, dirs, None)
         noise = noise_per_iter[it] if noise_per_iter is not None else None
         seed = 0 if (deterministic or noise is not None) else _seed_from_torch()
         eng.forward_backward(m, bufs, dirs.shape[0], cfg, gt, cos, dir_local=dirs, ray_frame=None, n_frames=1, noise=noise,
-                             rng_seed=seed, update_decoder=False, update_emb=False, update_pose=True, pose6=pose6)
+                             rng_seed=seed, update_decoder=False, update_emb=False, update_pose=True, pose6=pose6,
+                             refresh_weights=False)
         st = eng.read_stats()   # the reference syncs here too (hit_mask, None checks)
         if st.n_hit_rays <= 0 or (st.error & 1) or st.n_samples == 0:
             print("Encouter a bug while Tracking, currently not be fixed, Restarting!!")  # render_helpers.py:488-491
-            hit_mask = None
+            n_last = 0
             break
-        hit_mask = (eng.hit_rank[:dirs.shape[0]] >= 0).clone()
+        n_last = dirs.shape[0]
         if loss_log is not None:
             loss_log.append(st.loss)
         if opt is None:
             opt = FusedAdam([dict(param=pose6[0], grad=eng.pose_grad[0], lr=lr)])
         opt.step()
+    if n_last:
+        hit_mask = (eng.hit_rank[:n_last] >= 0).clone()   # of the last iteration, like the reference's return value
     return init_pose, hit_mask
