@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_mlp_tc_fwd(FwdParams p) {
 // the weight panels, and the A operand of backward layer 2 is the 0/1 mask itself -- exact in tf32, so that GEMM needs
 // two terms (mask x hi, mask x lo) instead of three and no lo panel.  ReLU masks are 2 x 256 bits per thread in registers.
 // With WGRAD the kernel writes h1 and dh1 to HBM in 16 KB "panel" blocks [(tile*8 + kblock)][row][32] (bulk copies of the
-// A stages) plus the relu'(h2) bits (32 B/sample) and dsdf; the same factorisation lets k_dw1_tc / k_dw0_panels rebuild
+// A stages) plus the relu'(h2) bits (32 B/sample) and dsdf; the same factorisation lets k_dw1_tc / k_dw0_tc / k_mask_colsum rebuild
 // everything that used to need dh2 and h2 panels (see there).
 // ================================================================================================
 struct TrainParams {
@@ -372,6 +372,24 @@ struct TrainParams {
     long long *dbg;                      // optional timeline stamps (NL_TC_TIMELINE=1), else nullptr
 };
 
+// registers -> TMEM, 32 lanes x 32 columns per warp (thread = lane/row); completion via tmem_wait_st()
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
+        "%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
+        "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]),
+        "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// A operand from TMEM (lane = row, one 32-bit column per tf32 element, K = 8 columns per instruction), B from shared memory
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc),
+        "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -379,62 +397,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
           "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// split 32 fp32 values of one row into tf32 hi/lo and store them as one 128 B row of the swizzled A panels
-__device__ __forceinline__ void store_a_row(uint8_t *stage, int row, const float (&h)[32]) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        float hi[4], lo[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { hi[i] = tf32_rna(h[c * 4 + i]); lo[i] = tf32_rna(h[c * 4 + i] - hi[i]); }
-        *reinterpret_cast<float4 *>(stage + panel_off(row, c)) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4 *>(stage + PANEL_A + panel_off(row, c)) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-    }
-}
-// one 128 B row of an HBM activation panel.  The panel is the exact shared-memory image the dW1 GEMM feeds to the tensor
-// core as an MN-major tf32 operand (K = sample row): the only layout tcgen05 accepts for that is SWIZZLE_128B_BASE32B
-// (cute Swizzle<2,5,2>, atoms of 4 rows x 128 B): 32-byte chunk c of row r is stored at position c ^ (r & 3).
-__device__ __forceinline__ void store_panel_row(float *dst, int row, const float (&h)[32]) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        float4 *d = reinterpret_cast<float4 *>(dst) + 2 * (c ^ (row & 3));
-        d[0] = make_float4(h[c * 8], h[c * 8 + 1], h[c * 8 + 2], h[c * 8 + 3]);
-        d[1] = make_float4(h[c * 8 + 4], h[c * 8 + 5], h[c * 8 + 6], h[c * 8 + 7]);
-    }
-}
-// float index of element k (0..31) of row r inside such a panel row
-__device__ __forceinline__ int panel_elem(int r, int k) { return ((((k >> 2) ^ (r & 7)) << 2) | (k & 3)); }
-// v[c] of lane l = element (row l, column c) of a 32x32 block; returns on lane l the sum over rows of column l
-__device__ __forceinline__ float colsum32(const float (&v)[32], int lane) {
-    float r16[16], r8[8], r4[4], r2[2];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const bool up = lane & 16;
-        const float send = up ? v[i] : v[i + 16], keep = up ? v[i + 16] : v[i];
-        r16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const bool up = lane & 8;
-        const float send = up ? r16[i] : r16[i + 8], keep = up ? r16[i + 8] : r16[i];
-        r8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const bool up = lane & 4;
-        const float send = up ? r8[i] : r8[i + 4], keep = up ? r8[i + 4] : r8[i];
-        r4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const bool up = lane & 2;
-        const float send = up ? r4[i] : r4[i + 2], keep = up ? r4[i + 2] : r4[i];
-        r2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-    const bool up = lane & 1;
-    const float send = up ? r2[0] : r2[1], keep = up ? r2[1] : r2[0];
-    return keep + __shfl_xor_sync(0xffffffffu, send, 1);
 }
 
 // smem -> global bulk copy (1-D TMA store) of this warp's rows of an activation panel; one instruction per warp and
@@ -465,7 +427,12 @@ __device__ __forceinline__ void store_a_row_fast(uint32_t stage, const uint32_t 
 // Warp roles (NTHREADS_TRAIN = 320): warps 0-7 epilogue (group g = warp >> 2, TMEM lane quarter q = warp & 3), warp 8
 // producer, warp 9 MMA issuer + TMEM owner.  The two single-thread roles get the HIGHEST warp ids: the per-SMSP arbiter
 // prefers the highest warp id, so the busy epilogue warps cannot starve the thread that feeds the tensor core.
-template <bool WGRAD>
+// TS = true: the A operands of both backward GEMMs come from TMEM instead of shared memory.  The 0/1 mask of backward
+// layer 2 is written (tcgen05.st) over the dead layer-2 accumulator right where each thread read its pre-activations, so
+// those 8 K-blocks need no activation stage, no smem stores and no per-chunk hand-shake; the dh1 chunks of backward
+// layer 1 go through two 64-column TMEM slots (hi | lo), one per epilogue group.  Shared-memory traffic of those 16
+// steps drops to the weight panels, and the tiny N = 16 MMAs no longer fetch a 4 KB A tile from smem each.
+template <bool WGRAD, bool TS>
 __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -477,9 +444,10 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
     float *w2s = b1s + WN;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sm + SMEM_DATA + 3 * WN * 4);
     // barriers: 0,1 b_full  2,3 b_empty  4,5 a_full  6,7 a_empty  8 d1_full  9 d2_full  10 d3_full  11 d4_full  12 d4_empty
+    //           TS: 14,15 slot_full[g]  16,17 slot_empty[g]  18..25 mask_full[K-block]
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * i; };
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 14);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 28);
     float *sdf_part = reinterpret_cast<float *>(sm + SMEM_DATA + 4096);   // [tile parity][group][row]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -496,6 +464,9 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
         mbar_init(BAR(6), 1); mbar_init(BAR(7), 1);
         mbar_init(BAR(8), 1); mbar_init(BAR(9), 1); mbar_init(BAR(10), 1); mbar_init(BAR(11), 1);
         mbar_init(BAR(12), 4);
+        for (int i = 0; i < 8; ++i) mbar_init(BAR(18 + i), 4);   // mask_full[K-block]: the 4 warps of the group that owns it
+        mbar_init(BAR(14), 4); mbar_init(BAR(15), 4);    // slot_full: the 4 warps of the group
+        mbar_init(BAR(16), 1); mbar_init(BAR(17), 1);    // slot_empty: tcgen05.commit
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 9) {
@@ -507,6 +478,10 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t D1 = tmem, D2 = tmem + 256;   // D3 aliases D1, D4 aliases D2[0:16]
+    // TS: mask2 overwrites D2 (all 256 columns) for steps 9..16; dh1 slot g = D2[64 + 64g, +64) (hi | lo) for steps 17..24
+    auto SLOT = [&](int g) { return D2 + 64u + 64u * (uint32_t)g; };
+    // activation-stage use index: without TS every step uses a stage, with TS only steps 0..8 of each tile do
+    auto AIT = [&](uint32_t tl, int step) { return TS ? tl * 9u + (uint32_t)step : tl * (uint32_t)STEPS_TRAIN + (uint32_t)step; };
 
     if (warp == 8) {
         // ===== producer (warp-uniform loop, one elected lane issues the copies) =====
@@ -538,22 +513,69 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
                 if (step == 1) mbar_wait(BAR(12), (tl & 1) ^ 1);   // D4 (in D2's columns) of the previous tile fully read
                 mbar_wait(BAR(0 + s), ph);
                 NL_STAMP(1, step, 1);
-                mbar_wait(BAR(4 + s), ph);
-                NL_STAMP(1, step, 2);
-                tc_fence_after();
-                const uint32_t a_hi = sA + s * STAGE_A, b_hi = sB + s * STAGE_B;
-                if (elect_one()) {
-                    if (step == 0) issue_kblock<2, 3>(D1, a_hi, b_hi, idesc256, 0u);                      // layer 1 (K = 16)
-                    else if (step <= 8) issue_kblock<4, 3>(D2, a_hi, b_hi, idesc256, step == 1 ? 0u : 1u);    // layer 2
-                    else if (step <= 16) issue_kblock<4, 2>(D1, a_hi, b_hi, idesc256, step == 9 ? 0u : 1u);   // backward layer 2: the 0/1
-                                                                                                              // mask operand has no lo part
-                    else issue_kblock<4, 3>(D2, a_hi, b_hi, idesc16, step == 17 ? 0u : 1u);                   // backward layer 1 (N = 16)
-                    tc_commit(BAR(2 + s));
-                    tc_commit(BAR(6 + s));
-                    if (step == 0) tc_commit(BAR(8));
-                    if (step == 8) tc_commit(BAR(9));
-                    if (step == 16) tc_commit(BAR(10));
-                    if (step == 24) tc_commit(BAR(11));
+                const uint32_t b_hi = sB + s * STAGE_B;
+                if (!TS || step <= 8) {
+                    const uint32_t ai = AIT(tl, step), as = ai & 1, aph = (ai >> 1) & 1;
+                    mbar_wait(BAR(4 + as), aph);
+                    NL_STAMP(1, step, 2);
+                    tc_fence_after();
+                    const uint32_t a_hi = sA + as * STAGE_A;
+                    if (elect_one()) {
+                        if (step == 0) issue_kblock<2, 3>(D1, a_hi, b_hi, idesc256, 0u);                      // layer 1 (K = 16)
+                        else if (step <= 8) issue_kblock<4, 3>(D2, a_hi, b_hi, idesc256, step == 1 ? 0u : 1u);    // layer 2
+                        else if (step <= 16) issue_kblock<4, 2>(D1, a_hi, b_hi, idesc256, step == 9 ? 0u : 1u);   // backward layer 2: the 0/1
+                                                                                                                  // mask operand has no lo part
+                        else issue_kblock<4, 3>(D2, a_hi, b_hi, idesc16, step == 17 ? 0u : 1u);                   // backward layer 1 (N = 16)
+                        tc_commit(BAR(2 + s));
+                        tc_commit(BAR(6 + as));
+                        if (step == 0) tc_commit(BAR(8));
+                        if (step == 8) tc_commit(BAR(9));
+                        if (step == 16) tc_commit(BAR(10));
+                        if (step == 24) tc_commit(BAR(11));
+                    }
+                } else if (step <= 16) {
+                    // ---- TS backward layer 2: A = mask2 columns of K-block jb in TMEM ----
+                    mbar_wait(BAR(18 + (step - 9)), tl & 1);
+                    NL_STAMP(1, step, 2);
+                    tc_fence_after();
+                    const uint32_t a_t = D2 + (uint32_t)(step - 9) * 32u;
+                    if (elect_one()) {
+                        const uint64_t bdh = make_desc(b_hi), bdl = make_desc(b_hi + PANEL_B);
+                        uint32_t acc = step == 9 ? 0u : 1u;
+#pragma unroll
+                        for (int term = 0; term < 2; ++term) {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                mma_tf32_ts(D1, a_t + 8 * ks, (term ? bdl : bdh) + 2 * ks, idesc256, acc);
+                                acc = 1u;
+                            }
+                        }
+                        tc_commit(BAR(2 + s));
+                        if (step == 16) tc_commit(BAR(10));
+                    }
+                } else {
+                    // ---- TS backward layer 1: A = dh1 chunk (hi | lo) in the TMEM slot of the group that owns K-block kb ----
+                    const int kb = step - 17, g = kb & 1;
+                    const uint32_t u = tl * 4u + (uint32_t)(kb >> 1);
+                    mbar_wait(BAR(14 + g), u & 1);
+                    NL_STAMP(1, step, 2);
+                    tc_fence_after();
+                    const uint32_t a_t = SLOT(g);
+                    if (elect_one()) {
+                        const uint64_t bdh = make_desc(b_hi), bdl = make_desc(b_hi + PANEL_B);
+                        uint32_t acc = step == 17 ? 0u : 1u;
+#pragma unroll
+                        for (int term = 0; term < 3; ++term) {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                mma_tf32_ts(D2, a_t + (term == 2 ? 32u : 0u) + 8 * ks, (term == 1 ? bdl : bdh) + 2 * ks, idesc16, acc);
+                                acc = 1u;
+                            }
+                        }
+                        tc_commit(BAR(2 + s));
+                        tc_commit(BAR(16 + g));
+                        if (step == 24) tc_commit(BAR(11));
+                    }
                 }
                 __syncwarp();
                 NL_STAMP(1, step, 3);
@@ -599,16 +621,17 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
             }
         };
         prefetch(blockIdx.x);
-        uint32_t it0 = 0, tl = 0;                      // it0: ring step index of this tile's step 0
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl, it0 += STEPS_TRAIN) {
+        uint32_t tl = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
             const long long m = tile * TM + row;
             const bool live = m < M;
             const uint32_t fl = fl_n;
             const float z = z_n, dgt = dgt_n, dext = dext_n;
             uint32_t mask1[4], mask2[4];
-            // ---- step 0: x -> A (group 0) ----
-            if (g == 0) {
-                const uint32_t it = it0, s = it & 1, ph = (it >> 1) & 1;
+            // ---- step 0: x -> A (group 0).  With TS the activation stages are idle during the backward steps, so the next
+            // tile's x was already staged at the end of the previous tile (stage_x below) ----
+            if (g == 0 && (!TS || tl == 0)) {
+                const uint32_t it = AIT(tl, 0), s = it & 1, ph = (it >> 1) & 1;
                 if (WGRAD) { if (lane == 0) bulk_wait_read(); __syncwarp(); }
                 mbar_wait(BAR(6 + s), ph ^ 1);
                 const uint32_t dst = sA + s * STAGE_A;
@@ -629,7 +652,7 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
 #pragma unroll 1
             for (int kk = 0; kk < 4; ++kk) {
                 const int kb = 2 * kk + g;
-                const uint32_t it = it0 + 1 + kb, s = it & 1, ph = (it >> 1) & 1;
+                const uint32_t it = AIT(tl, 1 + kb), s = it & 1, ph = (it >> 1) & 1;
                 if (q == 0 && lane == 0) NL_STAMP(2 + g, 1 + kb, 0);
                 uint32_t v[32];
                 tmem_ld32(D1 + lane_addr + kb * 32, v);
@@ -677,8 +700,16 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
                     const bool on = t > 0.f;
                     mk |= on ? (1u << i) : 0u;
                     acc4[i & 3] = fmaf(on ? t : 0.f, w2s[cb * 32 + i], acc4[i & 3]);
+                    if (TS) v[i] = on ? 0x3f800000u : 0u;       // 1.0f / 0.0f: the A operand of backward layer 2
                 }
                 mask2[kk] = mk;
+                if (TS) {   // same lanes / columns this thread just read; backward layer 2 may start on this K-block right away
+                    tmem_st32(D2 + lane_addr + cb * 32, v);
+                    tmem_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(BAR(18 + cb));
+                }
             }
             float *part = sdf_part + (tl & 1) * 256;
             part[g * 128 + row] = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
@@ -711,11 +742,11 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
                 }
                 *reinterpret_cast<uint4 *>(p.act_mask2 + (size_t)(tile * TM + row) * 8 + g * 4) = make_uint4(mask2[0], mask2[1], mask2[2], mask2[3]);
             }
-            // ---- steps 9..16: dh2 chunks, built from registers ----
+            // ---- steps 9..16: the 0/1 mask chunks as activation stages (TS: already in TMEM) ----
 #pragma unroll 1
-            for (int kk = 0; kk < 4; ++kk) {
+            for (int kk = 0; kk < (TS ? 0 : 4); ++kk) {
                 const int jb = 2 * kk + g;
-                const uint32_t it = it0 + 9 + jb, s = it & 1, ph = (it >> 1) & 1;
+                const uint32_t it = AIT(tl, 9 + jb), s = it & 1, ph = (it >> 1) & 1;
                 if (q == 0 && lane == 0) NL_STAMP(2 + g, 9 + jb, 0);
                 if (WGRAD) { if (lane == 0) bulk_wait_read(); __syncwarp(); }
                 if (q == 0 && lane == 0) NL_STAMP(2 + g, 9 + jb, 1);
@@ -740,27 +771,73 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
 #pragma unroll 1
             for (int kk = 0; kk < 4; ++kk) {
                 const int kb = 2 * kk + g;
-                const uint32_t it = it0 + 17 + kb, s = it & 1, ph = (it >> 1) & 1;
                 if (q == 0 && lane == 0) NL_STAMP(2 + g, 17 + kb, 0);
                 uint32_t v[32];
                 tmem_ld32(D1 + lane_addr + kb * 32, v);
                 float h[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) h[i] = ((mask1[kk] >> i) & 1u) ? dsdf * __uint_as_float(v[i]) : 0.f;
-                if (WGRAD) { if (lane == 0) bulk_wait_read(); __syncwarp(); }
                 if (q == 0 && lane == 0) NL_STAMP(2 + g, 17 + kb, 1);
-                mbar_wait(BAR(6 + s), ph ^ 1);
-                if (q == 0 && lane == 0) NL_STAMP(2 + g, 17 + kb, 2);
-                store_a_row_fast(sA + s * STAGE_A, offc, h);
-                fence_proxy_async();
-                __syncwarp();
-                if (WGRAD && lane == 0) bulk_s2g(p.act_dh1 + ((size_t)(tile * 8 + kb) * TM + q * 32) * 32, sA + s * STAGE_A + q * 4096, 4096);
-                if (lane == 0) mbar_arrive(BAR(4 + s));
+                if (TS) {
+                    // hi = the fp32 bits (the tensor core truncates to tf32), lo = x - trunc(x); both into this group's TMEM slot
+                    const uint32_t u = tl * 4u + (uint32_t)kk;
+                    mbar_wait(BAR(16 + g), (u & 1) ^ 1);               // the MMAs of this group's previous chunk retired
+                    if (q == 0 && lane == 0) NL_STAMP(2 + g, 17 + kb, 2);
+                    uint32_t w[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) w[i] = __float_as_uint(h[i]);
+                    tmem_st32(SLOT(g) + lane_addr, w);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) w[i] = __float_as_uint(h[i] - __uint_as_float(__float_as_uint(h[i]) & 0xffffe000u));
+                    tmem_st32(SLOT(g) + lane_addr + 32, w);
+                    tmem_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(BAR(14 + g));
+                    if (WGRAD) {   // panel store for gW0 / gb0: staged through the activation stage this group used in steps 1..8
+                        const uint32_t sg = sA + ((tl + 1u + (uint32_t)g) & 1u) * STAGE_A;
+                        if (lane == 0) bulk_wait_read();
+                        __syncwarp();
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) st_shared_v4(sg + offc[c], h[c * 4], h[c * 4 + 1], h[c * 4 + 2], h[c * 4 + 3]);
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) bulk_s2g(p.act_dh1 + ((size_t)(tile * 8 + kb) * TM + q * 32) * 32, sg + q * 4096, 4096);
+                    }
+                } else {
+                    const uint32_t it = AIT(tl, 17 + kb), s = it & 1, ph = (it >> 1) & 1;
+                    if (WGRAD) { if (lane == 0) bulk_wait_read(); __syncwarp(); }
+                    mbar_wait(BAR(6 + s), ph ^ 1);
+                    if (q == 0 && lane == 0) NL_STAMP(2 + g, 17 + kb, 2);
+                    store_a_row_fast(sA + s * STAGE_A, offc, h);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (WGRAD && lane == 0) bulk_s2g(p.act_dh1 + ((size_t)(tile * 8 + kb) * TM + q * 32) * 32, sA + s * STAGE_A + q * 4096, 4096);
+                    if (lane == 0) mbar_arrive(BAR(4 + s));
+                }
                 if (q == 0 && lane == 0) NL_STAMP(2 + g, 17 + kb, 3);
             }
             if (WGRAD) {   // stages change hands between the groups at the tile boundary: all panel stores must have left smem
                 if (lane == 0) bulk_wait_read();
                 asm volatile("bar.sync 2, 256;" ::: "memory");
+            }
+            if (TS && g == 0 && tile + gridDim.x < ntiles) {
+                // x of the next tile (prefetched above) -> its activation stage now: the MMA warp can issue the next layer 1
+                // right behind this tile's last backward MMAs instead of waiting for the d x read-back below
+                const uint32_t it = AIT(tl + 1, 0), s = it & 1, ph = (it >> 1) & 1;
+                if (WGRAD) { if (lane == 0) bulk_wait_read(); __syncwarp(); }
+                mbar_wait(BAR(6 + s), ph ^ 1);
+                const uint32_t dst = sA + s * STAGE_A;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float4 v = xn[c];
+                    const float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+                    st_shared_v4(dst + offc[c], hi.x, hi.y, hi.z, hi.w);
+                    st_shared_v4(dst + PANEL_A + offc[c], tf32_rna(v.x - hi.x), tf32_rna(v.y - hi.y), tf32_rna(v.z - hi.z), tf32_rna(v.w - hi.w));
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(4 + s));
             }
             // ---- d loss / d x (group 0) ----
             if (g == 0) {
@@ -808,7 +885,7 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
 // Weight gradients of the hidden and output layers on tensor cores.  With m2 = relu'(h2) (0/1) and d = dsdf:
 //   G[j][k]  = sum_s m2[s][j] * (d[s] h1[s][k])                 (256 x 256, fp32 in TMEM: 2 accumulators x 256 columns)
 //   gW1[j][k] += w2[j] G[j][k]                                   (= sum_s dh2[s][j] h1[s][k])
-//   gW2[j]    += sum_k W1[j][k] G[j][k]   (+ b1[j] c[j], added by k_dw0_panels;  = sum_s d[s] h2[s][j] because
+//   gW2[j]    += sum_k W1[j][k] G[j][k]   (+ b1[j] c[j], added by k_mask_colsum;  = sum_s d[s] h2[s][j] because
 //                                            h2 = m2 * (h1 . W1^T + b1), c[j] = sum_s m2[s][j] d[s])
 //   K = samples, streamed in K-blocks of 16 rows.  Both operands are MN-major (SWIZZLE_128B_BASE32B, the only layout
 //   tcgen05 takes for MN-major tf32).  Per K-block the producer bulk-copies the 16 rows of the h1 panels (16 KB, the
@@ -1007,94 +1084,206 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dw1_tc(long long M_host, const 
     }
 }
 
-// gW0[k][e] += sum_m dh1[m][k] x[m][e],  gb0[k] += sum_m dh1[m][k],  and with c[j] = sum_m relu'(h2)[m][j] dsdf[m]:
-// gb1[j] += w2[j] c[j],  gW2[j] += b1[j] c[j]  (the other part of gW2 comes from k_dw1_tc).  fp32 CUDA cores, HBM-bound
-// (1 KB/sample).  thread = (4 consecutive columns cg = tid & 63, row lane rl = tid >> 6); 8 independent 16-byte loads in
-// flight per thread, 2 CTAs per SM
-__global__ void __launch_bounds__(256, 2) k_dw0_panels(long long M_host, const int32_t *__restrict__ M_dev, const float *__restrict__ dh1,
-                                                     const uint32_t *__restrict__ mask2, const float *__restrict__ dsdf,
-                                                     const float *__restrict__ x, const float *__restrict__ b1, const float *__restrict__ w2,
-                                                     float *__restrict__ gW0, float *__restrict__ gb0, float *__restrict__ gb1,
-                                                     float *__restrict__ gW2) {
-    __shared__ float xs[32][16];
-    __shared__ float ds[32];
+// ================================================================================================
+// Weight gradient of the first layer on tensor cores:  gW0[k][e] += sum_s dh1[s][k] x[s][e],  gb0[k] += sum_s dh1[s][k]
+//   Same streaming skeleton as k_dw1_tc (K = samples in K-blocks of 16 rows, MN-major operands).  A = dh1^T from the
+//   stored panels (hi = fp32 bits, lo = x - trunc(x)), B = one 32-column panel [x (16) | 1 | 0 ...] (hi/lo), so column 16 of
+//   the accumulator is the bias gradient.  D = 256 x 32 fp32 in TMEM (2 x 32 columns), 3 tf32 terms, N = 32 MMAs.
+// ================================================================================================
+constexpr int D0_RAW = DW_OPER + 1024;          // dh1 raw (16 KB) | x rows (16 x 64 B)
+constexpr int D0_CONV = 2 * DW_OPER + 2 * DW_PANEL;   // A hi | A lo | B hi | B lo = 36 KB
+constexpr int D0_NRAW = 4, D0_NCONV = 4;
+constexpr int D0_SMEM = D0_NRAW * D0_RAW + D0_NCONV * D0_CONV + 1024 + 1024;
+
+__global__ void __launch_bounds__(NTHREADS, 1) k_dw0_tc(long long M_host, const int32_t *__restrict__ M_dev, const float *__restrict__ act_dh1,
+                                                         const float *__restrict__ feats, float *__restrict__ gW0, float *__restrict__ gb0) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t *sm = smem_raw + (base - raw);
+    const uint32_t sConv = base, sRaw = base + D0_NCONV * D0_CONV;
+    uint8_t *conv_gen = sm, *raw_gen = sm + D0_NCONV * D0_CONV;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + D0_NCONV * D0_CONV + D0_NRAW * D0_RAW);
+    // barriers: 0..3 raw_full  4..7 raw_empty  8..11 conv_full  12..15 conv_empty  16 d_full
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * i; };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 18);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long M = M_dev ? min((long long)*M_dev, M_host) : M_host;
-    const int cg = threadIdx.x & 63, rl = threadIdx.x >> 6;      // columns 4cg..4cg+3; rows rl, rl+4, ...
-    const int pnl = cg >> 3, c16 = cg & 7;
-    const int word = (pnl & 1) * 4 + (pnl >> 1), shift = c16 * 4;
-    float acc[4][16], sb0[4] = {0.f, 0.f, 0.f, 0.f}, sc[4] = {0.f, 0.f, 0.f, 0.f};
+    const long long nkb = ((M + TM - 1) / TM) * (TM / DW_KROWS);
+    if (tid == 0) {
+        for (int i = 0; i < D0_NRAW; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(4 + i), 4); }
+        for (int i = 0; i < D0_NCONV; ++i) { mbar_init(BAR(8 + i), 4); mbar_init(BAR(12 + i), 1); }
+        mbar_init(BAR(16), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(64u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const bool has_work = (long long)blockIdx.x < nkb;
+
+    if (warp == 0) {
+        uint32_t it = 0;
+        for (long long kb = blockIdx.x; kb < nkb; kb += gridDim.x, ++it) {
+            const uint32_t s = it % D0_NRAW, ph = (it / D0_NRAW) & 1;
+            mbar_wait(BAR(4 + s), ph ^ 1);
+            if (elect_one()) {
+                const long long tile = kb >> 3;
+                const int r0 = (int)(kb & 7) * DW_KROWS;
+                const long long left = M - (tile * TM + r0);                       // feature rows that exist (the panels are tile-padded,
+                const uint32_t xrows = left >= DW_KROWS ? DW_KROWS : (left > 0 ? (uint32_t)left : 0u);   // the feature array is not)
+                mbar_expect_tx(BAR(0 + s), DW_OPER + xrows * 64);
+                const uint32_t dst = sRaw + s * D0_RAW;
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int e = 0; e < 16; ++e) acc[c][e] = 0.f;
-    for (long long m0 = (long long)blockIdx.x * 32; m0 < M; m0 += (long long)gridDim.x * 32) {
-        for (int f = threadIdx.x; f < 32 * 16; f += 256) {
-            const long long m = m0 + (f >> 4);
-            xs[f >> 4][f & 15] = (m < M) ? x[(size_t)m * 16 + (f & 15)] : 0.f;
+                for (int pnl = 0; pnl < 8; ++pnl)
+                    bulk_g2s(dst + pnl * DW_PANEL, act_dh1 + ((size_t)(tile * 8 + pnl) * TM + r0) * 32, DW_PANEL, BAR(0 + s));
+                if (xrows) bulk_g2s(dst + DW_OPER, feats + (size_t)(tile * TM + r0) * 16, xrows * 64, BAR(0 + s));
+            }
+            __syncwarp();
         }
-        if (threadIdx.x < 32) ds[threadIdx.x] = (m0 + threadIdx.x < M) ? dsdf[m0 + threadIdx.x] : 0.f;
-        __syncthreads();
-        float4 d1[8];
-        uint32_t mk[8];
+    } else if (warp == 1) {
+        if (has_work) {
+            constexpr uint32_t idesc = make_idesc(TM, 32) | (1u << 15) | (1u << 16);   // both operands MN-major
+            uint32_t it = 0;
+            for (long long kb = blockIdx.x; kb < nkb; kb += gridDim.x, ++it) {
+                const uint32_t s = it % D0_NCONV, ph = (it / D0_NCONV) & 1;
+                mbar_wait(BAR(8 + s), ph);
+                tc_fence_after();
+                const uint32_t a_hi = sConv + s * D0_CONV, a_lo = a_hi + DW_OPER, b_hi = a_hi + 2 * DW_OPER, b_lo = b_hi + DW_PANEL;
+                if (elect_one()) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int r = rl + 4 * u;
-            const long long m = m0 + r;
-            const int rr = (int)(m & 127);
-            const size_t off = (((size_t)(m >> 7) * 8 + pnl) * TM + rr) * 32 + ((c16 ^ (rr & 7)) << 2);
-            const bool ok = m < M;
-            d1[u] = ok ? *reinterpret_cast<const float4 *>(dh1 + off) : make_float4(0.f, 0.f, 0.f, 0.f);
-            mk[u] = ok ? mask2[(size_t)m * 8 + word] : 0u;
+                    for (int jt = 0; jt < 2; ++jt) {
+                        uint32_t acc = it > 0 ? 1u : 0u;
+#pragma unroll
+                        for (int term = 0; term < 3; ++term) {
+                            const uint32_t a0 = (term == 2 ? a_lo : a_hi) + jt * 4 * DW_PANEL;
+                            const uint32_t b0 = (term == 1 ? b_lo : b_hi);
+#pragma unroll
+                            for (int ks = 0; ks < DW_KROWS / 8; ++ks) {
+                                mma_tf32(tmem + jt * 32, make_desc_mn(a0 + ks * 1024), make_desc_mn(b0 + ks * 1024), idesc, acc);
+                                acc = 1u;
+                            }
+                        }
+                    }
+                    tc_commit(BAR(12 + s));
+                }
+                __syncwarp();
+            }
+            if (elect_one()) tc_commit(BAR(16));
+            __syncwarp();
         }
+    } else {
+        const int ct = tid - 64;
+        uint32_t it = 0;
+        for (long long kb = blockIdx.x; kb < nkb; kb += gridDim.x, ++it) {
+            const uint32_t rs = it % D0_NRAW, rph = (it / D0_NRAW) & 1;
+            const uint32_t cs = it % D0_NCONV, cph = (it / D0_NCONV) & 1;
+            mbar_wait(BAR(0 + rs), rph);
+            mbar_wait(BAR(12 + cs), cph ^ 1);
+            const uint8_t *rawp = raw_gen + rs * D0_RAW;
+            const float4 *src = reinterpret_cast<const float4 *>(rawp);
+            float4 *hi = reinterpret_cast<float4 *>(conv_gen + cs * D0_CONV);
+            float4 *lo = reinterpret_cast<float4 *>(conv_gen + cs * D0_CONV + DW_OPER);
+            float4 *bh = reinterpret_cast<float4 *>(conv_gen + cs * D0_CONV + 2 * DW_OPER);
+            float4 *bl = reinterpret_cast<float4 *>(conv_gen + cs * D0_CONV + 2 * DW_OPER + DW_PANEL);
+            {   // B panel: row lr = [x (16 floats) | 1 | 0 x 15], 32-byte chunk c stored at c ^ (lr & 3)
+                const int lr = (ct & 63) >> 2, j = ct & 3;
+                const long long m = (kb >> 3) * TM + (kb & 7) * DW_KROWS + lr;
+                float4 v, l = make_float4(0.f, 0.f, 0.f, 0.f);
+                int chunk;
+                if (ct < 64) {
+                    chunk = j >> 1;
+                    v = (m < M) ? reinterpret_cast<const float4 *>(rawp + DW_OPER)[lr * 4 + j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    l.x = tf32_rna(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u));
+                    l.y = tf32_rna(v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u));
+                    l.z = tf32_rna(v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u));
+                    l.w = tf32_rna(v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
+                } else {
+                    chunk = 2 + (j >> 1);
+                    v = make_float4(j == 0 ? 1.f : 0.f, 0.f, 0.f, 0.f);
+                }
+                const int o = (lr << 3) | ((chunk ^ (lr & 3)) << 1) | (j & 1);
+                bh[o] = v;
+                bl[o] = l;
+            }
+#pragma unroll 4
+            for (int f = ct; f < DW_OPER / 16; f += 128) {
+                const int pnl = f >> 7, lr = (f >> 3) & 15, p16 = f & 7;
+                const int c16 = p16 ^ (lr & 7);
+                const int d16 = (((c16 >> 1) ^ (lr & 3)) << 1) | (c16 & 1);
+                const float4 v = src[f];
+                float4 l;
+                l.x = tf32_rna(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u));
+                l.y = tf32_rna(v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u));
+                l.z = tf32_rna(v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u));
+                l.w = tf32_rna(v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
+                const int o = (pnl << 7) | (lr << 3) | d16;
+                hi[o] = v;
+                lo[o] = l;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(BAR(8 + cs)); mbar_arrive(BAR(4 + rs)); }
+        }
+        if (has_work) {
+            mbar_wait(BAR(16), 0);
+            tc_fence_after();
+            const int q = warp & 3;
+            const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+            for (int jj = 0; jj < 2; ++jj) {
+                const int jt = (jj + (blockIdx.x >> 3)) & 1;
+                const int k = jt * 128 + q * 32 + lane;
+                uint32_t v[32];
+                tmem_ld32(tmem + lane_addr + jt * 32, v);
+                float4 *o = reinterpret_cast<float4 *>(gW0 + (size_t)k * 16);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int r = rl + 4 * u;
-            const float a[4] = {d1[u].x, d1[u].y, d1[u].z, d1[u].w};
-            const float dv = ds[r];
-            const uint32_t mb = mk[u] >> shift;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                sb0[c] += a[c];
-                sc[c] += (mb >> c) & 1u ? dv : 0.f;
-#pragma unroll
-                for (int e = 0; e < 16; ++e) acc[c][e] = fmaf(a[c], xs[r][e], acc[c][e]);
+                for (int c = 0; c < 4; ++c)
+                    atomicAdd(o + c, make_float4(__uint_as_float(v[c * 4]), __uint_as_float(v[c * 4 + 1]), __uint_as_float(v[c * 4 + 2]),
+                                                 __uint_as_float(v[c * 4 + 3])));
+                atomicAdd(gb0 + k, __uint_as_float(v[16]));
             }
         }
-        __syncthreads();
     }
-    // reduce the 4 row lanes of every column group in shared memory, then one atomic per output element and CTA
-    __shared__ float red[64][4 * 18 + 1];
-    for (int pass = 1; pass < 4; ++pass) {
-        __syncthreads();
-        if (rl == pass) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-#pragma unroll
-                for (int e = 0; e < 16; ++e) red[cg][c * 18 + e] = acc[c][e];
-                red[cg][c * 18 + 16] = sb0[c]; red[cg][c * 18 + 17] = sc[c];
-            }
-        }
-        __syncthreads();
-        if (rl == 0) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-#pragma unroll
-                for (int e = 0; e < 16; ++e) acc[c][e] += red[cg][c * 18 + e];
-                sb0[c] += red[cg][c * 18 + 16]; sc[c] += red[cg][c * 18 + 17];
-            }
-        }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64u) : "memory");
     }
-    if (rl == 0) {
+}
+
+// c[j] = sum_m relu'(h2)[m][j] dsdf[m]  ->  gb1[j] += w2[j] c[j],  gW2[j] += b1[j] c[j]  (the other part of gW2 comes from
+// k_dw1_tc).  thread = (storage word w = tid & 7, row lane tid >> 3); 36 B/sample, a few tens of microseconds
+__global__ void __launch_bounds__(256) k_mask_colsum(long long M_host, const int32_t *__restrict__ M_dev, const uint32_t *__restrict__ mask2,
+                                                      const float *__restrict__ dsdf, const float *__restrict__ b1, const float *__restrict__ w2,
+                                                      float *__restrict__ gb1, float *__restrict__ gW2) {
+    const long long M = M_dev ? min((long long)*M_dev, M_host) : M_host;
+    const int w = threadIdx.x & 7, rl = threadIdx.x >> 3;
+    float acc[32];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int k = cg * 4 + c;
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    for (long long m = (long long)blockIdx.x * 32 + rl; m < M; m += (long long)gridDim.x * 32) {
+        const uint32_t mk = mask2[(size_t)m * 8 + w];
+        const float d = dsdf[m];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) atomicAdd(gW0 + k * 16 + e, acc[c][e]);
-            atomicAdd(gb0 + k, sb0[c]);
-            atomicAdd(gb1 + k, w2[k] * sc[c]);
-            atomicAdd(gW2 + k, b1[k] * sc[c]);
-        }
+        for (int i = 0; i < 32; ++i) acc[i] += (mk >> i) & 1u ? d : 0.f;
     }
+    __shared__ float red[32][257];
+    const int cb = 2 * (w & 3) + (w >> 2);               // storage word g*4+kk holds columns 32(2kk+g)..+31
+#pragma unroll
+    for (int i = 0; i < 32; ++i) red[rl][cb * 32 + i] = acc[i];
+    __syncthreads();
+    const int j = threadIdx.x;
+    float c = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) c += red[r][j];
+    atomicAdd(gb1 + j, w2[j] * c);
+    atomicAdd(gW2 + j, b1[j] * c);
 }
 
 }  // namespace tc
@@ -1148,9 +1337,12 @@ extern "C" int nl_mlp_tc_train(int64_t M, const int32_t *d_M_dev, const float *f
         return nl_set_error("nl_mlp_tc_train: decoder gradients requested but a buffer is null");
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc::k_mlp_tc_train<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::k_mlp_tc_train<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL);
+        cudaError_t e = cudaFuncSetAttribute(tc::k_mlp_tc_train<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::k_mlp_tc_train<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::k_mlp_tc_train<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::k_mlp_tc_train<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::k_dw1_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::DW_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::k_dw0_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::D0_SMEM);
         if (e != cudaSuccess) return nl_set_error_code(NL_ERR_CUDA, cudaGetErrorString(e));
         configured = true;
     }
@@ -1165,6 +1357,7 @@ extern "C" int nl_mlp_tc_train(int64_t M, const int32_t *d_M_dev, const float *f
     static long long *dbg_dev = nullptr;
     static int dbg_calls = 0;
     const bool want_dbg = getenv("NL_TC_TIMELINE") != nullptr;
+    static const bool use_ts = [] { const char *e = getenv("NL_TC_TS"); return e ? atoi(e) != 0 : true; }();   // A operands of the backward GEMMs from TMEM (NL_TC_TS=0: shared memory)
     if (want_dbg && !dbg_dev) { cudaMalloc(&dbg_dev, 4 * 25 * 8 * sizeof(long long)); cudaMemset(dbg_dev, 0, 4 * 25 * 8 * sizeof(long long)); }
     p.dbg = want_dbg ? dbg_dev : nullptr;
     if (grads) {
@@ -1172,12 +1365,14 @@ extern "C" int nl_mlp_tc_train(int64_t M, const int32_t *d_M_dev, const float *f
         p.act_h1 = act; p.act_dh1 = act + panel; p.act_dsdf = act + 2 * panel;
         p.act_mask2 = reinterpret_cast<uint32_t *>(act + 2 * panel + (size_t)ntiles * tc::TM);
         p.gb2 = grads->gb2;
-        tc::k_mlp_tc_train<true><<<grid, tc::NTHREADS_TRAIN, tc::SMEM_TOTAL, stream>>>(p);
+        if (use_ts) tc::k_mlp_tc_train<true, true><<<grid, tc::NTHREADS_TRAIN, tc::SMEM_TOTAL, stream>>>(p);
+        else tc::k_mlp_tc_train<true, false><<<grid, tc::NTHREADS_TRAIN, tc::SMEM_TOTAL, stream>>>(p);
         tc::k_dw1_tc<<<sms, tc::NTHREADS, tc::DW_SMEM, stream>>>(M, d_M_dev, p.act_mask2, p.act_dsdf, p.act_h1, W1, w2, grads->gW1, grads->gW2);
-        tc::k_dw0_panels<<<sms * 2, 256, 0, stream>>>(M, d_M_dev, p.act_dh1, p.act_mask2, p.act_dsdf, feats, b1, w2, grads->gW0, grads->gb0,
-                                                      grads->gb1, grads->gW2);
+        tc::k_dw0_tc<<<sms, tc::NTHREADS, tc::D0_SMEM, stream>>>(M, d_M_dev, p.act_dh1, feats, grads->gW0, grads->gb0);
+        tc::k_mask_colsum<<<sms * 2, 256, 0, stream>>>(M, d_M_dev, p.act_mask2, p.act_dsdf, b1, w2, grads->gb1, grads->gW2);
     } else {
-        tc::k_mlp_tc_train<false><<<grid, tc::NTHREADS_TRAIN, tc::SMEM_TOTAL, stream>>>(p);
+        if (use_ts) tc::k_mlp_tc_train<false, true><<<grid, tc::NTHREADS_TRAIN, tc::SMEM_TOTAL, stream>>>(p);
+        else tc::k_mlp_tc_train<false, false><<<grid, tc::NTHREADS_TRAIN, tc::SMEM_TOTAL, stream>>>(p);
     }
     NL_CHECK_LAUNCH("nl_mlp_tc_train");
     if (want_dbg && ++dbg_calls == 8) {   // debug only: dump one steady-state tile timeline of CTA 0 (synchronises)

@@ -92,20 +92,32 @@ enum { SCAN_HITS = 0, SCAN_SAMPLES = 1 };
 template <int MODE>
 __global__ void __launch_bounds__(1024) k_scan(int n, const int32_t *__restrict__ in, int32_t *__restrict__ out,
                                                 int32_t *__restrict__ hitray, nl_render_stats *stats, int sample_capacity) {
-    // tiles of 4096 elements: every thread owns 4 consecutive ones (coalesced 16-byte accesses), warp shuffle scan,
-    // 32 warp totals scanned by warp 0, running carry across tiles
-    __shared__ int wsum[32];
-    __shared__ int carry_s;
+    // tiles of 4096 elements: every thread owns 4 consecutive ones (one 16-byte load, issued one tile ahead so that its
+    // latency hides behind the previous tile), warp shuffle scan, then every warp scans the 32 warp totals redundantly:
+    // one __syncthreads per tile (the totals are double-buffered) and the running carry stays in registers
+    __shared__ int wsum[2][32];
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    if (t == 0) carry_s = 0;
-    __syncthreads();
-    for (int base = 0; base < n; base += 4096) {
+    auto load4 = [&](int i0) {
+        int4 x = make_int4(0, 0, 0, 0);
+        if (i0 + 3 < n) {
+            x = *reinterpret_cast<const int4 *>(in + i0);
+        } else {
+            if (i0 < n) x.x = in[i0];
+            if (i0 + 1 < n) x.y = in[i0 + 1];
+            if (i0 + 2 < n) x.z = in[i0 + 2];
+        }
+        return x;
+    };
+    int carry = 0;
+    int4 nxt = load4(t * 4);
+    for (int base = 0, par = 0; base < n; base += 4096, par ^= 1) {
         const int i0 = base + t * 4;
-        int v[4];
+        const int4 x = nxt;
+        if (base + 4096 < n) nxt = load4(i0 + 4096);
+        int v[4] = {x.x, x.y, x.z, x.w};
+        if (MODE == SCAN_HITS) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int x = (i0 + k < n) ? in[i0 + k] : 0;
-            v[k] = (MODE == SCAN_HITS) ? (x > 0) : x;
+            for (int k = 0; k < 4; ++k) v[k] = v[k] > 0;
         }
         const int mine = v[0] + v[1] + v[2] + v[3];
         int incl = mine;
@@ -114,38 +126,41 @@ __global__ void __launch_bounds__(1024) k_scan(int n, const int32_t *__restrict_
             const int y = __shfl_up_sync(0xffffffffu, incl, off);
             if (lane >= off) incl += y;
         }
-        if (lane == 31) wsum[w] = incl;
+        if (lane == 31) wsum[par][w] = incl;
         __syncthreads();
-        if (w == 0) {
-            int ws = wsum[lane], wi = ws;
+        const int ws = wsum[par][lane];
+        int wi = ws;
 #pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const int y = __shfl_up_sync(0xffffffffu, wi, off);
-                if (lane >= off) wi += y;
-            }
-            wsum[lane] = wi - ws;   // exclusive prefix of the warp totals
+        for (int off = 1; off < 32; off <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, wi, off);
+            if (lane >= off) wi += y;
         }
-        __syncthreads();
-        const int carry = carry_s;
-        int run = carry + wsum[w] + incl - mine;
+        const int wexcl = __shfl_sync(0xffffffffu, wi - ws, w);      // exclusive prefix of this warp's total
+        const int tile_total = __shfl_sync(0xffffffffu, wi, 31);
+        int run = carry + wexcl + incl - mine;
+        if (MODE == SCAN_HITS) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (i0 + k < n) {
-                if (MODE == SCAN_HITS) {
+            for (int k = 0; k < 4; ++k) {
+                if (i0 + k < n) {
                     out[i0 + k] = v[k] ? run : -1;
                     if (v[k]) hitray[run] = i0 + k;
-                } else {
-                    out[i0 + k] = run;
                 }
+                run += v[k];
             }
-            run += v[k];
+        } else {
+            const int4 o = make_int4(run, run + v[0], run + v[0] + v[1], run + v[0] + v[1] + v[2]);
+            if (i0 + 3 < n) {
+                *reinterpret_cast<int4 *>(out + i0) = o;
+            } else {
+                if (i0 < n) out[i0] = o.x;
+                if (i0 + 1 < n) out[i0 + 1] = o.y;
+                if (i0 + 2 < n) out[i0 + 2] = o.z;
+            }
         }
-        __syncthreads();
-        if (t == 1023) carry_s = run;   // thread 1023's running value = carry + tile total
-        __syncthreads();
+        carry += tile_total;
     }
     if (t == 0) {
-        const int total = carry_s;
+        const int total = carry;
         if (MODE == SCAN_HITS) {
             stats->n_hit_rays = total;
         } else {
@@ -378,6 +393,8 @@ extern "C" int nl_render_samples(const nl_render_args *a, void *stream_) {
     if (a->workspace_bytes < nl_render_workspace_bytes(a->n_rays)) return nl_set_error("nl_render_samples: workspace too small");
     if (!(a->step_size > 0.f) || !(a->voxel_size > 0.f)) return nl_set_error("nl_render_samples: step_size and voxel_size must be > 0");
     if (a->d_noise && a->noise_stride <= 0) return nl_set_error("nl_render_samples: noise_stride must be > 0 with d_noise");
+    if ((((uintptr_t)a->d_ray_nsamp | (uintptr_t)a->d_ray_offset | (uintptr_t)a->d_workspace) & 15u) != 0)
+        return nl_set_error("nl_render_samples: d_ray_nsamp, d_ray_offset and d_workspace must be 16-byte aligned");
     const int R = a->n_rays;
     Workspace ws = carve(a->d_workspace, R);
     cudaMemsetAsync(a->d_stats, 0, sizeof(nl_render_stats), stream);
