@@ -150,7 +150,7 @@ typedef struct {
     float *d_s_depth;      /* f32[cap] sampled_point_depth                                          */
     float *d_s_xyz;        /* f32[cap,3] ray_o + ray_d * depth (mul then add, unfused) render_helpers.py:9-10 */
     uint8_t *d_s_flag;     /* u8[cap] bit0 front_mask, bit1 sdf_mask (criterion.py:67-82); 0 if d_gt_depth NULL */
-    int32_t *d_ray_nsamp;  /* i32[R] valid samples per ray (0 for missed rays); 16-byte aligned (also d_ray_offset, d_workspace) */
+    int32_t *d_ray_nsamp;  /* i32[R] valid samples per ray (0 for missed rays); 16-byte aligned (also d_ray_offset, d_hit_rank, d_workspace) */
     int32_t *d_ray_offset; /* i32[R] offset of the ray's first sample in the compact list */
 } nl_render_args;
 

@@ -14,6 +14,8 @@
 //
 // Numerics follow render_helpers.py:65: p = (xyz - centre) / voxel_size + 0.5 with a true division;
 // corner k = 4*kx + 2*ky + kz; w_k = (ax * ay) * az with a = p or 1-p.
+#include <cstdlib>
+
 #include "nl_cuda.cuh"
 
 namespace {
@@ -83,6 +85,10 @@ __global__ void __launch_bounds__(128) k_gather_fwd(long long M_host, const int3
 }
 
 // Backward: autograd of the forward above w.r.t. the embedding rows (scatter-add) and xyz (-> pose).
+// MERGE: consecutive samples of a ray usually sit in the same voxel (step = voxel/2) and therefore scatter to the same 8
+// rows; lanes at even positions of such a run add their right neighbour's (already bf16-rounded) contributions with one
+// shuffle per value and issue the atomics for both, the odd lanes issue none: ~40 % fewer L2 atomics.
+template <bool MERGE>
 __global__ void __launch_bounds__(128) k_gather_bwd(long long M_host, const int32_t *__restrict__ M_dev,
                                                      const float *__restrict__ xyz, const int32_t *__restrict__ vox,
                                                      const float *__restrict__ centres, const int32_t *__restrict__ vox2row,
@@ -100,51 +106,83 @@ __global__ void __launch_bounds__(128) k_gather_bwd(long long M_host, const int3
     }
     const long long M = M_dev ? min((long long)*M_dev, M_host) : M_host;
     const bool want_x = want_pose || dxyz_out != nullptr;
+    const int lane = threadIdx.x & 31;
     for (long long base = (long long)blockIdx.x * blockDim.x; base < M; base += (long long)gridDim.x * blockDim.x) {
         const long long i = base + threadIdx.x;
         const bool active = i < M;
         float gx = 0.f, gy = 0.f, gz = 0.f;
         int frame = -1;
+        int v = -1;
+        int rows[8];
+        float g[16];
+        Tri t;
+        t.px = t.py = t.pz = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) rows[k] = -1;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) g[e] = 0.f;
         if (active) {
-            const int v = vox[i];
+            v = vox[i];
             const int4 r0 = *reinterpret_cast<const int4 *>(vox2row + (size_t)v * 8);
             const int4 r1 = *reinterpret_cast<const int4 *>(vox2row + (size_t)v * 8 + 4);
-            const int rows[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+            rows[0] = r0.x; rows[1] = r0.y; rows[2] = r0.z; rows[3] = r0.w; rows[4] = r1.x; rows[5] = r1.y; rows[6] = r1.z; rows[7] = r1.w;
             const float4 *gp = dfeats + i * 4;
             const float4 g0 = gp[0], g1 = gp[1], g2 = gp[2], g3 = gp[3];
-            const float g[16] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x, g2.y, g2.z, g2.w, g3.x, g3.y, g3.z, g3.w};
-            const Tri t = tri_coords(xyz + i * 3, centres + (size_t)v * 3, voxel_size);
-            const float inv_vs = 1.0f / voxel_size;
+            g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+            g[8] = g2.x; g[9] = g2.y; g[10] = g2.z; g[11] = g2.w; g[12] = g3.x; g[13] = g3.y; g[14] = g3.z; g[15] = g3.w;
+            t = tri_coords(xyz + i * 3, centres + (size_t)v * 3, voxel_size);
+        }
+        // run structure inside the warp (MERGE): emitters = even positions of a run of equal voxel ids
+        bool emit = true, take = false;
+        if (MERGE && grad_emb) {
+            const int vprev = __shfl_up_sync(0xffffffffu, v, 1);
+            const bool head = (lane == 0) || (vprev != v) || (v < 0);
+            const unsigned hf = __ballot_sync(0xffffffffu, head);
+            const int head_lane = 31 - __clz(hf & (0xffffffffu >> (31 - lane)));
+            emit = ((lane - head_lane) & 1) == 0;
+            take = emit && lane < 31 && !((hf >> (lane + 1)) & 1u);   // the right neighbour continues this run
+        }
+        const float inv_vs = 1.0f / voxel_size;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float ax = (k & 4) ? t.px : __fsub_rn(1.0f, t.px);
-                const float ay = (k & 2) ? t.py : __fsub_rn(1.0f, t.py);
-                const float az = (k & 1) ? t.pz : __fsub_rn(1.0f, t.pz);
-                const float w = __fmul_rn(__fmul_rn(ax, ay), az);
-                if (rows[k] < 0) continue;
-                if (grad_emb) {
-                    // d(emb row): grad_out * w, rounded to bf16 where autograd casts it for a bf16 table
-                    float c[16];
+        for (int k = 0; k < 8; ++k) {
+            const float ax = (k & 4) ? t.px : __fsub_rn(1.0f, t.px);
+            const float ay = (k & 2) ? t.py : __fsub_rn(1.0f, t.py);
+            const float az = (k & 1) ? t.pz : __fsub_rn(1.0f, t.pz);
+            const float w = __fmul_rn(__fmul_rn(ax, ay), az);
+            const bool has_row = rows[k] >= 0;
+            if (grad_emb) {
+                // d(emb row): grad_out * w, rounded to bf16 where autograd casts it for a bf16 table
+                float c[16];
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) { c[e] = g[e] * w; if (round_bf16) c[e] = nl_round_bf16(c[e]); }
+                for (int e = 0; e < 16; ++e) {
+                    c[e] = has_row ? g[e] * w : 0.f;
+                    if (round_bf16) c[e] = nl_round_bf16(c[e]);
+                    if (MERGE) {
+                        const float nb = __shfl_down_sync(0xffffffffu, c[e], 1);
+                        if (take) c[e] += nb;
+                    }
+                }
+                if (has_row && emit) {
                     float4 *dst = reinterpret_cast<float4 *>(grad_emb + (size_t)rows[k] * 16);
                     atomicAdd(dst + 0, make_float4(c[0], c[1], c[2], c[3]));
                     atomicAdd(dst + 1, make_float4(c[4], c[5], c[6], c[7]));
                     atomicAdd(dst + 2, make_float4(c[8], c[9], c[10], c[11]));
                     atomicAdd(dst + 3, make_float4(c[12], c[13], c[14], c[15]));
                 }
-                if (want_x) {
-                    float f[16];
-                    unpack8(__ldg(emb + (size_t)rows[k] * 2), f);
-                    unpack8(__ldg(emb + (size_t)rows[k] * 2 + 1), f + 8);
-                    float dot = 0.f;  // d loss / d w_k = sum_e grad_out[e] * emb_k[e]
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) dot = fmaf(g[e], f[e], dot);
-                    gx += dot * ((k & 4) ? 1.f : -1.f) * ay * az;
-                    gy += dot * ((k & 2) ? 1.f : -1.f) * ax * az;
-                    gz += dot * ((k & 1) ? 1.f : -1.f) * ax * ay;
-                }
             }
+            if (want_x && has_row) {
+                float f[16];
+                unpack8(__ldg(emb + (size_t)rows[k] * 2), f);
+                unpack8(__ldg(emb + (size_t)rows[k] * 2 + 1), f + 8);
+                float dot = 0.f;  // d loss / d w_k = sum_e grad_out[e] * emb_k[e]
+#pragma unroll
+                for (int e = 0; e < 16; ++e) dot = fmaf(g[e], f[e], dot);
+                gx += dot * ((k & 4) ? 1.f : -1.f) * ay * az;
+                gy += dot * ((k & 2) ? 1.f : -1.f) * ax * az;
+                gz += dot * ((k & 1) ? 1.f : -1.f) * ax * ay;
+            }
+        }
+        if (active) {
             gx *= inv_vs; gy *= inv_vs; gz *= inv_vs;  // d p / d xyz = 1 / voxel_size
             if (dxyz_out) { dxyz_out[i * 3] = gx; dxyz_out[i * 3 + 1] = gy; dxyz_out[i * 3 + 2] = gz; }
             if (want_pose) frame = ray_frame ? ray_frame[s_ray[i]] : 0;
@@ -220,10 +258,17 @@ extern "C" int nl_gather_trilinear_bwd(int64_t M, const int32_t *d_M_dev, const 
     if (pose_acc && (!s_ray || !s_depth || !ray_dir_local || n_frames <= 0 || n_frames > 1024))
         return nl_set_error("nl_gather_trilinear_bwd: pose accumulation needs s_ray, s_depth, ray_dir_local, 0 < n_frames <= 1024");
     const size_t smem = pose_acc ? sizeof(float) * 12 * (size_t)n_frames : 0;
-    k_gather_bwd<<<persistent_blocks(M, 128, 16), 128, smem, (cudaStream_t)stream>>>(
-        M, d_M_dev, xyz, vox, centres, vox2row, reinterpret_cast<const uint4 *>(emb), voxel_size,
-        reinterpret_cast<const float4 *>(dfeats), round_bf16, grad_emb, dxyz, s_ray, s_depth, ray_dir_local, ray_frame,
-        n_frames, pose_acc);
+    static const bool merge = [] { const char *e = getenv("NL_GATHER_MERGE"); return e ? atoi(e) != 0 : true; }();
+    if (merge)
+        k_gather_bwd<true><<<persistent_blocks(M, 128, 16), 128, smem, (cudaStream_t)stream>>>(
+            M, d_M_dev, xyz, vox, centres, vox2row, reinterpret_cast<const uint4 *>(emb), voxel_size,
+            reinterpret_cast<const float4 *>(dfeats), round_bf16, grad_emb, dxyz, s_ray, s_depth, ray_dir_local, ray_frame,
+            n_frames, pose_acc);
+    else
+        k_gather_bwd<false><<<persistent_blocks(M, 128, 16), 128, smem, (cudaStream_t)stream>>>(
+            M, d_M_dev, xyz, vox, centres, vox2row, reinterpret_cast<const uint4 *>(emb), voxel_size,
+            reinterpret_cast<const float4 *>(dfeats), round_bf16, grad_emb, dxyz, s_ray, s_depth, ray_dir_local, ray_frame,
+            n_frames, pose_acc);
     NL_CHECK_LAUNCH("nl_gather_trilinear_bwd");
     return NL_OK;
 }

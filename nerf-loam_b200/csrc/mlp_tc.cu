@@ -908,7 +908,8 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(DW_PANEL >> 4) << 16) | (32ull << 32) | (1ull << 46) | (1ull << 61);
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) k_dw1_tc(long long M_host, const int32_t *__restrict__ M_dev, const uint32_t *__restrict__ act_mask2,
+template <int NCW>   // converter warps (4 or 8)
+__global__ void __launch_bounds__(64 + 32 * NCW, 1) k_dw1_tc(long long M_host, const int32_t *__restrict__ M_dev, const uint32_t *__restrict__ act_mask2,
                                                          const float *__restrict__ act_dsdf, const float *__restrict__ act_h1,
                                                          const float *__restrict__ W1, const float *__restrict__ w2, float *__restrict__ gW1,
                                                          float *__restrict__ gW2) {
@@ -928,8 +929,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dw1_tc(long long M_host, const 
     const long long M = M_dev ? min((long long)*M_dev, M_host) : M_host;
     const long long nkb = ((M + TM - 1) / TM) * (TM / DW_KROWS);   // K-blocks of 16 rows (whole tiles: padded rows have dsdf = 0)
     if (tid == 0) {
-        for (int i = 0; i < DW_NRAW; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(4 + i), 4); }
-        for (int i = 0; i < DW_NCONV; ++i) { mbar_init(BAR(8 + i), 4); mbar_init(BAR(11 + i), 1); }
+        for (int i = 0; i < DW_NRAW; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(4 + i), NCW); }
+        for (int i = 0; i < DW_NCONV; ++i) { mbar_init(BAR(8 + i), NCW); mbar_init(BAR(11 + i), 1); }
         mbar_init(BAR(14), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -997,8 +998,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dw1_tc(long long M_host, const 
         // converters (128 threads).  Stored h1 image: K-major SWIZZLE_128B (16 B chunk c of row r at c ^ (r & 7)); operand
         // tiles: MN-major SWIZZLE_128B_BASE32B (32 B chunk c of row r at c ^ (r & 3)).  hi = the fp32 bits of d*h1
         // (truncated to tf32 by the hardware), lo = tf32(x - trunc(x)).
+        constexpr int NCT = 32 * NCW;                              // converter threads
         const int ct = tid - 64;
-        const int m_pnl = ct >> 4, m_lr = ct & 15;                 // mask expansion: one (column block, sample row) per thread
+        // mask expansion: one (column block, sample row) per group of NCT/128 threads, 8 / (NCT/128) float4 each
+        constexpr int MSPLIT = NCT / 128;
+        const int m_pair = ct / MSPLIT, m_part = ct % MSPLIT;
+        const int m_pnl = m_pair >> 4, m_lr = m_pair & 15;
         const int m_word = (m_pnl & 1) * 4 + (m_pnl >> 1);         // storage order of k_mlp_tc_train: [group][kk]
         uint32_t it = 0;
         for (long long kb = blockIdx.x; kb < nkb; kb += gridDim.x, ++it) {
@@ -1016,7 +1021,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dw1_tc(long long M_host, const 
             {
                 const uint32_t mk = bits[m_lr * 8 + m_word];
 #pragma unroll
-                for (int c16 = 0; c16 < 8; ++c16) {
+                for (int cc = 0; cc < 8 / MSPLIT; ++cc) {
+                    const int c16 = m_part * (8 / MSPLIT) + cc;
                     const int d16 = (((c16 >> 1) ^ (m_lr & 3)) << 1) | (c16 & 1);
                     am[(m_pnl << 7) | (m_lr << 3) | d16] =
                         make_float4((mk >> (4 * c16)) & 1u ? 1.f : 0.f, (mk >> (4 * c16 + 1)) & 1u ? 1.f : 0.f,
@@ -1024,7 +1030,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dw1_tc(long long M_host, const 
                 }
             }
 #pragma unroll 4
-            for (int f = ct; f < DW_OPER / 16; f += 128) {        // f: float4 index = (panel, local row, stored chunk)
+            for (int f = ct; f < DW_OPER / 16; f += NCT) {        // f: float4 index = (panel, local row, stored chunk)
                 const int pnl = f >> 7, lr = (f >> 3) & 15, p16 = f & 7;
                 const int c16 = p16 ^ (lr & 7);                   // logical 16 B chunk (r0 is a multiple of 16: r & 7 == lr & 7)
                 const int d16 = (((c16 >> 1) ^ (lr & 3)) << 1) | (c16 & 1);
@@ -1051,9 +1057,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dw1_tc(long long M_host, const 
             const int q = warp & 3;
             const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
             // all CTAs finish at about the same time: start each one at a different (accumulator, column block) so the
-            // 148 partial sums do not hammer the same L2 lines simultaneously
-            for (int jj = 0; jj < 2; ++jj) {
-                const int jt = (jj + (blockIdx.x >> 3)) & 1;
+            // 148 partial sums do not hammer the same L2 lines simultaneously.  With 8 converter warps each accumulator
+            // half is drained by its own 4 warps.
+            for (int jj = 0; jj < (NCW == 8 ? 1 : 2); ++jj) {
+                const int jt = NCW == 8 ? ((warp - 2) >> 2) : ((jj + (blockIdx.x >> 3)) & 1);
                 const int j = jt * 128 + q * 32 + lane;
                 const float w2j = w2[j];
                 float dot = 0.f;
@@ -1095,7 +1102,8 @@ constexpr int D0_CONV = 2 * DW_OPER + 2 * DW_PANEL;   // A hi | A lo | B hi | B 
 constexpr int D0_NRAW = 4, D0_NCONV = 4;
 constexpr int D0_SMEM = D0_NRAW * D0_RAW + D0_NCONV * D0_CONV + 1024 + 1024;
 
-__global__ void __launch_bounds__(NTHREADS, 1) k_dw0_tc(long long M_host, const int32_t *__restrict__ M_dev, const float *__restrict__ act_dh1,
+template <int NCW>
+__global__ void __launch_bounds__(64 + 32 * NCW, 1) k_dw0_tc(long long M_host, const int32_t *__restrict__ M_dev, const float *__restrict__ act_dh1,
                                                          const float *__restrict__ feats, float *__restrict__ gW0, float *__restrict__ gb0) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -1112,8 +1120,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dw0_tc(long long M_host, const 
     const long long M = M_dev ? min((long long)*M_dev, M_host) : M_host;
     const long long nkb = ((M + TM - 1) / TM) * (TM / DW_KROWS);
     if (tid == 0) {
-        for (int i = 0; i < D0_NRAW; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(4 + i), 4); }
-        for (int i = 0; i < D0_NCONV; ++i) { mbar_init(BAR(8 + i), 4); mbar_init(BAR(12 + i), 1); }
+        for (int i = 0; i < D0_NRAW; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(4 + i), NCW); }
+        for (int i = 0; i < D0_NCONV; ++i) { mbar_init(BAR(8 + i), NCW); mbar_init(BAR(12 + i), 1); }
         mbar_init(BAR(16), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -1191,7 +1199,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dw0_tc(long long M_host, const 
             float4 *lo = reinterpret_cast<float4 *>(conv_gen + cs * D0_CONV + DW_OPER);
             float4 *bh = reinterpret_cast<float4 *>(conv_gen + cs * D0_CONV + 2 * DW_OPER);
             float4 *bl = reinterpret_cast<float4 *>(conv_gen + cs * D0_CONV + 2 * DW_OPER + DW_PANEL);
-            {   // B panel: row lr = [x (16 floats) | 1 | 0 x 15], 32-byte chunk c stored at c ^ (lr & 3)
+            if (ct < 128) {   // B panel: row lr = [x (16 floats) | 1 | 0 x 15], 32-byte chunk c stored at c ^ (lr & 3)
                 const int lr = (ct & 63) >> 2, j = ct & 3;
                 const long long m = (kb >> 3) * TM + (kb & 7) * DW_KROWS + lr;
                 float4 v, l = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1212,7 +1220,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dw0_tc(long long M_host, const 
                 bl[o] = l;
             }
 #pragma unroll 4
-            for (int f = ct; f < DW_OPER / 16; f += 128) {
+            for (int f = ct; f < DW_OPER / 16; f += 32 * NCW) {
                 const int pnl = f >> 7, lr = (f >> 3) & 15, p16 = f & 7;
                 const int c16 = p16 ^ (lr & 7);
                 const int d16 = (((c16 >> 1) ^ (lr & 3)) << 1) | (c16 & 1);
@@ -1235,8 +1243,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dw0_tc(long long M_host, const 
             tc_fence_after();
             const int q = warp & 3;
             const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-            for (int jj = 0; jj < 2; ++jj) {
-                const int jt = (jj + (blockIdx.x >> 3)) & 1;
+            for (int jj = 0; jj < (NCW == 8 ? 1 : 2); ++jj) {
+                const int jt = NCW == 8 ? ((warp - 2) >> 2) : ((jj + (blockIdx.x >> 3)) & 1);
                 const int k = jt * 128 + q * 32 + lane;
                 uint32_t v[32];
                 tmem_ld32(tmem + lane_addr + jt * 32, v);
@@ -1267,11 +1275,20 @@ __global__ void __launch_bounds__(256) k_mask_colsum(long long M_host, const int
     float acc[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-    for (long long m = (long long)blockIdx.x * 32 + rl; m < M; m += (long long)gridDim.x * 32) {
-        const uint32_t mk = mask2[(size_t)m * 8 + w];
-        const float d = dsdf[m];
+    const long long stride = (long long)gridDim.x * 32;
+    for (long long m0 = (long long)blockIdx.x * 32 + rl; m0 < M; m0 += 4 * stride) {   // 4 independent rows in flight per thread
+        uint32_t mk[4];
+        float d[4];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] += (mk >> i) & 1u ? d : 0.f;
+        for (int u = 0; u < 4; ++u) {
+            const long long m = m0 + u * stride;
+            mk[u] = m < M ? mask2[(size_t)m * 8 + w] : 0u;
+            d[u] = m < M ? dsdf[m] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] += (mk[u] >> i) & 1u ? d[u] : 0.f;
     }
     __shared__ float red[32][257];
     const int cb = 2 * (w & 3) + (w >> 2);               // storage word g*4+kk holds columns 32(2kk+g)..+31
@@ -1341,8 +1358,10 @@ extern "C" int nl_mlp_tc_train(int64_t M, const int32_t *d_M_dev, const float *f
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::k_mlp_tc_train<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::k_mlp_tc_train<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::k_mlp_tc_train<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::k_dw1_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::DW_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::k_dw0_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::D0_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::k_dw1_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::DW_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::k_dw1_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::DW_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::k_dw0_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::D0_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::k_dw0_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::D0_SMEM);
         if (e != cudaSuccess) return nl_set_error_code(NL_ERR_CUDA, cudaGetErrorString(e));
         configured = true;
     }
@@ -1357,6 +1376,7 @@ extern "C" int nl_mlp_tc_train(int64_t M, const int32_t *d_M_dev, const float *f
     static long long *dbg_dev = nullptr;
     static int dbg_calls = 0;
     const bool want_dbg = getenv("NL_TC_TIMELINE") != nullptr;
+    static const int conv_warps = [] { const char *e = getenv("NL_DW_CONV_WARPS"); return (e && atoi(e) == 4) ? 4 : 8; }();   // converter warps of the weight-gradient kernels
     static const bool use_ts = [] { const char *e = getenv("NL_TC_TS"); return e ? atoi(e) != 0 : true; }();   // A operands of the backward GEMMs from TMEM (NL_TC_TS=0: shared memory)
     if (want_dbg && !dbg_dev) { cudaMalloc(&dbg_dev, 4 * 25 * 8 * sizeof(long long)); cudaMemset(dbg_dev, 0, 4 * 25 * 8 * sizeof(long long)); }
     p.dbg = want_dbg ? dbg_dev : nullptr;
@@ -1367,9 +1387,14 @@ extern "C" int nl_mlp_tc_train(int64_t M, const int32_t *d_M_dev, const float *f
         p.gb2 = grads->gb2;
         if (use_ts) tc::k_mlp_tc_train<true, true><<<grid, tc::NTHREADS_TRAIN, tc::SMEM_TOTAL, stream>>>(p);
         else tc::k_mlp_tc_train<true, false><<<grid, tc::NTHREADS_TRAIN, tc::SMEM_TOTAL, stream>>>(p);
-        tc::k_dw1_tc<<<sms, tc::NTHREADS, tc::DW_SMEM, stream>>>(M, d_M_dev, p.act_mask2, p.act_dsdf, p.act_h1, W1, w2, grads->gW1, grads->gW2);
-        tc::k_dw0_tc<<<sms, tc::NTHREADS, tc::D0_SMEM, stream>>>(M, d_M_dev, p.act_dh1, feats, grads->gW0, grads->gb0);
-        tc::k_mask_colsum<<<sms * 2, 256, 0, stream>>>(M, d_M_dev, p.act_mask2, p.act_dsdf, b1, w2, grads->gb1, grads->gW2);
+        if (conv_warps == 8) {
+            tc::k_dw1_tc<8><<<sms, 320, tc::DW_SMEM, stream>>>(M, d_M_dev, p.act_mask2, p.act_dsdf, p.act_h1, W1, w2, grads->gW1, grads->gW2);
+            tc::k_dw0_tc<8><<<sms, 320, tc::D0_SMEM, stream>>>(M, d_M_dev, p.act_dh1, feats, grads->gW0, grads->gb0);
+        } else {
+            tc::k_dw1_tc<4><<<sms, 192, tc::DW_SMEM, stream>>>(M, d_M_dev, p.act_mask2, p.act_dsdf, p.act_h1, W1, w2, grads->gW1, grads->gW2);
+            tc::k_dw0_tc<4><<<sms, 192, tc::D0_SMEM, stream>>>(M, d_M_dev, p.act_dh1, feats, grads->gW0, grads->gb0);
+        }
+        tc::k_mask_colsum<<<sms * 8, 256, 0, stream>>>(M, d_M_dev, p.act_mask2, p.act_dsdf, b1, w2, grads->gb1, grads->gW2);
     } else {
         if (use_ts) tc::k_mlp_tc_train<false, true><<<grid, tc::NTHREADS_TRAIN, tc::SMEM_TOTAL, stream>>>(p);
         else tc::k_mlp_tc_train<false, false><<<grid, tc::NTHREADS_TRAIN, tc::SMEM_TOTAL, stream>>>(p);

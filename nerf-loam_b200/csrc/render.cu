@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(1024) k_scan(int n, const int32_t *__restrict_
     // latency hides behind the previous tile), warp shuffle scan, then every warp scans the 32 warp totals redundantly:
     // one __syncthreads per tile (the totals are double-buffered) and the running carry stays in registers
     __shared__ int wsum[2][32];
+    __shared__ int compact[MODE == SCAN_HITS ? 4096 : 1];
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     auto load4 = [&](int i0) {
         int4 x = make_int4(0, 0, 0, 0);
@@ -139,14 +140,30 @@ __global__ void __launch_bounds__(1024) k_scan(int n, const int32_t *__restrict_
         const int tile_total = __shfl_sync(0xffffffffu, wi, 31);
         int run = carry + wexcl + incl - mine;
         if (MODE == SCAN_HITS) {
+            // ranks as one 16-byte store; the compacted ray list of this tile is contiguous in the output, so it is staged in
+            // shared memory and written back coalesced
+            int4 o;
+            o.x = v[0] ? run : -1;
+            o.y = v[1] ? run + v[0] : -1;
+            o.z = v[2] ? run + v[0] + v[1] : -1;
+            o.w = v[3] ? run + v[0] + v[1] + v[2] : -1;
+            if (i0 + 3 < n) {
+                *reinterpret_cast<int4 *>(out + i0) = o;
+            } else {
+                if (i0 < n) out[i0] = o.x;
+                if (i0 + 1 < n) out[i0 + 1] = o.y;
+                if (i0 + 2 < n) out[i0 + 2] = o.z;
+            }
+            int loc = run - carry;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                if (i0 + k < n) {
-                    out[i0 + k] = v[k] ? run : -1;
-                    if (v[k]) hitray[run] = i0 + k;
-                }
-                run += v[k];
+                if (v[k]) compact[loc] = i0 + k;     // v[k] is 0 for i0 + k >= n
+                loc += v[k];
             }
+            __syncthreads();
+            for (int j = t; j < tile_total; j += 1024) hitray[carry + j] = compact[j];
+            // the next tile's writes to compact[] come after its own __syncthreads (warp totals), which every thread reaches
+            // only after finishing this copy
         } else {
             const int4 o = make_int4(run, run + v[0], run + v[0] + v[1], run + v[0] + v[1] + v[2]);
             if (i0 + 3 < n) {
@@ -393,8 +410,8 @@ extern "C" int nl_render_samples(const nl_render_args *a, void *stream_) {
     if (a->workspace_bytes < nl_render_workspace_bytes(a->n_rays)) return nl_set_error("nl_render_samples: workspace too small");
     if (!(a->step_size > 0.f) || !(a->voxel_size > 0.f)) return nl_set_error("nl_render_samples: step_size and voxel_size must be > 0");
     if (a->d_noise && a->noise_stride <= 0) return nl_set_error("nl_render_samples: noise_stride must be > 0 with d_noise");
-    if ((((uintptr_t)a->d_ray_nsamp | (uintptr_t)a->d_ray_offset | (uintptr_t)a->d_workspace) & 15u) != 0)
-        return nl_set_error("nl_render_samples: d_ray_nsamp, d_ray_offset and d_workspace must be 16-byte aligned");
+    if ((((uintptr_t)a->d_ray_nsamp | (uintptr_t)a->d_ray_offset | (uintptr_t)a->d_hit_rank | (uintptr_t)a->d_workspace) & 15u) != 0)
+        return nl_set_error("nl_render_samples: d_ray_nsamp, d_ray_offset, d_hit_rank and d_workspace must be 16-byte aligned");
     const int R = a->n_rays;
     Workspace ws = carve(a->d_workspace, R);
     cudaMemsetAsync(a->d_stats, 0, sizeof(nl_render_stats), stream);
