@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(128) k_gather_fwd(long long M_host, const int3
 // MERGE: consecutive samples of a ray usually sit in the same voxel (step = voxel/2) and therefore scatter to the same 8
 // rows; lanes at even positions of such a run add their right neighbour's (already bf16-rounded) contributions with one
 // shuffle per value and issue the atomics for both, the odd lanes issue none: ~40 % fewer L2 atomics.
-template <bool MERGE>
+template <int MERGE>   // 0: one atomic set per sample; 1: runs merged pairwise; 2: in groups of up to four
 __global__ void __launch_bounds__(128) k_gather_bwd(long long M_host, const int32_t *__restrict__ M_dev,
                                                      const float *__restrict__ xyz, const int32_t *__restrict__ vox,
                                                      const float *__restrict__ centres, const int32_t *__restrict__ vox2row,
@@ -133,14 +133,19 @@ __global__ void __launch_bounds__(128) k_gather_bwd(long long M_host, const int3
             t = tri_coords(xyz + i * 3, centres + (size_t)v * 3, voxel_size);
         }
         // run structure inside the warp (MERGE): emitters = even positions of a run of equal voxel ids
-        bool emit = true, take = false;
+        bool emit = true, take = false, take2 = false;
         if (MERGE && grad_emb) {
             const int vprev = __shfl_up_sync(0xffffffffu, v, 1);
             const bool head = (lane == 0) || (vprev != v) || (v < 0);
             const unsigned hf = __ballot_sync(0xffffffffu, head);
             const int head_lane = 31 - __clz(hf & (0xffffffffu >> (31 - lane)));
-            emit = ((lane - head_lane) & 1) == 0;
+            const int pos = lane - head_lane;
+            emit = (pos & 1) == 0;
             take = emit && lane < 31 && !((hf >> (lane + 1)) & 1u);   // the right neighbour continues this run
+            if (MERGE == 2) {
+                emit = (pos & 3) == 0;
+                take2 = emit && lane < 30 && !((hf >> (lane + 1)) & 3u);   // so does the lane after it (which holds a pair sum)
+            }
         }
         const float inv_vs = 1.0f / voxel_size;
 #pragma unroll
@@ -160,6 +165,10 @@ __global__ void __launch_bounds__(128) k_gather_bwd(long long M_host, const int3
                     if (MERGE) {
                         const float nb = __shfl_down_sync(0xffffffffu, c[e], 1);
                         if (take) c[e] += nb;
+                    }
+                    if (MERGE == 2) {
+                        const float nb = __shfl_down_sync(0xffffffffu, c[e], 2);
+                        if (take2) c[e] += nb;
                     }
                 }
                 if (has_row && emit) {
@@ -258,17 +267,16 @@ extern "C" int nl_gather_trilinear_bwd(int64_t M, const int32_t *d_M_dev, const 
     if (pose_acc && (!s_ray || !s_depth || !ray_dir_local || n_frames <= 0 || n_frames > 1024))
         return nl_set_error("nl_gather_trilinear_bwd: pose accumulation needs s_ray, s_depth, ray_dir_local, 0 < n_frames <= 1024");
     const size_t smem = pose_acc ? sizeof(float) * 12 * (size_t)n_frames : 0;
-    static const bool merge = [] { const char *e = getenv("NL_GATHER_MERGE"); return e ? atoi(e) != 0 : true; }();
-    if (merge)
-        k_gather_bwd<true><<<persistent_blocks(M, 128, 16), 128, smem, (cudaStream_t)stream>>>(
-            M, d_M_dev, xyz, vox, centres, vox2row, reinterpret_cast<const uint4 *>(emb), voxel_size,
-            reinterpret_cast<const float4 *>(dfeats), round_bf16, grad_emb, dxyz, s_ray, s_depth, ray_dir_local, ray_frame,
-            n_frames, pose_acc);
-    else
-        k_gather_bwd<false><<<persistent_blocks(M, 128, 16), 128, smem, (cudaStream_t)stream>>>(
-            M, d_M_dev, xyz, vox, centres, vox2row, reinterpret_cast<const uint4 *>(emb), voxel_size,
-            reinterpret_cast<const float4 *>(dfeats), round_bf16, grad_emb, dxyz, s_ray, s_depth, ray_dir_local, ray_frame,
-            n_frames, pose_acc);
+    static const int merge = [] { const char *e = getenv("NL_GATHER_MERGE"); return e ? atoi(e) : 2; }();
+#define NL_LAUNCH_GBWD(MG)                                                                                                          \
+    k_gather_bwd<MG><<<persistent_blocks(M, 128, 16), 128, smem, (cudaStream_t)stream>>>(                                          \
+        M, d_M_dev, xyz, vox, centres, vox2row, reinterpret_cast<const uint4 *>(emb), voxel_size,                                   \
+        reinterpret_cast<const float4 *>(dfeats), round_bf16, grad_emb, dxyz, s_ray, s_depth, ray_dir_local, ray_frame, n_frames,   \
+        pose_acc)
+    if (merge == 2) NL_LAUNCH_GBWD(2);
+    else if (merge == 1) NL_LAUNCH_GBWD(1);
+    else NL_LAUNCH_GBWD(0);
+#undef NL_LAUNCH_GBWD
     NL_CHECK_LAUNCH("nl_gather_trilinear_bwd");
     return NL_OK;
 }
