@@ -152,9 +152,18 @@ typedef struct {
     uint8_t *d_s_flag;     /* u8[cap] bit0 front_mask, bit1 sdf_mask (criterion.py:67-82); 0 if d_gt_depth NULL */
     int32_t *d_ray_nsamp;  /* i32[R] valid samples per ray (0 for missed rays); 16-byte aligned (also d_ray_offset, d_hit_rank, d_workspace) */
     int32_t *d_ray_offset; /* i32[R] offset of the ray's first sample in the compact list */
+    const void *d_packed_children; /* optional: nl_octree_pack_children() image of (d_centres, d_structure).  With it the
+                                    * traversal runs warp-cooperatively (8 lanes per ray, one child each, ballot + shared-memory
+                                    * stack); NULL = one thread per ray over the reference's two arrays (same results) */
 } nl_render_args;
 
 NL_API int64_t nl_render_workspace_bytes(int32_t n_rays);
+/* Device-side traversal image of the octree: for node n and child slot u one 16-byte record {child centre xyz, child id
+ * (int bits, -1 = none)}, 128 B per node (n_nodes * 128 bytes): the 8 lanes that expand a node read one 128-byte line instead
+ * of the node's row of `structure` followed by dependent, scattered reads of `centres`.  Rebuild after every map update.
+ * Requires what the reference's octree guarantees: a child's side is half its parent's. */
+NL_API int64_t nl_octree_packed_bytes(int32_t n_nodes);
+NL_API int nl_octree_pack_children(int32_t n_nodes, const float *d_centres, const int32_t *d_structure, void *d_packed, void *stream);
 NL_API int nl_render_samples(const nl_render_args *args, void *stream);
 
 /* ============================================================================================
@@ -209,12 +218,16 @@ NL_API int nl_mlp_tc_forward(int64_t M, const int32_t *d_M_dev, const float *d_f
                       const float *d_b1, const float *d_w2, const float *d_b2, float *d_sdf, void *stream);
 /* Tensor-core forward + loss + backward (same contract as nl_mlp_train, width 256 only).  With grads != NULL d_act is a
  * scratch buffer of nl_mlp_tc_act_floats(M) floats (internal panel-major activations for the weight-gradient GEMMs).
- * The panels must have been prepared from the same W0 / W1 / w2 (the backward panels hold diag(w2) W1). */
+ * The panels must have been prepared from the same W0 / W1 / w2 (the backward panels hold diag(w2) W1).
+ * wgrad_stream (may be NULL = stream): the weight-gradient kernels are enqueued there, ordered after the forward/backward
+ * kernel by an event, so that they overlap with later work on `stream`; the caller joins the two streams before it reads
+ * `grads` or reuses d_act. */
 NL_API int64_t nl_mlp_tc_act_floats(int64_t M);
 NL_API int nl_mlp_tc_train(int64_t M, const int32_t *d_M_dev, const float *d_feats, const void *d_panels, const float *d_W1,
                     const float *d_b0, const float *d_b1, const float *d_w2, const float *d_b2, const uint8_t *d_s_flag, const float *d_s_depth,
                     const int32_t *d_s_ray, const float *d_cos, const float *d_gt_depth, nl_render_stats *d_stats, float truncation,
-                    float *d_sdf, float *d_dfeats, const nl_mlp_grads *grads, float *d_act, const float *d_dsdf_ext, void *stream);
+                    float *d_sdf, float *d_dfeats, const nl_mlp_grads *grads, float *d_act, const float *d_dsdf_ext, void *wgrad_stream,
+                    void *stream);
 /* loss constants from the sample statistics (criterion.py:84-88, 97-100); call after nl_render_samples */
 NL_API int nl_loss_prepare(nl_render_stats *d_stats, float fs_weight, float sdf_weight, void *stream);
 NL_API int nl_loss_finalize(nl_render_stats *d_stats, float fs_weight, float sdf_weight, void *stream);

@@ -37,6 +37,7 @@ class RenderArgs(C.Structure):
         ("d_noise", vp), ("noise_stride", C.c_int32), ("rng_seed", C.c_uint32), ("d_workspace", vp),
         ("workspace_bytes", C.c_int64), ("d_stats", vp), ("d_hit_rank", vp), ("d_s_ray", vp), ("d_s_vox", vp),
         ("d_s_depth", vp), ("d_s_xyz", vp), ("d_s_flag", vp), ("d_ray_nsamp", vp), ("d_ray_offset", vp),
+        ("d_packed_children", vp),
     ]
 
 
@@ -83,7 +84,9 @@ _SIGNATURES = {
     "nl_mlp_tc_forward": (C.c_int, [C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "nl_mlp_tc_act_floats": (C.c_int64, [C.c_int64]),
     "nl_mlp_tc_train": (C.c_int, [C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_float, vp, vp, C.POINTER(MlpGrads),
-                                  vp, vp, vp]),
+                                  vp, vp, vp, vp]),
+    "nl_octree_packed_bytes": (C.c_int64, [C.c_int32]),
+    "nl_octree_pack_children": (C.c_int, [C.c_int32, vp, vp, vp, vp]),
     "nl_loss_prepare": (C.c_int, [vp, C.c_float, C.c_float, vp]),
     "nl_loss_finalize": (C.c_int, [vp, C.c_float, C.c_float, vp]),
     "nl_pose_matrices": (C.c_int, [C.c_int, vp, vp, vp]),

@@ -1343,7 +1343,7 @@ extern "C" int nl_mlp_tc_train(int64_t M, const int32_t *d_M_dev, const float *f
                                const float *b1, const float *w2, const float *b2, const uint8_t *s_flag, const float *s_depth,
                                const int32_t *s_ray, const float *cosv, const float *gt_depth, nl_render_stats *stats,
                                float truncation, float *sdf, float *dfeats, const nl_mlp_grads *grads, float *act,
-                               const float *dsdf_ext, void *stream_) {
+                               const float *dsdf_ext, void *wgrad_stream_, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (M < 0) return nl_set_error("nl_mlp_tc_train: negative M");
     if (M == 0) return NL_OK;
@@ -1387,14 +1387,23 @@ extern "C" int nl_mlp_tc_train(int64_t M, const int32_t *d_M_dev, const float *f
         p.gb2 = grads->gb2;
         if (use_ts) tc::k_mlp_tc_train<true, true><<<grid, tc::NTHREADS_TRAIN, tc::SMEM_TOTAL, stream>>>(p);
         else tc::k_mlp_tc_train<true, false><<<grid, tc::NTHREADS_TRAIN, tc::SMEM_TOTAL, stream>>>(p);
-        if (conv_warps == 8) {
-            tc::k_dw1_tc<8><<<sms, 320, tc::DW_SMEM, stream>>>(M, d_M_dev, p.act_mask2, p.act_dsdf, p.act_h1, W1, w2, grads->gW1, grads->gW2);
-            tc::k_dw0_tc<8><<<sms, 320, tc::D0_SMEM, stream>>>(M, d_M_dev, p.act_dh1, feats, grads->gW0, grads->gb0);
-        } else {
-            tc::k_dw1_tc<4><<<sms, 192, tc::DW_SMEM, stream>>>(M, d_M_dev, p.act_mask2, p.act_dsdf, p.act_h1, W1, w2, grads->gW1, grads->gW2);
-            tc::k_dw0_tc<4><<<sms, 192, tc::D0_SMEM, stream>>>(M, d_M_dev, p.act_dh1, feats, grads->gW0, grads->gb0);
+        // The weight-gradient kernels only need what the kernel above wrote; on a second stream they overlap with whatever the
+        // caller enqueues next on `stream` (the embedding scatter, which is L2-atomic bound and leaves the SMs mostly idle).
+        cudaStream_t ws = wgrad_stream_ ? (cudaStream_t)wgrad_stream_ : stream;
+        if (ws != stream) {
+            static cudaEvent_t ev = nullptr;
+            if (!ev && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return nl_set_error_code(NL_ERR_CUDA, "cudaEventCreate");
+            cudaEventRecord(ev, stream);
+            cudaStreamWaitEvent(ws, ev, 0);
         }
-        tc::k_mask_colsum<<<sms * 8, 256, 0, stream>>>(M, d_M_dev, p.act_mask2, p.act_dsdf, b1, w2, grads->gb1, grads->gW2);
+        if (conv_warps == 8) {
+            tc::k_dw1_tc<8><<<sms, 320, tc::DW_SMEM, ws>>>(M, d_M_dev, p.act_mask2, p.act_dsdf, p.act_h1, W1, w2, grads->gW1, grads->gW2);
+            tc::k_dw0_tc<8><<<sms, 320, tc::D0_SMEM, ws>>>(M, d_M_dev, p.act_dh1, feats, grads->gW0, grads->gb0);
+        } else {
+            tc::k_dw1_tc<4><<<sms, 192, tc::DW_SMEM, ws>>>(M, d_M_dev, p.act_mask2, p.act_dsdf, p.act_h1, W1, w2, grads->gW1, grads->gW2);
+            tc::k_dw0_tc<4><<<sms, 192, tc::D0_SMEM, ws>>>(M, d_M_dev, p.act_dh1, feats, grads->gW0, grads->gb0);
+        }
+        tc::k_mask_colsum<<<sms * 8, 256, 0, ws>>>(M, d_M_dev, p.act_mask2, p.act_dsdf, b1, w2, grads->gb1, grads->gW2);
     } else {
         if (use_ts) tc::k_mlp_tc_train<false, true><<<grid, tc::NTHREADS_TRAIN, tc::SMEM_TOTAL, stream>>>(p);
         else tc::k_mlp_tc_train<false, false><<<grid, tc::NTHREADS_TRAIN, tc::SMEM_TOTAL, stream>>>(p);

@@ -38,7 +38,7 @@ def mlp_forward(bufs, M_cap, M_dev, feats, sdf):
 
 
 def mlp_train(bufs, M_cap, M_dev, feats, sdf, dfeats, want_wgrad, act, s_flag=None, s_depth=None, s_ray=None, cos=None, gt_depth=None,
-              stats_ptr=None, truncation=0.0, dsdf_ext=None):
+              stats_ptr=None, truncation=0.0, dsdf_ext=None, wgrad_stream=None):
     """Forward + (loss | external d sdf) + backward.  act: dict with scratch tensors for the weight gradients
     ('h1','dh2' [cap,W] for simt; one 'buf' of nl_mlp_tc_act_floats(cap) floats for tc).  Accumulates into bufs.grads when want_wgrad."""
     lib, st = _capi.lib(), _capi.stream_ptr()
@@ -49,7 +49,8 @@ def mlp_train(bufs, M_cap, M_dev, feats, sdf, dfeats, want_wgrad, act, s_flag=No
         _capi.check(lib.nl_mlp_tc_train(M_cap, M_dev, _capi.ptr(feats), _capi.ptr(bufs.tc_panels), _capi.ptr(p[2]), _capi.ptr(p[1]), _capi.ptr(p[3]),
                                         _capi.ptr(p[4]), _capi.ptr(p[5]), _capi.ptr(s_flag), _capi.ptr(s_depth), _capi.ptr(s_ray),
                                         _capi.ptr(cos), _capi.ptr(gt_depth), stats_ptr, float(truncation), _capi.ptr(sdf),
-                                        _capi.ptr(dfeats), gp, _capi.ptr(act["buf"]) if want_wgrad else None, _capi.ptr(dsdf_ext), st),
+                                        _capi.ptr(dfeats), gp, _capi.ptr(act["buf"]) if want_wgrad else None, _capi.ptr(dsdf_ext),
+                                        C.c_void_p(wgrad_stream.cuda_stream) if (want_wgrad and wgrad_stream is not None) else None, st),
                     "nl_mlp_tc_train")
         _capi.LAUNCHES += 4 if want_wgrad else 1
     else:
@@ -69,6 +70,22 @@ def alloc_act(width, M_cap, device):
     return {k: torch.empty((int(M_cap), width), dtype=torch.float32, device=device) for k in ("h1", "dh2")}
 
 
+def pack_children(centres, structure):
+    """nl_octree_pack_children: [n, 8] records {child centre, child id} (128 B per node) for the cooperative traversal kernel.
+    Checks the octree invariant it relies on (a child's side is half its parent's, octree.cpp:51-111)."""
+    n = centres.shape[0]
+    ch = structure[:, :8].long()
+    present = ch >= 0
+    child_side = structure[ch.clamp(min=0), 8]
+    if not bool(((child_side * 2 == structure[:, 8:9]) | ~present).all()):
+        raise _capi.NerfLoamError("octree structure violates side(child) == side(parent) / 2")
+    packed = torch.empty(int(_capi.lib().nl_octree_packed_bytes(n)), dtype=torch.uint8, device=centres.device)
+    _capi.check(_capi.lib().nl_octree_pack_children(n, _capi.ptr(centres), _capi.ptr(structure), _capi.ptr(packed), _capi.stream_ptr()),
+                "nl_octree_pack_children")
+    _capi.LAUNCHES += 1
+    return packed
+
+
 class MapState:
     """Device-resident map in hot-path layout: centres f32[n,3], structure i32[n,9], vox2row i32[n,8],
     emb bf16[V,16].  Built from the reference's map_states dict (mapping.py:328-337) by composing
@@ -84,8 +101,15 @@ class MapState:
         assert self.centres.shape[1] == 3 and self.structure.shape[1] == 9 and self.vox2row.shape[1] == 8
         assert self.emb.shape[1] == 16, "embedding dim must be 16 (decoder_specs.in_dim of every shipped config)"
         self.n_nodes = self.centres.shape[0]
+        self._packed = None
 
     _cache = {}
+
+    def packed_children(self):
+        """Traversal image of the octree (nl_octree_pack_children), built once per map version."""
+        if getattr(self, "_packed", None) is None:
+            self._packed = pack_children(self.centres, self.structure)
+        return self._packed
 
     @classmethod
     def from_map_states(cls, map_states, device="cuda"):
@@ -101,9 +125,11 @@ class MapState:
             cls._cache = {"key": key, "vox2row": rows.to(torch.int32).to(device).contiguous(),
                           "centres": map_states["voxel_center_xyz"].detach().to(device=device, dtype=torch.float32).contiguous(),
                           "structure": map_states["voxel_structure"].detach().to(device=device, dtype=torch.int32).contiguous()}
+            cls._cache["packed"] = pack_children(cls._cache["centres"], cls._cache["structure"])
         c = cls._cache
         obj = cls.__new__(cls)
         obj.centres, obj.structure, obj.vox2row = c["centres"], c["structure"], c["vox2row"]
+        obj._packed = c["packed"]
         emb = map_states["voxel_vertex_emb"]
         obj.emb = emb if (emb.is_cuda and emb.dtype == torch.bfloat16 and emb.is_contiguous()) else \
             emb.detach().to(device=device, dtype=torch.bfloat16).contiguous()
@@ -187,6 +213,11 @@ class SDFEngine:
         self.pose_grad = None
         self._stats_host = torch.empty(STATS_BYTES, dtype=torch.uint8).pin_memory() if torch.cuda.is_available() else None
         self.events = None            # set to {} to record CUDA events around the main kernels (bench.py)
+        # the weight-gradient kernels of the decoder run on a second stream, concurrently with the embedding scatter
+        self.overlap_wgrad = os.environ.get("NL_OVERLAP_WGRAD", "1") != "0"
+        # warp-cooperative traversal over the packed octree image; False: one thread per ray over (centres, structure)
+        self.use_packed_octree = os.environ.get("NL_PACKED_OCTREE", "1") != "0"
+        self._side = None
 
     def _mark(self, name):
         if self.events is not None:
@@ -234,6 +265,7 @@ class SDFEngine:
         a.truncation, a.max_depth = cfg.get("truncation", 0.0), cfg.get("max_depth", 0.0)
         a.fs_weight, a.sdf_weight = cfg.get("fs_weight", 0.0), cfg.get("sdf_weight", 0.0)
         a.d_centres, a.d_structure = m.centres.data_ptr(), m.structure.data_ptr()
+        a.d_packed_children = m.packed_children().data_ptr() if self.use_packed_octree else None
         a.d_ray_o = (ray_o if ray_o is not None else self.ray_o).data_ptr()
         a.d_ray_d = (ray_d if ray_d is not None else self.ray_d).data_ptr()
         a.d_gt_depth = gt_depth.data_ptr() if gt_depth is not None else None
@@ -292,9 +324,14 @@ class SDFEngine:
             self._ensure_act(dec.width)
             for g in dec.grads:
                 g.zero_()
+        side = None
+        if update_decoder and self.overlap_wgrad and mlp_impl(dec.width) == "tc":
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+            side = self._side
         mlp_train(dec, self.max_samples, self.n_samples_dev, self.feats, self.sdf, self.dfeats, update_decoder, self.act,
                   s_flag=self.s_flag, s_depth=self.s_depth, s_ray=self.s_ray, cos=cos, gt_depth=gt_depth,
-                  stats_ptr=C.c_void_p(self.stats.data_ptr()), truncation=cfg["truncation"])
+                  stats_ptr=C.c_void_p(self.stats.data_ptr()), truncation=cfg["truncation"], wgrad_stream=side)
         self._mark("t_mlp")
         if update_emb:
             if self.grad_emb is None or self.grad_emb.shape[0] != m.emb.shape[0]:
@@ -316,6 +353,8 @@ class SDFEngine:
                 _capi.ptr(dir_local) if want_pose else None, _capi.ptr(ray_frame) if want_pose else None, int(n_frames),
                 _capi.ptr(self.pose_acc) if want_pose else None, st), "nl_gather_trilinear_bwd")
             _capi.LAUNCHES += 1
+        if side is not None:
+            torch.cuda.current_stream(self.device).wait_stream(side)   # decoder gradients complete before they are reduced / applied
         self._mark("t_gather_bwd")
         if group is not None:
             from . import dist as nldist

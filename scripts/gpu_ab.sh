@@ -12,7 +12,7 @@ for spec in "$@"; do
     python - <<PY
 import json
 try:
-    d=json.load(open("$out/bench_$name.json")); print("[$name]", round(d["value"]/1e6,1), "M/s", round(d["ms_per_step"],4), "ms", {k: round(v,4) for k,v in d["stage_ms"].items()}, "frozen", round(d["frozen_decoder"]["ms_per_step"],4), round(d["frozen_decoder"]["mlp_fwd_bwd_ms"],4), "track", round(d["tracking"].get("ms_per_scan",0),2))
+    d=json.load(open("$out/bench_$name.json")); print("[$name]", round(d["value"]/1e6,1), "M/s", round(d["ms_per_step"],4), "ms", {k: (round(v,4) if isinstance(v,float) else "") for k,v in d["stage_ms"].items()}, "frozen", round(d["frozen_decoder"]["ms_per_step"],4), round(d["frozen_decoder"]["mlp_fwd_bwd_ms"],4), "track", round(d["tracking"].get("ms_per_scan",0),2))
 except Exception as e: print("[$name] bench parse failed", e)
 PY
   )
