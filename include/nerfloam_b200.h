@@ -155,6 +155,8 @@ typedef struct {
     const void *d_packed_children; /* optional: nl_octree_pack_children() image of (d_centres, d_structure).  With it the
                                     * traversal runs warp-cooperatively (8 lanes per ray, one child each, ballot + shared-memory
                                     * stack); NULL = one thread per ray over the reference's two arrays (same results) */
+    const uint32_t *d_rng_seed;    /* optional device-side seed (overrides rng_seed; 0 is mapped to 1): lets a captured CUDA graph draw
+                                    * new sampler noise on every replay */
 } nl_render_args;
 
 NL_API int64_t nl_render_workspace_bytes(int32_t n_rays);
@@ -249,6 +251,10 @@ NL_API int nl_adam_f32(int64_t n, float *d_param, const float *d_grad, float *d_
                 double beta2, double eps, int step, void *stream);
 NL_API int nl_adam_bf16(int64_t n, uint16_t *d_param, const float *d_grad_f32, uint16_t *d_m, uint16_t *d_v, double lr,
                  double beta1, double beta2, double eps, int step, void *stream);
+/* nl_adam_f32 with the step count in device memory: *d_step is incremented, then used -- so the pair of launches can be
+ * captured in a CUDA graph and replayed (the tracking loop, render_helpers.py:452-510, is launch-bound). */
+NL_API int nl_adam_f32_devstep(int64_t n, float *d_param, const float *d_grad, float *d_m, float *d_v, double lr, double beta1,
+                        double beta2, double eps, int32_t *d_step, void *stream);
 
 #ifdef __cplusplus
 }

@@ -37,7 +37,7 @@ class RenderArgs(C.Structure):
         ("d_noise", vp), ("noise_stride", C.c_int32), ("rng_seed", C.c_uint32), ("d_workspace", vp),
         ("workspace_bytes", C.c_int64), ("d_stats", vp), ("d_hit_rank", vp), ("d_s_ray", vp), ("d_s_vox", vp),
         ("d_s_depth", vp), ("d_s_xyz", vp), ("d_s_flag", vp), ("d_ray_nsamp", vp), ("d_ray_offset", vp),
-        ("d_packed_children", vp),
+        ("d_packed_children", vp), ("d_rng_seed", vp),
     ]
 
 
@@ -93,6 +93,7 @@ _SIGNATURES = {
     "nl_rays_from_poses": (C.c_int, [C.c_int64, vp, vp, vp, vp, vp, vp]),
     "nl_pose_grad": (C.c_int, [C.c_int, vp, vp, vp, vp]),
     "nl_adam_f32": (C.c_int, [C.c_int64, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, vp]),
+    "nl_adam_f32_devstep": (C.c_int, [C.c_int64, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, C.c_double, vp, vp]),
     "nl_adam_bf16": (C.c_int, [C.c_int64, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, vp]),
 }
 

@@ -344,6 +344,7 @@ struct SampleParams {
     const float *ray_o, *ray_d, *gt_depth, *cosv, *noise;
     int noise_stride;
     uint32_t rng_seed;
+    const uint32_t *rng_seed_dev;
     int32_t *s_ray, *s_vox;
     float *s_depth, *s_xyz;
     uint8_t *s_flag;
@@ -438,11 +439,13 @@ __global__ void __launch_bounds__(128) k_sample(SampleParams p, Workspace ws, nl
         const float inv_steps = __frcp_rn(steps);
         float z_low = curr_min_depth;
         const int total_steps = (int)ceilf(steps);
+        uint32_t seed = p.rng_seed;
+        if (p.rng_seed_dev) { seed = *p.rng_seed_dev; seed = seed ? seed : 1u; }
         bool done = false;
         for (int curr_step = 0; curr_step < total_steps; ++curr_step) {
             float nz = 0.5f;
             if (p.noise) nz = p.noise[(size_t)q * p.noise_stride + curr_step];
-            else if (p.rng_seed) nz = hash_uniform(p.rng_seed, (uint32_t)r, (uint32_t)curr_step);
+            else if (seed) nz = hash_uniform(seed, (uint32_t)r, (uint32_t)curr_step);
             const float curr_cdf = __fmul_rn(__fadd_rn((float)curr_step, nz), inv_steps);
             while (curr_cdf > curr_max_cdf) {
                 emit(bidx[curr_bin], __fmul_rn(__fadd_rn(curr_max_depth, z_low), 0.5f));
@@ -583,7 +586,7 @@ extern "C" int nl_render_samples(const nl_render_args *a, void *stream_) {
     p.R = R; p.sample_capacity = a->sample_capacity; p.compat = a->reference_compat;
     p.step_size = a->step_size; p.truncation = a->truncation; p.max_depth = a->max_depth;
     p.ray_o = a->d_ray_o; p.ray_d = a->d_ray_d; p.gt_depth = a->d_gt_depth; p.cosv = a->d_cos; p.noise = a->d_noise;
-    p.noise_stride = a->noise_stride; p.rng_seed = a->rng_seed;
+    p.noise_stride = a->noise_stride; p.rng_seed = a->rng_seed; p.rng_seed_dev = a->d_noise ? nullptr : a->d_rng_seed;
     p.s_ray = a->d_s_ray; p.s_vox = a->d_s_vox; p.s_depth = a->d_s_depth; p.s_xyz = a->d_s_xyz; p.s_flag = a->d_s_flag;
     p.ray_nsamp = a->d_ray_nsamp; p.ray_offset = a->d_ray_offset;
     k_sample<false><<<blocks, 128, 0, stream>>>(p, ws, a->d_stats);

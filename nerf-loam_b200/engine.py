@@ -255,7 +255,7 @@ class SDFEngine:
         _capi.LAUNCHES += 2
 
     def render_samples(self, m, R, cfg, ray_o=None, ray_d=None, gt_depth=None, cos=None, noise=None, rng_seed=0,
-                       reference_compat=True):
+                       reference_compat=True, rng_seed_dev=None):
         """rays -> compact sample list (nl_render_samples).  cfg: dict(voxel_size, step_size, max_distance,
         truncation, max_depth, fs_weight, sdf_weight)."""
         assert R <= self.max_rays
@@ -274,6 +274,7 @@ class SDFEngine:
             assert noise.is_cuda and noise.dtype == torch.float32 and noise.is_contiguous() and noise.dim() == 2
             a.d_noise, a.noise_stride = noise.data_ptr(), noise.shape[1]
         a.rng_seed = int(rng_seed) & 0xffffffff
+        a.d_rng_seed = rng_seed_dev.data_ptr() if rng_seed_dev is not None else None   # int32 tensor on the device (CUDA-graph replays)
         a.d_workspace, a.workspace_bytes = self.workspace.data_ptr(), self.ws_bytes
         a.d_stats, a.d_hit_rank = self.stats.data_ptr(), self.hit_rank.data_ptr()
         a.d_s_ray, a.d_s_vox, a.d_s_depth = self.s_ray.data_ptr(), self.s_vox.data_ptr(), self.s_depth.data_ptr()
@@ -301,14 +302,14 @@ class SDFEngine:
 
     def forward_backward(self, m, dec, R, cfg, gt_depth, cos, dir_local=None, ray_frame=None, n_frames=1, ray_o=None,
                          ray_d=None, noise=None, rng_seed=0, reference_compat=True, update_decoder=True, update_emb=True,
-                         update_pose=True, pose6=None, group=None, refresh_weights=True):
+                         update_pose=True, pose6=None, group=None, refresh_weights=True, rng_seed_dev=None):
         """One optimisation iteration without the optimiser step.  Gradients land in
         self.grad_emb (fp32 [V,16]), dec.grads (fp32), self.pose_grad (fp32 [F,6]); the loss in stats."""
         lib = _capi.lib()
         st = _capi.stream_ptr()
         self._vs = cfg["voxel_size"]
         self._mark("t0")
-        self.render_samples(m, R, cfg, ray_o, ray_d, gt_depth, cos, noise, rng_seed, reference_compat)
+        self.render_samples(m, R, cfg, ray_o, ray_d, gt_depth, cos, noise, rng_seed, reference_compat, rng_seed_dev)
         if group is not None:   # the loss normalisation is global (criterion.py:84-100): one tiny exchange before backward
             from . import dist as nldist
             nldist.allreduce_sample_stats(self.stats, group)

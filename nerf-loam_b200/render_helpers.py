@@ -279,14 +279,136 @@ def bundle_adjust_frames(keyframe_graph, embeddings, map_states, sdf_network, lo
                 f.pose.data.copy_(host[i].to(f.pose.data.device))
 
 
+class _TrackGraph:
+    """One captured tracking iteration (ray selection -> rays -> traversal -> sampling -> gather -> decoder fwd/bwd -> pose gradient
+    -> Adam) with every per-scan input in static device buffers, so that the capture (tens of ms) is paid once per map / decoder
+    version and every scan is 25 graph replays plus one statistics read-back."""
+
+    _cache = {}
+
+    def __init__(self, key, m, sdf_network, cfg, N_rays, lr, deterministic, cap):
+        dev = m.centres.device
+        # a private engine: the shared ones may re-allocate buffers (pose accumulators, scratch) between scans, which would leave
+        # the captured graph with dangling pointers
+        eng = SDFEngine(N_rays, N_rays * 64, dev)
+        bufs = DecoderBuffers(sdf_network, dev)
+        self.key, self.eng, self.cap, self.N = key, eng, cap, N_rays
+        self.m, self.bufs, self.packed = m, bufs, m.packed_children()   # keep the captured tensors alive
+        self.dirs = torch.tensor([0.0, 0.0, -1.0], device=dev).repeat(cap, 1)   # valid unit rays for the throw-away warm-up iteration
+        self.gt = torch.ones(cap, device=dev)
+        self.cos = torch.ones(cap, device=dev)
+        self.n_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.arange = torch.arange(cap, device=dev)
+        self.pose6 = torch.zeros((1, 6), device=dev)
+        self.seed_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.min_hits = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.adam_m, self.adam_v = torch.zeros(6, device=dev), torch.zeros(6, device=dev)
+        stats_i32 = eng.stats.view(torch.int32)
+        lib = _capi.lib()
+
+        def body():
+            keys = torch.where(self.arange < self.n_dev, torch.rand(cap, device=dev), torch.full((), -1.0, device=dev))
+            idx = keys.topk(N_rays).indices.sort().values        # uniform without replacement among the scan's n points
+            dirs, gt, cos = self.dirs[idx].contiguous(), self.gt[idx].contiguous(), self.cos[idx].contiguous()
+            eng.rays_from_poses(self.pose6, dirs, None)
+            eng.forward_backward(m, bufs, N_rays, cfg, gt, cos, dir_local=dirs, ray_frame=None, n_frames=1, update_decoder=False,
+                                 update_emb=False, update_pose=True, pose6=self.pose6, refresh_weights=False,
+                                 rng_seed_dev=None if deterministic else self.seed_dev)
+            torch.minimum(self.min_hits, stats_i32[0:1], out=self.min_hits)      # n_hit_rays is the first field of nl_render_stats
+            _capi.check(lib.nl_adam_f32_devstep(6, _capi.ptr(self.pose6), _capi.ptr(eng.pose_grad), _capi.ptr(self.adam_m),
+                                                _capi.ptr(self.adam_v), float(lr), 0.9, 0.999, 1e-8, _capi.ptr(self.step_dev),
+                                                _capi.stream_ptr()), "nl_adam_f32_devstep")
+            self.seed_dev.add_(0x3779B1)
+
+        # one throw-away eager iteration on a side stream (allocations, one-time kernel attributes), then the capture
+        bufs.refresh_transposes()
+        self.n_dev.fill_(cap)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        l0 = _capi.LAUNCHES
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            body()
+        self.launches_per_iter = _capi.LAUNCHES - l0 + 2
+
+    @classmethod
+    def get(cls, m, sdf_network, cfg, N_rays, lr, deterministic, n_points):
+        cap = max(1 << 17, 1 << (int(n_points) - 1).bit_length())
+        key = (N_rays, float(lr), bool(deterministic), cap, m.centres.data_ptr(), m.structure.data_ptr(), m.vox2row.data_ptr(),
+               m.packed_children().data_ptr(), m.emb.data_ptr(), m.n_nodes, int(m.emb.shape[0]),
+               tuple(p.data_ptr() for p in _decoder_params(sdf_network)), tuple(sorted(cfg.items())))
+        g = cls._cache.get("g")
+        if g is None or g.key != key:
+            cls._cache = {}                                     # one live graph: a new map / decoder version replaces it
+            g = cls(key, m, sdf_network, cfg, N_rays, lr, deterministic, cap)
+            cls._cache = {"g": g}
+        return g
+
+    def run(self, frame, pose6_init, num_iterations, seed):
+        rd = frame.rays_d.reshape(-1, 3).float()
+        n = rd.shape[0]
+        dev = self.dirs.device
+        self.bufs.refresh_transposes()        # the decoder may have been updated in place since the capture (same pointers, new values)
+        self.dirs[:n].copy_(rd, non_blocking=True)
+        cosv = frame.pointsCos.float().view(-1).to(dev, non_blocking=True)
+        self.cos[:n].copy_(cosv)
+        self.gt[:n].copy_(torch.norm(frame.points.float().to(dev, non_blocking=True), 2, -1) * cosv)       # criterion.py:30-32
+        self.n_dev.fill_(n)
+        self.pose6.copy_(pose6_init)
+        self.seed_dev.fill_(seed if seed < 2 ** 31 else seed - 2 ** 32)
+        self.step_dev.zero_(); self.adam_m.zero_(); self.adam_v.zero_()
+        self.min_hits.fill_(2 ** 30)
+        for _ in range(num_iterations):
+            self.graph.replay()
+        _capi.LAUNCHES += self.launches_per_iter * num_iterations
+        st = self.eng.read_stats()
+        return st, int(self.min_hits.item())
+
+
+def _track_frame_graph(frame_pose, curr_frame, map_states, sdf_network, loss_criteria, voxel_size, N_rays, step_size, num_iterations,
+                       learning_rate, max_distance, deterministic):
+    dev = torch.device("cuda")
+    m = map_states if isinstance(map_states, MapState) else MapState.from_map_states(map_states, dev)
+    cfg = _cfg(step_size, voxel_size, max_distance, loss_criteria)
+    init_pose = deepcopy(frame_pose).cuda()
+    init_pose.requires_grad_(True)
+    lr = learning_rate * 2 if curr_frame.index < 2 else learning_rate / 3   # render_helpers.py:448-450
+    n_points = curr_frame.points.shape[0]
+    if n_points < N_rays:
+        raise ValueError("cuda_graph=True needs at least N_rays points in the scan")
+    g = _TrackGraph.get(m, sdf_network, cfg, N_rays, lr, deterministic, n_points)
+    eng = g.eng
+    seed = 0 if deterministic else _seed_from_torch()
+    st, min_hits = g.run(curr_frame, init_pose.data.detach().reshape(1, 6), num_iterations, seed)
+    with torch.no_grad():
+        init_pose.data.copy_(g.pose6.reshape(init_pose.data.shape))
+    if min_hits <= 0 or (st.error & 1) or st.n_samples == 0:
+        print("Encouter a bug while Tracking, currently not be fixed, Restarting!!")  # render_helpers.py:488-491
+        return init_pose, None
+    return init_pose, (eng.hit_rank[:N_rays] >= 0).clone()
+
+
 def track_frame(frame_pose, curr_frame, map_states, sdf_network, loss_criteria, voxel_size, N_rays=512, step_size=0.05,
                 num_iterations=10, truncation=0.1, learning_rate=1e-3, max_voxel_hit=10, max_distance=10, profiler=None,
-                depth_variance=False, deterministic=False, noise_per_iter=None, loss_log=None, ray_selection="host"):
+                depth_variance=False, deterministic=False, noise_per_iter=None, loss_log=None, ray_selection="host",
+                cuda_graph=False):
     """render_helpers.py:428-514: optimise the 6-vector pose of one scan against a frozen map.
     Returns (OptimizablePose on the GPU, hit_mask bool[N_rays]) or (pose, None) if nothing was hit.
-    ray_selection: see _FrameBatch.select."""
+    ray_selection: see _FrameBatch.select.  cuda_graph=True (needs ray_selection="device"): the iteration -- ray selection,
+    rays, traversal, sampling, gather, decoder forward/backward, pose gradient, Adam -- is captured once and replayed, with
+    the sampler seed and the Adam step count in device memory; the host looks at the statistics once at the end instead of
+    every iteration (an iteration without hits makes the call return (pose, None) like the reference, just later)."""
     if ray_selection not in ("host", "device"):
         raise ValueError("ray_selection must be 'host' or 'device'")
+    if cuda_graph:
+        if ray_selection != "device" or noise_per_iter is not None or loss_log is not None:
+            raise ValueError("cuda_graph=True needs ray_selection='device' and no per-iteration host inputs/outputs")
+        return _track_frame_graph(frame_pose, curr_frame, map_states, sdf_network, loss_criteria, voxel_size, N_rays, step_size,
+                                  num_iterations, learning_rate, max_distance, deterministic)
     dev = torch.device("cuda")
     m = map_states if isinstance(map_states, MapState) else MapState.from_map_states(map_states, dev)
     cfg = _cfg(step_size, voxel_size, max_distance, loss_criteria)

@@ -1,6 +1,6 @@
 #!/bin/bash
 tag=${1:-ll}; out=gpurun_out/$tag; mkdir -p $out
-export NL_BENCH_SKIP_CPU=1
+export NL_BENCH_SKIP_CPU=1 NL_BENCH_SKIP_TRACKING=1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $out/launches.csv python bench.py --steps 2 --warmup 3 > $out/bench_under_ncu.json 2> $out/launches.err
 python - <<PY
 import csv

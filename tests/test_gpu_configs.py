@@ -229,3 +229,39 @@ def test_cooperative_traversal_equals_thread_per_ray(nl):
     assert a[:4] == b[:4] and a[3] > 700000
     for x, y in zip(a[4:], b[4:]):
         assert torch.equal(x, y)
+
+
+def test_track_frame_device_selection_and_cuda_graph(nl):
+    """Tracking with rays drawn on the GPU, eagerly and as a captured + replayed CUDA graph.  With N_rays == number of points
+    (every ray selected) and deterministic sampling the two run the same arithmetic, so the optimised poses must agree up to
+    float atomics / the device-side evaluation of Adam's bias correction.  Three iterations: Adam's first steps are
+    lr * g / |g| per component, so over many iterations a component whose gradient passes through zero amplifies atomics noise
+    into +-lr differences -- that is a property of Adam, not of the graph."""
+    syn = nl.synthetic
+    pts, cos, pose = syn.make_scan(n_beams=16, n_az=120, seed=9)
+    N = pts.shape[0]            # every ray selected in both modes
+    mu = nl.mapping.MapUpdater(0.3, init_std=0.02, seed=4)
+    ms = mu.insert_voxels(torch.from_numpy(syn.voxelize(pts, pose, 0.3)))
+    dev = torch.device("cuda")
+    torch.manual_seed(3)
+    dec = nl.lidar.Decoder(depth=2, width=256, in_dim=16, skips=[], embedder="none", multires=0).to(dev)
+    crit = nl.criterion.Criterion(Args())
+    start6 = nl.se3pose.OptimizablePose.from_matrix(torch.from_numpy(pose)).data.detach().clone()
+    start6[:3] += torch.tensor([0.05, -0.03, 0.02])
+    outs = []
+    for graph in (False, True):
+        fr = nl.frame.LidarFrame(5, torch.from_numpy(pts), torch.from_numpy(cos), nl.se3pose.OptimizablePose(start6.clone()), new_keyframe=True)
+        out, hit = nl.render_helpers.track_frame(fr.pose, fr, ms, dec, crit, 0.3, N_rays=N, step_size=0.06, num_iterations=3, truncation=0.3,
+                                                 learning_rate=0.03, max_voxel_hit=20, max_distance=40.0, ray_selection="device", cuda_graph=graph,
+                                                 deterministic=True)
+        assert hit is not None and hit.shape == (N,) and int(hit.sum()) > 0.5 * N
+        assert torch.equal(fr.pose.data.detach(), start6)          # the input pose object is not modified
+        outs.append(out.data.detach().cpu().clone())
+    assert float((outs[0] - start6).abs().max()) > 1e-3            # the Adam steps moved the pose
+    torch.testing.assert_close(outs[1], outs[0], rtol=0, atol=2e-4)
+    # a second scan through the cached graph (same map and decoder): identical result
+    fr = nl.frame.LidarFrame(6, torch.from_numpy(pts), torch.from_numpy(cos), nl.se3pose.OptimizablePose(start6.clone()), new_keyframe=True)
+    out2, _ = nl.render_helpers.track_frame(fr.pose, fr, ms, dec, crit, 0.3, N_rays=N, step_size=0.06, num_iterations=3, truncation=0.3,
+                                            learning_rate=0.03, max_voxel_hit=20, max_distance=40.0, ray_selection="device", cuda_graph=True,
+                                            deterministic=True)
+    torch.testing.assert_close(out2.data.detach().cpu(), outs[1], rtol=0, atol=2e-5)
