@@ -106,6 +106,7 @@ def run_ours(args):
     group = None
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL prints its banner to stdout)
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
     scans, mu, ms, dec = build_problem(nl, world, dev)

@@ -31,10 +31,23 @@ def allreduce_loss_sums(stats_u8, group=None):
 
 
 def allreduce_grads(tensors, group=None):
-    """Gradient reduction: embedding-gradient table [V,16] fp32, decoder grads, pose accumulators [F,12]."""
-    for t in tensors:
-        if t is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    """Gradient reduction: embedding-gradient table [V,16] fp32, decoder grads, pose accumulators [F,12] -- all fp32, one
+    coalesced all-reduce (a single grouped NCCL launch instead of eight latency-bound ones)."""
+    ts = [t for t in tensors if t is not None]
+    if not ts:
+        return
+    if len(ts) > 1 and all(t.dtype == ts[0].dtype for t in ts):
+        try:
+            from torch.distributed.distributed_c10d import _coalescing_manager
+            with _coalescing_manager(group=group, async_ops=False):
+                for t in ts:
+                    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            return
+        except (ImportError, RuntimeError, ValueError, NotImplementedError):
+            from torch.distributed import distributed_c10d as _c10d
+            _c10d._world.pg_coalesce_state.pop(group or _c10d._get_default_group(), None)   # leave no half-open coalescing state
+    for t in ts:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
 
 
 def shard_bounds(n, rank, world):

@@ -84,8 +84,12 @@ def _worker(rank, world, port, q):
     nldist.allreduce_loss_sums(buf)
     g = torch.full((7, 16), float(rank + 1))
     nldist.allreduce_grads([g, None])
+    # the per-iteration set: embedding table, six decoder tensors, pose accumulators -- one coalesced reduction
+    many = [torch.full(shape, float(rank + 1) * (i + 1)) for i, shape in enumerate([(50, 16), (256, 16), (256,), (256, 256), (256,), (1, 256), (1,), (3, 12)])]
+    nldist.allreduce_grads([many[0], None] + many[1:])
+    ok_many = all(bool((t == 3.0 * (i + 1)).all()) for i, t in enumerate(many))
     out = nl._capi.RenderStats.from_buffer_copy(buf.numpy().tobytes())
-    q.put((rank, _prepare(out), out.fs_sum, out.sdf_sum, float(g[0, 0]), (lo, hi)))
+    q.put((rank, _prepare(out), out.fs_sum, out.sdf_sum, float(g[0, 0]) if ok_many else -1.0, (lo, hi)))
     dist.destroy_process_group()
 
 
