@@ -106,7 +106,6 @@ def run_ours(args):
     group = None
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL prints its banner to stdout)
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
     scans, mu, ms, dec = build_problem(nl, world, dev)
@@ -397,6 +396,19 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     a = ap.parse_args()
+    # stdout carries exactly one JSON line: while the benchmark runs, file descriptor 1 points at stderr, so that library
+    # banners written with printf (NCCL prints its version there) cannot get in front of it
+    sys.stdout.flush()
+    _saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    _real_print = print
+
+    def print(*args, **kw):   # noqa: A001  (the two result prints below go to the real stdout)
+        sys.stdout.flush()
+        os.dup2(_saved_stdout, 1)
+        _real_print(*args, **kw)
+        sys.stdout.flush()
+        os.dup2(2, 1)
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -14,6 +14,8 @@
 //   k_scan<SAMPLES> : 1 block       exclusive scan of samples per ray -> offsets, M
 //   k_sample<true>  : 1 thread/hit ray  sampler again, writes the compact sample list
 // The reference keeps every intermediate as a padded dense tensor and syncs the host 6 times to size them.
+#include <cstdlib>
+
 #include "traverse.cuh"
 
 namespace {
@@ -83,33 +85,39 @@ __global__ void __launch_bounds__(64) k_traverse_sort(int R, float voxel_size, f
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_traverse_coop: the same traversal, 8 lanes per ray (an "octet"; 4 rays per warp, 32 per block).
+// k_traverse_coop<LANES>: the same traversal, LANES (4 or 8) lanes per ray, 32/LANES rays per warp.
 //   The thread-per-ray kernel above is latency-bound: 83 k rays give 17 warps per SM, each walking a chain of dependent
-//   loads (ncu: 0.65 IPC/SM, stalls = long scoreboard).  Here every node expansion is one step of an octet: lane u loads
-//   the packed record of child slot u (the octet reads one 128-byte line), slab-tests it, a warp ballot yields the octet's
-//   8-bit hit mask, and the hit children are pushed onto the ray's stack in SHARED memory at positions given by the
-//   popcount of the lower mask bits -- slot order 0..7, i.e. they pop 7..0 like the reference.  8x more warps hide the
-//   latency; the stack and the hit lists never touch local memory.
-//   Emission order (decides ties of the stable sort and WHICH 20 hits survive the cap) is the reference's: a node's side is
-//   carried on the stack as log2(side) (children have half the side); when a node of side 2 is expanded, its hit children
-//   are leaves and are recorded right away in DESCENDING slot order -- exactly the order in which the reference pops them
-//   (it pushes slots 0..7, pops 7..0, and a leaf pushes nothing, so those pops are consecutive) -- and the 20-hit cut-off
-//   drops the same tail.  Then a rank-by-counting stable sort by min_depth inside the octet, distance clipping, and a
-//   block-wide transposed write of the [20][R] planes (32 consecutive rays per 128-byte segment).
+//   loads (ncu: 0.65 IPC/SM, stalls = long scoreboard).  Here every node expansion is one step of a lane group: lane u loads
+//   record u of the node's packed child list (the group reads one 64/128-byte piece of a 128-byte line), slab-tests it, a
+//   warp ballot yields the group's hit mask, and the hit children are pushed onto the ray's stack in SHARED memory at
+//   positions given by the popcount of the lower mask bits.  Many more warps hide the latency; the stack and the hit lists
+//   never touch local memory.
+//   The packed list holds the node's EXISTING children, compacted (terminated by id -1): in ascending slot order for inner
+//   nodes -- so pushes are in slot order 0..7 and pop 7..0 like the reference -- and in DESCENDING slot order for nodes of
+//   side 2, whose children are leaves: those are recorded right away, in exactly the order in which the reference pops them
+//   (it pushes slots 0..7, pops 7..0, and a leaf pushes nothing, so those pops are consecutive), and the 20-hit cut-off drops
+//   the same tail.  With 4 lanes a node with more than 4 children takes a second pass (octree nodes here have 2.8 children on
+//   average), which halves the predicated-off slab tests of the 8-lane variant.  A node's side is carried on the stack as
+//   log2(side) (children have half the side).  Then a rank-by-counting stable sort by min_depth inside the group, distance
+//   clipping, and a block-wide transposed write of the [20][R] planes.
 // ------------------------------------------------------------------------------------------------
-constexpr int CO_RAYS = 32;                 // rays per block (256 threads)
 constexpr int CO_HPAD = NL_MAX_HITS + 1;    // row padding: conflict-free column reads in the transposed write
 
+template <int LANES>
 __global__ void __launch_bounds__(256) k_traverse_coop(int R, float voxel_size, float max_distance, const float *__restrict__ centres,
                                                         const int32_t *__restrict__ structure, const float4 *__restrict__ packed,
                                                         const float *__restrict__ ray_o, const float *__restrict__ ray_d, Workspace ws,
                                                         int32_t *__restrict__ ray_nsamp, nl_render_stats *stats) {
-    __shared__ int s_stk[CO_RAYS][NL_STACK_CAP];
-    __shared__ int s_idx[2][CO_RAYS][CO_HPAD];
-    __shared__ float s_mn[2][CO_RAYS][CO_HPAD];
-    __shared__ float s_mx[2][CO_RAYS][CO_HPAD];
+    constexpr int CO_RAYS = 256 / LANES;        // rays per block
+    constexpr int STK = NL_STACK_CAP;           // same bound as the thread-per-ray kernel (1 + 7 x 18 levels)
+    constexpr int NE = (NL_MAX_HITS + LANES - 1) / LANES;   // hit-list entries per lane in the sort
+    __shared__ int s_stk[CO_RAYS][STK];
+    __shared__ int s_idx[CO_RAYS][CO_HPAD];
+    __shared__ float s_mn[CO_RAYS][CO_HPAD];
+    __shared__ float s_mx[CO_RAYS][CO_HPAD];
     __shared__ int s_nv[CO_RAYS];
-    const int tid = threadIdx.x, lane = tid & 31, o = tid >> 3, u = tid & 7, ow = (lane >> 3) * 8;
+    const int tid = threadIdx.x, lane = tid & 31, o = tid / LANES, u = tid % LANES, gb = lane & ~(LANES - 1);
+    const unsigned gmask = (LANES == 8 ? 0xffu : 0xfu);
     const int r = blockIdx.x * CO_RAYS + o;
     const float half_voxel = voxel_size * 0.5f;
     NlRay ray = nl_make_ray(0.f, 0.f, 0.f, 1.f, 1.f, 1.f);
@@ -121,7 +129,7 @@ __global__ void __launch_bounds__(256) k_traverse_coop(int R, float voxel_size, 
         float lo, hi;
         if (nl_slab(ray, centres[0], centres[1], centres[2], __fmul_rn(half_voxel, (float)root_side), lo, hi)) {
             if (root_side == 1) {      // degenerate one-voxel tree: the root is the only leaf
-                if (u == 0) { s_idx[0][o][0] = 0; s_mn[0][o][0] = lo; s_mx[0][o][0] = hi; }
+                if (u == 0) { s_idx[o][0] = 0; s_mn[o][0] = lo; s_mx[o][0] = hi; }
                 cnt = 1;
             } else {
                 if (u == 0) s_stk[o][0] = (31 - __clz(root_side)) << 26;
@@ -132,68 +140,89 @@ __global__ void __launch_bounds__(256) k_traverse_coop(int R, float voxel_size, 
     __syncwarp();
     bool alive = ptr >= 0;
     while (__any_sync(0xffffffffu, alive)) {
-        bool hit = false;
-        float lo = 0.f, hi = 0.f;
-        int id = -1, lg = 0;
+        int lg = 0;
+        const float4 *rec = packed;
         if (alive) {
             const int e = s_stk[o][ptr];
             lg = e >> 26;
-            const float4 c = packed[(size_t)(e & 0x3ffffff) * 8 + u];
-            id = __float_as_int(c.w);
-            if (id > -1) hit = nl_slab(ray, c.x, c.y, c.z, __fmul_rn(__fmul_rn(half_voxel, (float)(1 << lg)), 0.5f), lo, hi);
+            rec = packed + (size_t)(e & 0x3ffffff) * 8;
         }
-        const unsigned m8 = (__ballot_sync(0xffffffffu, hit) >> ow) & 0xffu;
-        __syncwarp();                                           // every lane of the octet has read the stack top
-        if (alive) {
-            --ptr;
-            const int nh = __popc(m8);
-            if (lg == 1) {
-                if (hit) {
-                    const int p = cnt + __popc(m8 >> (u + 1));  // descending slot order
-                    if (p < NL_MAX_HITS) { s_idx[0][o][p] = id; s_mn[0][o][p] = lo; s_mx[0][o][p] = hi; }
-                }
-                cnt = min(cnt + nh, NL_MAX_HITS);
-            } else if (ptr + nh >= NL_STACK_CAP) {
-                overflow = true;
-                ptr = -1;
-            } else {
-                if (hit) s_stk[o][ptr + 1 + __popc(m8 & ((1u << u) - 1u))] = id | ((lg - 1) << 26);   // ascending slot order
-                ptr += nh;
+        const float half = __fmul_rn(__fmul_rn(half_voxel, (float)(1 << lg)), 0.5f);
+        __syncwarp();                                           // every lane of the group has read the stack top
+        if (alive) --ptr;
+        bool more = alive;                                      // this group still has records of the node to look at
+#pragma unroll
+        for (int pass = 0; pass < 8 / LANES; ++pass) {
+            bool hit = false;
+            float lo = 0.f, hi = 0.f;
+            int id = -1;
+            if (more) {
+                const float4 c = rec[pass * LANES + u];
+                id = __float_as_int(c.w);
+                if (id > -1) hit = nl_slab(ray, c.x, c.y, c.z, half, lo, hi);
             }
-            alive = ptr >= 0 && cnt < NL_MAX_HITS;
+            const unsigned mg = (__ballot_sync(0xffffffffu, hit) >> gb) & gmask;
+            const int last_id = __shfl_sync(0xffffffffu, id, gb + LANES - 1);
+            if (more) {
+                const int nh = __popc(mg), below = __popc(mg & ((1u << u) - 1u));
+                if (lg == 1) {
+                    if (hit && cnt + below < NL_MAX_HITS) { s_idx[o][cnt + below] = id; s_mn[o][cnt + below] = lo; s_mx[o][cnt + below] = hi; }
+                    cnt = min(cnt + nh, NL_MAX_HITS);
+                } else if (ptr + nh >= STK) {
+                    overflow = true;
+                    ptr = -1;
+                    more = false;
+                } else {
+                    if (hit) s_stk[o][ptr + 1 + below] = id | ((lg - 1) << 26);
+                    ptr += nh;
+                }
+                more = more && last_id > -1 && cnt < NL_MAX_HITS;   // the list may continue in the next pass
+            }
+            if (pass + 1 < 8 / LANES && !__any_sync(0xffffffffu, more)) break;
         }
+        if (alive) alive = !overflow && ptr >= 0 && cnt < NL_MAX_HITS;
         __syncwarp();                                           // pushes visible before the next pop
     }
     if (overflow && u == 0) atomicOr(&stats->error, 4);
     // ---- stable sort by min_depth (rank by counting; ties keep emission order), clipping (voxel_helpers.py:546-556) ----
     const float two_md = 2.0f * max_distance;
+    int e_idx[NE], e_pos[NE];
+    float e_mn[NE], e_mx[NE];
 #pragma unroll
-    for (int i = u; i < NL_MAX_HITS; i += 8) {
+    for (int t = 0; t < NE; ++t) {
+        const int i = u + t * LANES;
+        e_pos[t] = -1;
         if (i < cnt) {
-            const float key = s_mn[0][o][i];
+            const float key = s_mn[o][i];
             int pos = 0;
             for (int j = 0; j < cnt; ++j) {
-                const float kj = s_mn[0][o][j];
+                const float kj = s_mn[o][j];
                 pos += (kj < key || (kj == key && j < i)) ? 1 : 0;
             }
-            s_idx[1][o][pos] = s_idx[0][o][i]; s_mn[1][o][pos] = key; s_mx[1][o][pos] = s_mx[0][o][i];
+            e_pos[t] = pos; e_idx[t] = s_idx[o][i]; e_mn[t] = key; e_mx[t] = s_mx[o][i];
         }
     }
+    __syncwarp();                                               // every entry is in registers: permute in place
+#pragma unroll
+    for (int t = 0; t < NE; ++t)
+        if (e_pos[t] >= 0) { s_idx[o][e_pos[t]] = e_idx[t]; s_mn[o][e_pos[t]] = e_mn[t]; s_mx[o][e_pos[t]] = e_mx[t]; }
     __syncwarp();
     int nv = 0;
 #pragma unroll
-    for (int c = u; c < NL_MAX_HITS; c += 8) {
-        int32_t i = -1;
-        float a = max_distance, b = max_distance;
-        if (c < cnt) {
-            const float mn = s_mn[1][o][c], mx = s_mx[1][o][c];
-            if (!(mx > two_md) && !(mn > max_distance)) { i = s_idx[1][o][c]; a = mn; b = mx; ++nv; }
+    for (int t = 0; t < NE; ++t) {
+        const int c = u + t * LANES;
+        if (c < NL_MAX_HITS) {
+            int32_t i = -1;
+            float a = max_distance, b = max_distance;
+            if (c < cnt) {
+                const float mn = s_mn[o][c], mx = s_mx[o][c];
+                if (!(mx > two_md) && !(mn > max_distance)) { i = s_idx[o][c]; a = mn; b = mx; ++nv; }
+            }
+            s_idx[o][c] = i; s_mn[o][c] = a; s_mx[o][c] = b;
         }
-        s_idx[0][o][c] = i; s_mn[0][o][c] = a; s_mx[0][o][c] = b;
     }
-    nv += __shfl_xor_sync(0xffffffffu, nv, 1);
-    nv += __shfl_xor_sync(0xffffffffu, nv, 2);
-    nv += __shfl_xor_sync(0xffffffffu, nv, 4);
+#pragma unroll
+    for (int off = 1; off < LANES; off <<= 1) nv += __shfl_xor_sync(0xffffffffu, nv, off);
     if (u == 0) s_nv[o] = nv;
     const int wm = warp_max(r < R ? nv : 0);
     if (lane == 0 && wm > 0) atomicMax(&stats->max_hits, wm);
@@ -201,12 +230,12 @@ __global__ void __launch_bounds__(256) k_traverse_coop(int R, float voxel_size, 
     // ---- transposed, coalesced write of the hit planes ----
     const int r0 = blockIdx.x * CO_RAYS;
     for (int e = tid; e < NL_MAX_HITS * CO_RAYS; e += 256) {
-        const int c = e >> 5, ol = e & 31;
+        const int c = e / CO_RAYS, ol = e % CO_RAYS;
         if (r0 + ol < R) {
             const size_t off = (size_t)c * R + r0 + ol;
-            ws.h_idx[off] = s_idx[0][ol][c];
-            ws.h_min[off] = s_mn[0][ol][c];
-            ws.h_max[off] = s_mx[0][ol][c];
+            ws.h_idx[off] = s_idx[ol][c];
+            ws.h_min[off] = s_mn[ol][c];
+            ws.h_max[off] = s_mx[ol][c];
         }
     }
     if (tid < CO_RAYS && r0 + tid < R) {
@@ -217,12 +246,20 @@ __global__ void __launch_bounds__(256) k_traverse_coop(int R, float voxel_size, 
 
 __global__ void k_pack_children(int n_nodes, const float *__restrict__ centres, const int32_t *__restrict__ structure,
                                 float4 *__restrict__ packed) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;   // (node, slot)
-    if (t >= n_nodes * 8) return;
-    const int c = structure[(size_t)(t >> 3) * 9 + (t & 7)];
-    float4 o = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-    if (c > -1) o = make_float4(centres[(size_t)c * 3], centres[(size_t)c * 3 + 1], centres[(size_t)c * 3 + 2], __int_as_float(c));
-    packed[t] = o;
+    // one thread per node: the existing children compacted to the front of the node's 8 records (terminated by id -1), in
+    // ascending slot order for inner nodes (push order) and DESCENDING slot order for nodes of side 2, whose children are
+    // leaves and are recorded in the order the reference pops them
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_nodes) return;
+    const int32_t *st = structure + (size_t)n * 9;
+    const bool leaf_parent = st[8] == 2;
+    float4 *rec = packed + (size_t)n * 8;
+    int j = 0;
+    for (int i = 0; i < 8; ++i) {
+        const int c = st[leaf_parent ? 7 - i : i];
+        if (c > -1) rec[j++] = make_float4(centres[(size_t)c * 3], centres[(size_t)c * 3 + 1], centres[(size_t)c * 3 + 2], __int_as_float(c));
+    }
+    for (; j < 8; ++j) rec[j] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -547,7 +584,7 @@ extern "C" int nl_octree_pack_children(int32_t n_nodes, const float *d_centres, 
     if (n_nodes >= (1 << 26)) return nl_set_error("nl_octree_pack_children: at most 2^26 nodes (the traversal stack packs id and level)");
     if (!d_centres || !d_structure || !d_packed) return nl_set_error("nl_octree_pack_children: null pointer");
     if (((uintptr_t)d_packed & 15u) != 0) return nl_set_error("nl_octree_pack_children: d_packed must be 16-byte aligned");
-    k_pack_children<<<nl_div_up(n_nodes * 8, 256), 256, 0, (cudaStream_t)stream>>>(n_nodes, d_centres, d_structure, (float4 *)d_packed);
+    k_pack_children<<<nl_div_up(n_nodes, 128), 128, 0, (cudaStream_t)stream>>>(n_nodes, d_centres, d_structure, (float4 *)d_packed);
     NL_CHECK_LAUNCH("nl_octree_pack_children");
     return NL_OK;
 }
@@ -574,10 +611,15 @@ extern "C" int nl_render_samples(const nl_render_args *a, void *stream_) {
     Workspace ws = carve(a->d_workspace, R);
     cudaMemsetAsync(a->d_stats, 0, sizeof(nl_render_stats), stream);
     const int blocks = nl_div_up(R, 128);
-    if (a->d_packed_children)
-        k_traverse_coop<<<nl_div_up(R, CO_RAYS), 256, 0, stream>>>(R, a->voxel_size, a->max_distance, a->d_centres, a->d_structure,
-                                                                    (const float4 *)a->d_packed_children, a->d_ray_o, a->d_ray_d, ws,
-                                                                    a->d_ray_nsamp, a->d_stats);
+    static const int co_lanes = [] { const char *e = getenv("NL_TRAVERSE_LANES"); return (e && atoi(e) == 8) ? 8 : 4; }();
+    if (a->d_packed_children && co_lanes == 8)
+        k_traverse_coop<8><<<nl_div_up(R, 32), 256, 0, stream>>>(R, a->voxel_size, a->max_distance, a->d_centres, a->d_structure,
+                                                                  (const float4 *)a->d_packed_children, a->d_ray_o, a->d_ray_d, ws,
+                                                                  a->d_ray_nsamp, a->d_stats);
+    else if (a->d_packed_children)
+        k_traverse_coop<4><<<nl_div_up(R, 64), 256, 0, stream>>>(R, a->voxel_size, a->max_distance, a->d_centres, a->d_structure,
+                                                                  (const float4 *)a->d_packed_children, a->d_ray_o, a->d_ray_d, ws,
+                                                                  a->d_ray_nsamp, a->d_stats);
     else
         k_traverse_sort<<<nl_div_up(R, 64), 64, 0, stream>>>(R, a->voxel_size, a->max_distance, a->d_centres, a->d_structure, a->d_ray_o,
                                                               a->d_ray_d, ws, a->d_ray_nsamp, a->d_stats);
