@@ -891,7 +891,7 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
 //   tcgen05 takes for MN-major tf32).  Per K-block the producer bulk-copies the 16 rows of the h1 panels (16 KB, the
 //   K-major image k_mlp_tc_train stored), 512 B of mask bits and 64 B of dsdf; 4 converter warps expand the bits into
 //   the 0/1 A operand (exact in tf32: one term fewer than 3xTF32) and write hi/lo of d*h1 as the B operand.
-//   4-deep raw ring (17 KB) + 3-deep converted ring (48 KB).  Every CTA finally adds its partial sums with atomics.
+//   3-deep raw ring (17 KB) + 2-deep converted ring (48 KB).  Every CTA finally adds its partial sums with atomics.
 // ================================================================================================
 constexpr int DW_KROWS = 16;
 constexpr int DW_PANEL = DW_KROWS * 128;        // 2 KB: 16 sample rows x 128 B
@@ -899,8 +899,9 @@ constexpr int DW_OPER = 8 * DW_PANEL;           // 16 KB: all 256 columns of one
 constexpr int DW_BITS = DW_KROWS * 32;          // 512 B of relu'(h2) bits
 constexpr int DW_RAW = DW_OPER + 1024;          // h1 raw (K-major SWIZZLE_128B image as stored in HBM) | bits | dsdf
 constexpr int DW_CONV = 3 * DW_OPER;            // 48 KB: A mask | B hi | B lo (MN-major SWIZZLE_128B_BASE32B)
-constexpr int DW_NRAW = 4, DW_NCONV = 3;
-constexpr int DW_SMEM = DW_NRAW * DW_RAW + DW_NCONV * DW_CONV + 1024 + 1024;
+// ring depths are kept small enough (149 KB / 161 KB of shared memory) that blocks of other kernels -- the next iteration's
+// traversal needs 48 KB -- can share the SM with these persistent CTAs when the engine pipelines iterations
+constexpr int dw_smem(int nraw, int nconv) { return nraw * DW_RAW + nconv * DW_CONV + 1024 + 1024; }
 
 // MN-major SWIZZLE_128B_BASE32B descriptor (layout type 1): LBO = byte stride between 32-element MN groups (= one 2 KB
 // panel), SBO = byte stride between groups of 4 K rows (512 B); one k-step (K = 8) spans two such groups
@@ -908,7 +909,7 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(DW_PANEL >> 4) << 16) | (32ull << 32) | (1ull << 46) | (1ull << 61);
 }
 
-template <int NCW>   // converter warps (4 or 8)
+template <int NCW, int NRAW, int NCONV>   // converter warps (4 or 8), ring depths
 __global__ void __launch_bounds__(64 + 32 * NCW, 1) k_dw1_tc(long long M_host, const int32_t *__restrict__ M_dev, const uint32_t *__restrict__ act_mask2,
                                                          const float *__restrict__ act_dsdf, const float *__restrict__ act_h1,
                                                          const float *__restrict__ W1, const float *__restrict__ w2, float *__restrict__ gW1,
@@ -918,9 +919,9 @@ __global__ void __launch_bounds__(64 + 32 * NCW, 1) k_dw1_tc(long long M_host, c
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t *sm = smem_raw + (base - raw);
     // converted stages first: their operand tiles need 1024-byte alignment, the raw stages only 16
-    const uint32_t sConv = base, sRaw = base + DW_NCONV * DW_CONV;
-    uint8_t *conv_gen = sm, *raw_gen = sm + DW_NCONV * DW_CONV;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + DW_NCONV * DW_CONV + DW_NRAW * DW_RAW);
+    const uint32_t sConv = base, sRaw = base + NCONV * DW_CONV;
+    uint8_t *conv_gen = sm, *raw_gen = sm + NCONV * DW_CONV;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + NCONV * DW_CONV + NRAW * DW_RAW);
     // barriers: 0..3 raw_full  4..7 raw_empty  8..10 conv_full  11..13 conv_empty  14 d_full
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * i; };
@@ -929,8 +930,8 @@ __global__ void __launch_bounds__(64 + 32 * NCW, 1) k_dw1_tc(long long M_host, c
     const long long M = M_dev ? min((long long)*M_dev, M_host) : M_host;
     const long long nkb = ((M + TM - 1) / TM) * (TM / DW_KROWS);   // K-blocks of 16 rows (whole tiles: padded rows have dsdf = 0)
     if (tid == 0) {
-        for (int i = 0; i < DW_NRAW; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(4 + i), NCW); }
-        for (int i = 0; i < DW_NCONV; ++i) { mbar_init(BAR(8 + i), NCW); mbar_init(BAR(11 + i), 1); }
+        for (int i = 0; i < NRAW; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(4 + i), NCW); }
+        for (int i = 0; i < NCONV; ++i) { mbar_init(BAR(8 + i), NCW); mbar_init(BAR(11 + i), 1); }
         mbar_init(BAR(14), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -947,7 +948,7 @@ __global__ void __launch_bounds__(64 + 32 * NCW, 1) k_dw1_tc(long long M_host, c
     if (warp == 0) {
         uint32_t it = 0;
         for (long long kb = blockIdx.x; kb < nkb; kb += gridDim.x, ++it) {
-            const uint32_t s = it % DW_NRAW, ph = (it / DW_NRAW) & 1;
+            const uint32_t s = it % NRAW, ph = (it / NRAW) & 1;
             mbar_wait(BAR(4 + s), ph ^ 1);
             if (elect_one()) {
                 mbar_expect_tx(BAR(0 + s), DW_OPER + DW_BITS + DW_KROWS * 4);
@@ -968,7 +969,7 @@ __global__ void __launch_bounds__(64 + 32 * NCW, 1) k_dw1_tc(long long M_host, c
             constexpr uint32_t idesc = make_idesc(TM, WN) | (1u << 15) | (1u << 16);
             uint32_t it = 0;
             for (long long kb = blockIdx.x; kb < nkb; kb += gridDim.x, ++it) {
-                const uint32_t s = it % DW_NCONV, ph = (it / DW_NCONV) & 1;
+                const uint32_t s = it % NCONV, ph = (it / NCONV) & 1;
                 mbar_wait(BAR(8 + s), ph);
                 tc_fence_after();
                 const uint32_t a_m = sConv + s * DW_CONV, b_hi = a_m + DW_OPER, b_lo = a_m + 2 * DW_OPER;
@@ -1007,8 +1008,8 @@ __global__ void __launch_bounds__(64 + 32 * NCW, 1) k_dw1_tc(long long M_host, c
         const int m_word = (m_pnl & 1) * 4 + (m_pnl >> 1);         // storage order of k_mlp_tc_train: [group][kk]
         uint32_t it = 0;
         for (long long kb = blockIdx.x; kb < nkb; kb += gridDim.x, ++it) {
-            const uint32_t rs = it % DW_NRAW, rph = (it / DW_NRAW) & 1;
-            const uint32_t cs = it % DW_NCONV, cph = (it / DW_NCONV) & 1;
+            const uint32_t rs = it % NRAW, rph = (it / NRAW) & 1;
+            const uint32_t cs = it % NCONV, cph = (it / NCONV) & 1;
             mbar_wait(BAR(0 + rs), rph);          // raw tiles landed
             mbar_wait(BAR(11 + cs), cph ^ 1);     // converted stage free (its MMAs retired)
             const uint8_t *rawp = raw_gen + rs * DW_RAW;
@@ -1099,19 +1100,18 @@ __global__ void __launch_bounds__(64 + 32 * NCW, 1) k_dw1_tc(long long M_host, c
 // ================================================================================================
 constexpr int D0_RAW = DW_OPER + 1024;          // dh1 raw (16 KB) | x rows (16 x 64 B)
 constexpr int D0_CONV = 2 * DW_OPER + 2 * DW_PANEL;   // A hi | A lo | B hi | B lo = 36 KB
-constexpr int D0_NRAW = 4, D0_NCONV = 4;
-constexpr int D0_SMEM = D0_NRAW * D0_RAW + D0_NCONV * D0_CONV + 1024 + 1024;
+constexpr int d0_smem(int nraw, int nconv) { return nraw * D0_RAW + nconv * D0_CONV + 1024 + 1024; }
 
-template <int NCW>
+template <int NCW, int NRAW, int NCONV>
 __global__ void __launch_bounds__(64 + 32 * NCW, 1) k_dw0_tc(long long M_host, const int32_t *__restrict__ M_dev, const float *__restrict__ act_dh1,
                                                          const float *__restrict__ feats, float *__restrict__ gW0, float *__restrict__ gb0) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t *sm = smem_raw + (base - raw);
-    const uint32_t sConv = base, sRaw = base + D0_NCONV * D0_CONV;
-    uint8_t *conv_gen = sm, *raw_gen = sm + D0_NCONV * D0_CONV;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + D0_NCONV * D0_CONV + D0_NRAW * D0_RAW);
+    const uint32_t sConv = base, sRaw = base + NCONV * D0_CONV;
+    uint8_t *conv_gen = sm, *raw_gen = sm + NCONV * D0_CONV;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + NCONV * D0_CONV + NRAW * D0_RAW);
     // barriers: 0..3 raw_full  4..7 raw_empty  8..11 conv_full  12..15 conv_empty  16 d_full
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * i; };
@@ -1120,8 +1120,8 @@ __global__ void __launch_bounds__(64 + 32 * NCW, 1) k_dw0_tc(long long M_host, c
     const long long M = M_dev ? min((long long)*M_dev, M_host) : M_host;
     const long long nkb = ((M + TM - 1) / TM) * (TM / DW_KROWS);
     if (tid == 0) {
-        for (int i = 0; i < D0_NRAW; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(4 + i), NCW); }
-        for (int i = 0; i < D0_NCONV; ++i) { mbar_init(BAR(8 + i), NCW); mbar_init(BAR(12 + i), 1); }
+        for (int i = 0; i < NRAW; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(4 + i), NCW); }
+        for (int i = 0; i < NCONV; ++i) { mbar_init(BAR(8 + i), NCW); mbar_init(BAR(12 + i), 1); }
         mbar_init(BAR(16), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -1138,7 +1138,7 @@ __global__ void __launch_bounds__(64 + 32 * NCW, 1) k_dw0_tc(long long M_host, c
     if (warp == 0) {
         uint32_t it = 0;
         for (long long kb = blockIdx.x; kb < nkb; kb += gridDim.x, ++it) {
-            const uint32_t s = it % D0_NRAW, ph = (it / D0_NRAW) & 1;
+            const uint32_t s = it % NRAW, ph = (it / NRAW) & 1;
             mbar_wait(BAR(4 + s), ph ^ 1);
             if (elect_one()) {
                 const long long tile = kb >> 3;
@@ -1159,7 +1159,7 @@ __global__ void __launch_bounds__(64 + 32 * NCW, 1) k_dw0_tc(long long M_host, c
             constexpr uint32_t idesc = make_idesc(TM, 32) | (1u << 15) | (1u << 16);   // both operands MN-major
             uint32_t it = 0;
             for (long long kb = blockIdx.x; kb < nkb; kb += gridDim.x, ++it) {
-                const uint32_t s = it % D0_NCONV, ph = (it / D0_NCONV) & 1;
+                const uint32_t s = it % NCONV, ph = (it / NCONV) & 1;
                 mbar_wait(BAR(8 + s), ph);
                 tc_fence_after();
                 const uint32_t a_hi = sConv + s * D0_CONV, a_lo = a_hi + DW_OPER, b_hi = a_hi + 2 * DW_OPER, b_lo = b_hi + DW_PANEL;
@@ -1189,8 +1189,8 @@ __global__ void __launch_bounds__(64 + 32 * NCW, 1) k_dw0_tc(long long M_host, c
         const int ct = tid - 64;
         uint32_t it = 0;
         for (long long kb = blockIdx.x; kb < nkb; kb += gridDim.x, ++it) {
-            const uint32_t rs = it % D0_NRAW, rph = (it / D0_NRAW) & 1;
-            const uint32_t cs = it % D0_NCONV, cph = (it / D0_NCONV) & 1;
+            const uint32_t rs = it % NRAW, rph = (it / NRAW) & 1;
+            const uint32_t cs = it % NCONV, cph = (it / NCONV) & 1;
             mbar_wait(BAR(0 + rs), rph);
             mbar_wait(BAR(12 + cs), cph ^ 1);
             const uint8_t *rawp = raw_gen + rs * D0_RAW;
@@ -1358,10 +1358,12 @@ extern "C" int nl_mlp_tc_train(int64_t M, const int32_t *d_M_dev, const float *f
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::k_mlp_tc_train<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::k_mlp_tc_train<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::k_mlp_tc_train<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::k_dw1_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::DW_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::k_dw1_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::DW_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::k_dw0_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::D0_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::k_dw0_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::D0_SMEM);
+#define NL_DW_ATTR(K, NR, NC, SM)                                                                                               \
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::K<4, NR, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SM(NR, NC)); \
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::K<8, NR, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SM(NR, NC));
+        NL_DW_ATTR(k_dw1_tc, 4, 3, dw_smem) NL_DW_ATTR(k_dw1_tc, 3, 3, dw_smem) NL_DW_ATTR(k_dw1_tc, 3, 2, dw_smem)
+        NL_DW_ATTR(k_dw0_tc, 4, 4, d0_smem) NL_DW_ATTR(k_dw0_tc, 4, 3, d0_smem) NL_DW_ATTR(k_dw0_tc, 3, 3, d0_smem)
+#undef NL_DW_ATTR
         if (e != cudaSuccess) return nl_set_error_code(NL_ERR_CUDA, cudaGetErrorString(e));
         configured = true;
     }
@@ -1377,6 +1379,10 @@ extern "C" int nl_mlp_tc_train(int64_t M, const int32_t *d_M_dev, const float *f
     static int dbg_calls = 0;
     const bool want_dbg = getenv("NL_TC_TIMELINE") != nullptr;
     static const int conv_warps = [] { const char *e = getenv("NL_DW_CONV_WARPS"); return (e && atoi(e) == 4) ? 4 : 8; }();   // converter warps of the weight-gradient kernels
+    static const int dw_rings = [] {
+        const char *e = getenv("NL_DW_RINGS");
+        return !e ? 2 : (e[0] == 's' ? 0 : (e[0] == 'm' ? 1 : 2));
+    }();
     static const bool use_ts = [] { const char *e = getenv("NL_TC_TS"); return e ? atoi(e) != 0 : true; }();   // A operands of the backward GEMMs from TMEM (NL_TC_TS=0: shared memory)
     if (want_dbg && !dbg_dev) { cudaMalloc(&dbg_dev, 4 * 25 * 8 * sizeof(long long)); cudaMemset(dbg_dev, 0, 4 * 25 * 8 * sizeof(long long)); }
     p.dbg = want_dbg ? dbg_dev : nullptr;
@@ -1396,13 +1402,19 @@ extern "C" int nl_mlp_tc_train(int64_t M, const int32_t *d_M_dev, const float *f
             cudaEventRecord(ev, stream);
             cudaStreamWaitEvent(ws, ev, 0);
         }
+        // ring depths (raw, converted): "deep" (4,3)/(4,4) = 219 KB of shared memory per CTA, "mid" (3,3)/(4,3) = 201/183 KB,
+        // "shallow" (3,2)/(3,3) = 149/161 KB -- the smaller ones leave room for blocks of other kernels on the same SM when
+        // the engine pipelines iterations (NL_DW_RINGS)
+#define NL_DW_LAUNCH(NCW_, THR, R1, C1, R0, C0)                                                                                     \
+        tc::k_dw1_tc<NCW_, R1, C1><<<sms, THR, tc::dw_smem(R1, C1), ws>>>(M, d_M_dev, p.act_mask2, p.act_dsdf, p.act_h1, W1, w2, grads->gW1, \
+                                                                           grads->gW2);                                              \
+        tc::k_dw0_tc<NCW_, R0, C0><<<sms, THR, tc::d0_smem(R0, C0), ws>>>(M, d_M_dev, p.act_dh1, feats, grads->gW0, grads->gb0);
         if (conv_warps == 8) {
-            tc::k_dw1_tc<8><<<sms, 320, tc::DW_SMEM, ws>>>(M, d_M_dev, p.act_mask2, p.act_dsdf, p.act_h1, W1, w2, grads->gW1, grads->gW2);
-            tc::k_dw0_tc<8><<<sms, 320, tc::D0_SMEM, ws>>>(M, d_M_dev, p.act_dh1, feats, grads->gW0, grads->gb0);
+            if (dw_rings == 2) { NL_DW_LAUNCH(8, 320, 4, 3, 4, 4) } else if (dw_rings == 1) { NL_DW_LAUNCH(8, 320, 3, 3, 4, 3) } else { NL_DW_LAUNCH(8, 320, 3, 2, 3, 3) }
         } else {
-            tc::k_dw1_tc<4><<<sms, 192, tc::DW_SMEM, ws>>>(M, d_M_dev, p.act_mask2, p.act_dsdf, p.act_h1, W1, w2, grads->gW1, grads->gW2);
-            tc::k_dw0_tc<4><<<sms, 192, tc::D0_SMEM, ws>>>(M, d_M_dev, p.act_dh1, feats, grads->gW0, grads->gb0);
+            if (dw_rings == 2) { NL_DW_LAUNCH(4, 192, 4, 3, 4, 4) } else if (dw_rings == 1) { NL_DW_LAUNCH(4, 192, 3, 3, 4, 3) } else { NL_DW_LAUNCH(4, 192, 3, 2, 3, 3) }
         }
+#undef NL_DW_LAUNCH
         tc::k_mask_colsum<<<sms * 8, 256, 0, ws>>>(M, d_M_dev, p.act_mask2, p.act_dsdf, b1, w2, grads->gb1, grads->gW2);
     } else {
         if (use_ts) tc::k_mlp_tc_train<false, true><<<grid, tc::NTHREADS_TRAIN, tc::SMEM_TOTAL, stream>>>(p);

@@ -5,14 +5,14 @@ synchronisation inside an iteration.
 This is the host-side orchestration of SURVEY.md section 8 a-2 .. a-12; the arithmetic is all in
 libnerfloam_b200.so.  torch is used for device memory and streams only.
 """
+import contextlib
 import ctypes as C
+import os
 
 import torch
 
 from . import _capi
 from ._capi import MlpGrads, MlpWeights, RenderArgs, RenderStats
-
-import os
 
 STATS_BYTES = C.sizeof(RenderStats)
 N_SAMPLES_OFFSET = RenderStats.n_samples.offset
@@ -218,6 +218,11 @@ class SDFEngine:
         # warp-cooperative traversal over the packed octree image; False: one thread per ray over (centres, structure)
         self.use_packed_octree = os.environ.get("NL_PACKED_OCTREE", "1") != "0"
         self._side = None
+        # software pipelining across iterations (forward_backward(defer_wgrad=True)): the weight-gradient kernels and the decoder's
+        # Adam of iteration i stay on the side stream while the main stream already runs the embedding scatter, the other Adam
+        # steps and iteration i+1 up to its decoder; what they read of iteration i (sample count, features) is double-buffered
+        self._pending = False
+        self._alt = None
 
     def _mark(self, name):
         if self.events is not None:
@@ -292,8 +297,25 @@ class SDFEngine:
         _capi.LAUNCHES += 1
 
     # ------------------------------------------------------------------ full passes
+    def side_stream(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
+
+    def join_side(self):
+        """Main stream waits for deferred decoder work (weight gradients + the decoder's Adam) of the previous iteration."""
+        if self._pending:
+            torch.cuda.current_stream(self.device).wait_stream(self._side)
+            self._pending = False
+
+    def _flip_buffers(self):
+        if self._alt is None:
+            self._alt = (torch.zeros_like(self.stats), torch.empty_like(self.feats))
+        (self.stats, self.feats), self._alt = self._alt, (self.stats, self.feats)
+
     def forward(self, m, dec, R, cfg, ray_o=None, ray_d=None, noise=None, rng_seed=0, reference_compat=True):
         """Forward only (render_rays / evaluation): fills s_*, feats, sdf.  Returns nothing; read_stats() for sizes."""
+        self.join_side()
         self._vs = cfg["voxel_size"]
         self.render_samples(m, R, cfg, ray_o, ray_d, None, None, noise, rng_seed, reference_compat)
         dec.refresh_transposes()
@@ -302,12 +324,16 @@ class SDFEngine:
 
     def forward_backward(self, m, dec, R, cfg, gt_depth, cos, dir_local=None, ray_frame=None, n_frames=1, ray_o=None,
                          ray_d=None, noise=None, rng_seed=0, reference_compat=True, update_decoder=True, update_emb=True,
-                         update_pose=True, pose6=None, group=None, refresh_weights=True, rng_seed_dev=None):
+                         update_pose=True, pose6=None, group=None, refresh_weights=True, rng_seed_dev=None, defer_wgrad=False):
         """One optimisation iteration without the optimiser step.  Gradients land in
-        self.grad_emb (fp32 [V,16]), dec.grads (fp32), self.pose_grad (fp32 [F,6]); the loss in stats."""
+        self.grad_emb (fp32 [V,16]), dec.grads (fp32), self.pose_grad (fp32 [F,6]); the loss in stats.
+        defer_wgrad=True: return without waiting for the decoder's weight gradients -- they (and whatever the caller enqueues on
+        side_stream(), i.e. the decoder's optimiser step) are joined right before the next iteration's decoder, or by join_side()."""
         lib = _capi.lib()
         st = _capi.stream_ptr()
         self._vs = cfg["voxel_size"]
+        if self._pending:
+            self._flip_buffers()     # the deferred kernels still read the previous iteration's sample count and features
         self._mark("t0")
         self.render_samples(m, R, cfg, ray_o, ray_d, gt_depth, cos, noise, rng_seed, reference_compat, rng_seed_dev)
         if group is not None:   # the loss normalisation is global (criterion.py:84-100): one tiny exchange before backward
@@ -317,9 +343,10 @@ class SDFEngine:
                         "nl_loss_prepare")
             _capi.LAUNCHES += 1
         self._mark("t_samples")
+        self.gather_forward(m)
+        self.join_side()             # decoder weights (and gradient buffers) of the previous iteration are final from here on
         if refresh_weights:
             dec.refresh_transposes()
-        self.gather_forward(m)
         self._mark("t_gather_fwd")
         if update_decoder:
             self._ensure_act(dec.width)
@@ -354,14 +381,20 @@ class SDFEngine:
                 _capi.ptr(dir_local) if want_pose else None, _capi.ptr(ray_frame) if want_pose else None, int(n_frames),
                 _capi.ptr(self.pose_acc) if want_pose else None, st), "nl_gather_trilinear_bwd")
             _capi.LAUNCHES += 1
-        if side is not None:
+        defer = defer_wgrad and side is not None
+        if side is not None and not defer:
             torch.cuda.current_stream(self.device).wait_stream(side)   # decoder gradients complete before they are reduced / applied
         self._mark("t_gather_bwd")
         if group is not None:
             from . import dist as nldist
             nldist.allreduce_loss_sums(self.stats, group)
-            nldist.allreduce_grads([self.grad_emb if update_emb else None] + (list(dec.grads) if update_decoder else []) +
+            nldist.allreduce_grads([self.grad_emb if update_emb else None] + (list(dec.grads) if (update_decoder and not defer) else []) +
                                    [self.pose_acc if want_pose else None], group)
+            if defer:                # the decoder's gradients are reduced where they are produced
+                with torch.cuda.stream(side):
+                    nldist.allreduce_grads(list(dec.grads), group)
+        if defer:
+            self._pending = True
         if want_pose:
             _capi.check(lib.nl_pose_grad(n_frames, _capi.ptr(pose6), _capi.ptr(self.pose_acc), _capi.ptr(self.pose_grad), st),
                         "nl_pose_grad")
@@ -384,13 +417,18 @@ class FusedAdam:
             g["m"] = torch.zeros_like(p)
             g["v"] = torch.zeros_like(p)
 
-    def step(self):
+    def step(self, side_stream=None):
+        """side_stream: the groups marked side=True (the decoder, whose gradients are produced there) are updated on that stream."""
         self.step_count += 1
         lib = _capi.lib()
-        st = _capi.stream_ptr()
-        for g in self.groups:
-            p = g["param"]
-            fn = lib.nl_adam_bf16 if p.dtype == torch.bfloat16 else lib.nl_adam_f32
-            _capi.check(fn(p.numel(), _capi.ptr(p), _capi.ptr(g["grad"]), _capi.ptr(g["m"]), _capi.ptr(g["v"]), float(g["lr"]),
-                           self.betas[0], self.betas[1], self.eps, self.step_count, st), "nl_adam")
-            _capi.LAUNCHES += 1
+        passes = [(None, self.groups)] if side_stream is None else \
+            [(None, [g for g in self.groups if not g.get("side")]), (side_stream, [g for g in self.groups if g.get("side")])]
+        for stream, gs in passes:
+            with (torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()):
+                st = _capi.stream_ptr()
+                for g in gs:
+                    p = g["param"]
+                    fn = lib.nl_adam_bf16 if p.dtype == torch.bfloat16 else lib.nl_adam_f32
+                    _capi.check(fn(p.numel(), _capi.ptr(p), _capi.ptr(g["grad"]), _capi.ptr(g["m"]), _capi.ptr(g["v"]), float(g["lr"]),
+                                   self.betas[0], self.betas[1], self.eps, self.step_count, st), "nl_adam")
+                    _capi.LAUNCHES += 1

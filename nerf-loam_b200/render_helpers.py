@@ -12,6 +12,7 @@ Behavioural notes (also in DESIGN.md):
     (voxel_helpers.py:531-533; render_helpers.py:190-318);
   * the unused autograd.grad(sdf, xyz) of render_helpers.py:293-297 is not computed.
 """
+import os
 from copy import deepcopy
 
 import torch
@@ -250,7 +251,10 @@ def bundle_adjust_frames(keyframe_graph, embeddings, map_states, sdf_network, lo
             f.pose.requires_grad_(True)
     groups = [dict(param=emb, grad=None, lr=learning_rate[0])]
     if update_decoder:
-        groups += [dict(param=p.data, grad=g, lr=learning_rate[1]) for p, g in zip(bufs.params, bufs.grads)]
+        groups += [dict(param=p.data, grad=g, lr=learning_rate[1], side=True) for p, g in zip(bufs.params, bufs.grads)]
+    # decoder weight gradients + the decoder's Adam stay on the engine's side stream and are joined right before the next
+    # iteration's decoder (engine.SDFEngine.forward_backward, defer_wgrad): same arithmetic, shorter critical path
+    pipeline = update_decoder and os.environ.get("NL_PIPELINE", "1") != "0"
     pose_rows = [i for i, po in enumerate(pose_opt) if po]
     pose_params = [pose6[i] for i in pose_rows]                    # views into pose6 (contiguous rows)
     opt = None
@@ -260,7 +264,8 @@ def bundle_adjust_frames(keyframe_graph, embeddings, map_states, sdf_network, lo
         noise = noise_per_iter[it] if noise_per_iter is not None else None
         seed = 0 if (deterministic or noise is not None) else _seed_from_torch()
         eng.forward_backward(m, bufs, dirs.shape[0], cfg, gt, cos, dir_local=dirs, ray_frame=fid, n_frames=F, noise=noise,
-                             rng_seed=seed, update_decoder=update_decoder, update_emb=True, update_pose=any(pose_opt), pose6=pose6)
+                             rng_seed=seed, update_decoder=update_decoder, update_emb=True, update_pose=any(pose_opt), pose6=pose6,
+                             defer_wgrad=pipeline)
         if opt is None:
             groups[0]["grad"] = eng.grad_emb
             pg = [dict(param=pose_params[k], grad=eng.pose_grad[i], lr=learning_rate[2]) for k, i in enumerate(pose_rows)]
@@ -271,7 +276,8 @@ def bundle_adjust_frames(keyframe_graph, embeddings, map_states, sdf_network, lo
                 print("Encouter a bug while Mapping, currently not be fixed, Continue!!")  # render_helpers.py:407-409
                 continue
             loss_log.append(st.loss)
-        opt.step()
+        opt.step(side_stream=eng.side_stream() if eng._pending else None)
+    eng.join_side()
     with torch.no_grad():
         host = pose6.cpu()
         for i, f in enumerate(frames):
