@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(64) k_traverse_sort(int R, float voxel_size, f
     if (r < R) {
         int32_t idx[NL_MAX_HITS];
         float mn[NL_MAX_HITS], mx[NL_MAX_HITS];
+        mn[0] = 0.f;   // never read before the first insertion (the loop guard tests p > 0 first); keeps the compiler quiet
         const NlRay ray = nl_make_ray(ray_o[r * 3], ray_o[r * 3 + 1], ray_o[r * 3 + 2], ray_d[r * 3], ray_d[r * 3 + 1], ray_d[r * 3 + 2]);
         int cnt = 0;
         const int rc = nl_traverse(ray, centres, structure, voxel_size * 0.5f, NL_MAX_HITS, [&](int k, float lo, float hi) {

@@ -30,6 +30,22 @@ def test_library_exports_every_declared_symbol(nl):
     assert ctypes.sizeof(nl._capi.RenderStats) == 160 and nl._capi.RenderStats.n_samples.offset == 12
 
 
+def test_ctypes_signatures_match_the_header(nl):
+    """Every prototype in the header has the same number of parameters as the ctypes binding (catches ABI drift between
+    include/nerfloam_b200.h, the .cu/.cpp definitions behind it and _capi.py)."""
+    hdr = open(os.path.join(ROOT, "include", "nerfloam_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    protos = dict(re.findall(r"NL_API [^;(]*?\b(nl_[a-z0-9_]+)\(([^;]*?)\);", hdr, flags=re.S))
+    assert set(protos) == set(nl._capi._SIGNATURES)
+    for name, params in protos.items():
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(nl._capi._SIGNATURES[name][1]), (name, n, len(nl._capi._SIGNATURES[name][1]))
+    sizes = (ctypes.c_int32 * 4)()
+    nl._capi.lib().nl_abi_sizes(ctypes.byref(sizes))
+    assert list(sizes)[:3] == [ctypes.sizeof(nl._capi.RenderStats), nl._capi.RenderStats.n_samples.offset, ctypes.sizeof(nl._capi.RenderArgs)]
+
+
 def test_octree_bit_exact_vs_reference_golden(nl):
     z = golden("octree.npz")
     o = nl.svo.Octree()
