@@ -103,10 +103,6 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if os.environ.get("NL_HP_STREAM", "0") != "0":
-        # the engine's deferred weight-gradient kernels run on a default-priority side stream; with the caller's work on a
-        # high-priority stream the next iteration's traversal / sampling blocks win freed SM resources ahead of them
-        torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=-1))
     group = None
     if world > 1:
         import torch.distributed as dist
