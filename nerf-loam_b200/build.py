@@ -64,5 +64,30 @@ def build(force=False, verbose=False):
     return LIB
 
 
+SVO_LIB = os.path.join(HERE, "svo_b200.so")
+
+
+def build_svo_shim(force=False, verbose=False):
+    """TorchScript custom-class shim `torch.classes.svo.Octree` (csrc/shim/svo_torch.cpp): host-only C++ compiled with g++
+    against libtorch; it carries its own copy of the octree (octree_host.cpp, nl_error.cpp), so it has no CUDA dependency and can
+    be loaded with torch.classes.load_library() exactly where the reference loads its svo extension (src/mapping.py:19-20)."""
+    from torch.utils import cpp_extension as ce
+    import torch
+    src = [os.path.join(CSRC, "shim", "svo_torch.cpp"), os.path.join(CSRC, "octree_host.cpp"), os.path.join(CSRC, "nl_error.cpp")]
+    deps = src + [os.path.join(os.path.dirname(HERE), "include", "nerfloam_b200.h"), os.path.join(CSRC, "nl_error.h")]
+    if not (force or _stale(SVO_LIB, deps)):
+        return SVO_LIB
+    inc = [a for pth in ce.include_paths() for a in ("-isystem", pth)] + ["-I", os.path.join(os.path.dirname(HERE), "include"), "-I", CSRC]
+    libdir = os.path.join(os.path.dirname(torch.__file__), "lib")
+    abi = "-D_GLIBCXX_USE_CXX11_ABI=%d" % int(torch._C._GLIBCXX_USE_CXX11_ABI)
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", abi, "-DNL_NO_CUDA"] + inc + src + \
+          ["-o", SVO_LIB, "-L", libdir, "-Wl,-rpath," + libdir, "-ltorch", "-ltorch_cpu", "-lc10"]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return SVO_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_svo_shim(force="--force" in sys.argv, verbose=True))

@@ -215,3 +215,38 @@ def test_product_never_touches_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dp, fn), errors="ignore").read()
                 assert "oracle" not in src.replace("oracle/ is", "").lower() or fn == "__init__.py" and False, f"{fn} mentions oracle"
+
+
+def test_torchscript_svo_shim_is_a_drop_in_for_the_reference_extension(nl):
+    """`torch.classes.load_library(<svo_b200.so>)` + `torch.classes.svo.Octree()` -- the two statements of src/mapping.py:19-20,81 --
+    give an object with the reference's methods whose exports are bit-identical to the executed reference (goldens)."""
+    import io
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "nerf-loam_b200"))
+    import build as nlbuild
+    torch.classes.load_library(nlbuild.build_svo_shim())
+    z = golden("octree.npz")
+    o = torch.classes.svo.Octree()
+    o.init(256 * 256 * 4, 16, 0.3)
+    o.insert(torch.from_numpy(z["v1"]))
+    v, c, f = o.get_centres_and_children()
+    assert np.array_equal(v.numpy(), z["voxels1"]) and np.array_equal(c.numpy(), z["children1"]) and np.array_equal(f.numpy(), z["features1"])
+    assert [o.count_nodes(), o.count_leaf_nodes()] == list(z["count1"])
+    o.insert(torch.from_numpy(z["v2"]))
+    v, c, f = o.get_centres_and_children()
+    assert np.array_equal(v.numpy(), z["voxels2"]) and np.array_equal(c.numpy(), z["children2"]) and np.array_equal(f.numpy(), z["features2"])
+    assert [o.count_nodes(), o.count_leaf_nodes()] == list(z["count2"])
+    p = nl.svo.Octree()
+    p.init(256 * 256 * 4, 16, 0.3)
+    p.insert(torch.from_numpy(z["v1"])); p.insert(torch.from_numpy(z["v2"]))
+    assert torch.equal(o.get_voxels(), p.get_voxels()) and torch.equal(o.get_leaf_voxels(), p.get_leaf_voxels())
+    pt = torch.from_numpy(z["v1"][0])
+    assert o.has_voxel(pt) and not o.has_voxel(torch.tensor([1, 1, 1], dtype=torch.int32))
+    assert o.try_insert(torch.from_numpy(z["v1"][:10])) == p.try_insert(torch.from_numpy(z["v1"][:10]))
+    assert torch.ops.svo.encode(torch.tensor([3, 5, 7], dtype=torch.int32)) == nl.svo.encode(3, 5, 7)
+    buf = io.BytesIO()                                                   # def_pickle: state = (size, feat_dim, voxel_size, inserted tensors)
+    torch.save(o, buf)
+    buf.seek(0)
+    o2 = torch.load(buf, weights_only=False)
+    v2, c2, f2 = o2.get_centres_and_children()
+    assert torch.equal(v2, v) and torch.equal(c2, c) and torch.equal(f2, f)
