@@ -139,7 +139,7 @@ def run_ours(args):
             state["opt"] = nl.engine.FusedAdam(groups)
         # pipelined: the decoder's Adam follows its weight-gradient kernels on the side stream; the main stream goes on with the
         # embedding / pose update and the next iteration's rays, traversal, sampling and gather, and joins before its decoder
-        state["opt"].step(side_stream=eng.side_stream() if eng._pending else None)
+        state["opt"].step(side_stream=eng.deferred_stream())
 
     def sync_all():
         if world > 1:

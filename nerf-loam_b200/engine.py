@@ -302,6 +302,11 @@ class SDFEngine:
             self._side = torch.cuda.Stream(device=self.device)
         return self._side
 
+    def deferred_stream(self):
+        """The side stream if the last forward_backward(defer_wgrad=True) left decoder work on it (pass it to
+        FusedAdam.step(side_stream=...) so the decoder's update follows its gradients there), else None."""
+        return self._side if self._pending else None
+
     def join_side(self):
         """Main stream waits for deferred decoder work (weight gradients + the decoder's Adam) of the previous iteration."""
         if self._pending:

@@ -276,7 +276,7 @@ def bundle_adjust_frames(keyframe_graph, embeddings, map_states, sdf_network, lo
                 print("Encouter a bug while Mapping, currently not be fixed, Continue!!")  # render_helpers.py:407-409
                 continue
             loss_log.append(st.loss)
-        opt.step(side_stream=eng.side_stream() if eng._pending else None)
+        opt.step(side_stream=eng.deferred_stream())
     eng.join_side()
     with torch.no_grad():
         host = pose6.cpu()
