@@ -106,25 +106,30 @@ int64_t encode_torch(torch::Tensor pt) {                                 // util
 
 }  // namespace
 
-TORCH_LIBRARY(svo, m) {
-    m.def("encode", &encode_torch);
-    m.class_<Octree>("Octree")
-        .def(torch::init<>())
-        .def("init", &Octree::init)
-        .def("insert", &Octree::insert)
-        .def("try_insert", &Octree::try_insert)
-        .def("get_voxels", &Octree::get_voxels)
-        .def("get_leaf_voxels", &Octree::get_leaf_voxels)
-        .def("get_features", &Octree::get_features)
-        .def("count_nodes", &Octree::count_nodes)
-        .def("count_leaf_nodes", &Octree::count_leaf_nodes)
-        .def("has_voxel", &Octree::has_voxel)
-        .def("get_centres_and_children", &Octree::get_centres_and_children)
-        .def_pickle(
-            [](const c10::intrusive_ptr<Octree> &self) -> std::tuple<int64_t, int64_t, double, std::vector<torch::Tensor>> {
-                return std::make_tuple(self->size_, self->feat_dim_, self->voxel_size_, self->all_pts);
-            },
-            [](std::tuple<int64_t, int64_t, double, std::vector<torch::Tensor>> state) {
-                return c10::make_intrusive<Octree>(std::get<0>(state), std::get<1>(state), std::get<2>(state), std::get<3>(state));
-            });
+// Serialised form used by torch.save / copy.deepcopy of the reference's class: tree extent, feature width, voxel size and
+// every tensor that was ever inserted (the tree is rebuilt by replaying them, which also reproduces the node ids).
+using OctreeState = std::tuple<int64_t, int64_t, double, std::vector<torch::Tensor>>;
+
+OctreeState octree_getstate(const c10::intrusive_ptr<Octree> &tree) {
+    return OctreeState(tree->size_, tree->feat_dim_, tree->voxel_size_, tree->all_pts);
+}
+
+c10::intrusive_ptr<Octree> octree_setstate(OctreeState st) {
+    auto &[extent, width, voxel, inserted] = st;
+    return c10::make_intrusive<Octree>(extent, width, voxel, std::move(inserted));
+}
+
+TORCH_LIBRARY(svo, lib) {
+    lib.def("encode", &encode_torch);
+    auto cls = lib.class_<Octree>("Octree");
+    cls.def(torch::init<>());
+    // allocation and queries, names and argument lists as in third_party/sparse_octree/src/bindings.cpp:11-22
+    cls.def("init", &Octree::init).def("insert", &Octree::insert).def("try_insert", &Octree::try_insert);
+    cls.def("has_voxel", &Octree::has_voxel).def("get_features", &Octree::get_features);
+    cls.def("get_voxels", &Octree::get_voxels).def("get_leaf_voxels", &Octree::get_leaf_voxels);
+    cls.def("count_nodes", &Octree::count_nodes).def("count_leaf_nodes", &Octree::count_leaf_nodes);
+    cls.def("get_centres_and_children", &Octree::get_centres_and_children);
+    // def_pickle only takes lambdas (torch/custom_class.h)
+    cls.def_pickle([](const c10::intrusive_ptr<Octree> &tree) { return octree_getstate(tree); },
+                   [](OctreeState st) { return octree_setstate(std::move(st)); });
 }
