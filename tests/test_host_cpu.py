@@ -192,6 +192,21 @@ def test_pose_and_frame_host_api(nl):
     assert float(f.pose.data[0]) == 2000.0 and f.rays_d.shape == (500, 1, 3)
     f.sample_rays(64)
     assert f.sample_mask.shape == (500, 1) and int(f.sample_mask.sum()) == 64
+    # same seed -> same rays as the reference's selection (sample_util.py:4-19 restated literally: Gumbel top-k on log-probabilities)
+    def reference_mask(n, k):
+        mask = torch.ones((n, 1))[None, ...]
+        probs = (mask / (mask.sum() + 1e-9)).reshape(1, -1)
+        logp = torch.log(probs + 1e-9)
+        scores = logp + (-torch.log(-torch.log(torch.rand_like(logp) + 1e-7) + 1e-7))
+        idx = scores.topk(k, dim=-1)[1]
+        return (torch.zeros_like(probs).scatter_(-1, idx, 1).reshape(1, n, 1) > 0)[0, ...]
+    for seed in (0, 7):
+        torch.manual_seed(seed)
+        ref = reference_mask(500, 64)
+        torch.manual_seed(seed)
+        f.sample_rays(64)
+        assert torch.equal(f.sample_mask, ref)
+    np.testing.assert_array_equal(f.rays_norm.numpy(), (torch.norm(pts, 2, -1, keepdim=True) + 1e-8).numpy())
 
 
 def test_criterion_host_forward_vs_reference_golden(nl):
