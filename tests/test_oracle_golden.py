@@ -185,3 +185,61 @@ def test_mapping_iterations_vs_reference(name, upd_dec):
     assert np.mean(np.abs(emb.detach().float().numpy() - e_ref) > 1e-3) < 1e-3
     for k, v in dec.state_dict().items():
         np.testing.assert_allclose(v.numpy(), z[f"{name}_dec_after_{k}"], atol=2e-4)
+
+
+def test_config0_plumbing_on_cpu():
+    """BASELINE.json configs[0]: a 1k-point scan, an 8^3 octree and a 2x32 decoder, entirely on the CPU through the oracle: the chain
+    runs end to end, the loss is finite, and its gradient w.r.t. the pose agrees with central finite differences."""
+    import torch
+    from oracle import chain as OC
+    from oracle import kernels as OK
+    rng = np.random.default_rng(7)
+    n = 1000
+    world = np.stack([rng.uniform(1.0, 6.0, n), rng.uniform(1.0, 6.0, n), np.full(n, 2.3) + rng.normal(0, 0.02, n)], -1)
+    sensor = np.array([3.5, 3.5, 5.8])
+    pts = torch.from_numpy((world - sensor).astype(np.float32))
+    vox = np.floor(world.astype(np.float32) / np.float32(1.0)).astype(np.int32)
+    tree = OK.Octree()
+    tree.init(8, 16, 1.0)
+    tree.insert(vox)
+    v, c, f = tree.get_centres_and_children()
+    centres, structure, vertex = OK.map_arrays(v, c, f, 1.0)
+    assert structure[0, 8] == 8 and (structure[:, 8] == 1).sum() == tree.count_leaf_nodes() > 0
+    ids = np.unique(vertex[vertex >= 0])
+    remap = np.full(int(vertex.max()) + 1, -1, np.int64)
+    remap[ids] = np.arange(ids.shape[0])
+    rows = np.where(vertex >= 0, remap[np.clip(vertex, 0, None)], -1)
+    torch.manual_seed(0)
+    emb = (torch.randn(ids.shape[0], 16) * 0.05).requires_grad_()
+    dec = OC.Decoder(depth=2, width=32, in_dim=16)
+    map_np = {"centres": centres, "structure": structure, "vertex_rows": rows}
+    cfg = dict(step_size=0.5, voxel_size=1.0, max_distance=40.0, truncation=0.3, max_depth=40.0, fs_weight=1.0, sdf_weight=10000.0)
+    dirs = pts / pts.norm(dim=-1, keepdim=True)
+    cos = torch.ones(n)
+
+    def loss_at(p6):
+        loss, out = OC.mapping_iteration([dict(pose=p6, dirs=dirs, points=pts, cos=cos)], map_np, emb, dec, cfg, deterministic=True)
+        return loss, out
+    pose = torch.tensor([3.5, 3.5, 5.8, 0.0, 0.0, 0.0], requires_grad=True)
+    loss, out = loss_at(pose)
+    assert out is not None and torch.isfinite(loss) and int(out["ray_mask"].sum()) > 0.9 * n
+    loss.backward()
+    assert emb.grad is not None and torch.isfinite(emb.grad).all() and float(emb.grad.abs().max()) > 0
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in dec.parameters())
+    assert pose.grad is not None and torch.isfinite(pose.grad).all() and float(pose.grad.abs().max()) > 0
+    # Finite differences against autograd where the chain is differentiable: the embedding table (the ray/voxel intersection and
+    # the sampler run without gradient in the reference, voxel_helpers.py:92-137 / :262-344, so d loss / d pose deliberately ignores
+    # how the sample depths move with the pose and cannot be checked this way).
+    ge = emb.grad.clone()
+    flat = ge.abs().flatten()
+    for idx in torch.topk(flat, 3).indices.tolist():
+        r, cidx = divmod(idx, 16)
+        h = 1e-2
+        with torch.no_grad():
+            emb[r, cidx] += h
+            lp, _ = loss_at(pose.detach())
+            emb[r, cidx] -= 2 * h
+            lm, _ = loss_at(pose.detach())
+            emb[r, cidx] += h
+        fd = float(lp - lm) / (2 * h)
+        assert abs(fd - float(ge[r, cidx])) <= 0.05 * abs(float(ge[r, cidx])) + 1e-3, (r, cidx, fd, float(ge[r, cidx]))
