@@ -265,3 +265,27 @@ def test_torchscript_svo_shim_is_a_drop_in_for_the_reference_extension(nl):
     o2 = torch.load(buf, weights_only=False)
     v2, c2, f2 = o2.get_centres_and_children()
     assert torch.equal(v2, v) and torch.equal(c2, c) and torch.equal(f2, f)
+
+
+def test_c_abi_rejects_bad_arguments_without_touching_the_gpu(nl):
+    """Every entry point validates its arguments before the first CUDA call and reports through a status + nl_last_error()
+    (the reference's kernels exit(-1) on errors, cuda_utils.h:37-48; its CHECK_* macros raise on bad tensors)."""
+    L = nl._capi.lib()
+    err = lambda: L.nl_last_error().decode()
+    assert L.nl_gather_trilinear_fwd(-1, None, None, None, None, None, None, 0.3, None, None) != 0 and "negative" in err()
+    assert L.nl_gather_trilinear_fwd(5, None, None, None, None, None, None, 0.3, None, None) != 0 and "null" in err()
+    assert L.nl_gather_trilinear_fwd(0, None, None, None, None, None, None, 0.3, None, None) == 0          # empty input is fine
+    assert L.nl_mlp_tc_forward(7, None, None, None, None, None, None, None, None, None) != 0 and "null" in err()
+    assert L.nl_mlp_tc_forward(0, None, None, None, None, None, None, None, None, None) == 0
+    assert L.nl_adam_f32(3, None, None, None, None, 1e-3, 0.9, 0.999, 1e-8, 1, None) != 0 and "null" in err()
+    assert L.nl_adam_f32(3, None, None, None, None, 1e-3, 0.9, 0.999, 1e-8, 0, None) != 0                 # Adam steps start at 1
+    assert L.nl_octree_pack_children(0, None, None, None, None) != 0 and "positive" in err()
+    assert L.nl_octree_pack_children(1 << 26, None, None, None, None) != 0 and "2^26" in err()
+    assert L.nl_render_samples(None, None) != 0 and "null" in err()
+    a = nl._capi.RenderArgs()
+    a.n_rays, a.n_nodes = 0, 5
+    assert L.nl_render_samples(ctypes.byref(a), None) != 0 and "positive" in err()
+    assert L.nl_render_workspace_bytes(-1) == -1 and L.nl_render_workspace_bytes(1000) > 1000 * 240
+    assert L.nl_octree_create(0, 16, 0.3) is None and err() != ""                                        # grid_dim must be positive
+    with pytest.raises(nl._capi.NerfLoamError):
+        nl._capi.check(L.nl_svo_intersect(1, 1, 1, 0.3, 20, None, None, None, None, None, None, None, None), "nl_svo_intersect")
