@@ -98,6 +98,19 @@ def host_rays(pts, cos):
     return dirs.pin_memory(), gt.pin_memory(), torch.from_numpy(cos).float().contiguous().pin_memory()
 
 
+def _traffic_record(kernel_key):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture of THIS build (profiles/r02_traffic.json, written by
+    scripts/summarise_profiles.py from an `ncu --set full` report); None when no capture is recorded."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    d = json.load(open(p))
+    rec = d.get(kernel_key)
+    if not rec:
+        return None, None
+    return rec.get("dram_bytes"), {"ncu_report": rec.get("report"), "read": rec.get("read"), "write": rec.get("write"), "samples": rec.get("samples")}
+
+
 def run_ours(args):
     import nerfloam_b200 as nl
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
@@ -108,6 +121,9 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
+    # ONE clock poller for the whole job, started before the warm-up (eight NVML attaches right before the timed region were a
+    # transient inside it in round 1)
+    clocks = ClockSampler(local) if rank == 0 else None
     scans, mu, ms, dec = build_problem(nl, world, dev)
     pts, cos, pose = scans[rank]
     h_dirs, h_gt, h_cos = host_rays(pts, cos)
@@ -129,14 +145,14 @@ def run_ours(args):
         if not update_decoder:          # steady-state variant (decoder frozen after freeze_frame frames, mapping.py:196)
             if "opt_frozen" not in state:
                 state["opt_frozen"] = nl.engine.FusedAdam([dict(param=emb, grad=eng.grad_emb, lr=LR[0]),
-                                                           dict(param=pose6[0], grad=eng.pose_grad[0], lr=LR[2])])
+                                                           dict(param=pose6[0], grad=eng.pose_grad[0], lr=LR[2])], ctl=lambda: eng.ctl)
             state["opt_frozen"].step()
             return
         if state["opt"] is None:
             groups = [dict(param=emb, grad=eng.grad_emb, lr=LR[0])]
             groups += [dict(param=p.data, grad=g, lr=LR[1], side=True) for p, g in zip(bufs.params, bufs.grads)]
             groups += [dict(param=pose6[0], grad=eng.pose_grad[0], lr=LR[2])]
-            state["opt"] = nl.engine.FusedAdam(groups)
+            state["opt"] = nl.engine.FusedAdam(groups, ctl=lambda: eng.ctl)
         # pipelined: the decoder's Adam follows its weight-gradient kernels on the side stream; the main stream goes on with the
         # embedding / pose update and the next iteration's rays, traversal, sampling and gather, and joins before its decoder
         state["opt"].step(side_stream=eng.deferred_stream())
@@ -147,24 +163,60 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(fn, n, finish=None):
+        """n calls of fn between two events (barrier + synchronize on both sides): total ms."""
+        sync_all()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        if finish:
+            finish()
+        b.record()
+        sync_all()
+        return a.elapsed_time(b)
+
     # ---------------- device-resident timing (value) ----------------
-    for _ in range(max(args.warmup, 3)):
+    eng.begin_call()
+    W = max(args.warmup, 3)
+    for _ in range(W):
         step(d_dirs, d_gt, d_cos)
+    # settle: clocks, allocator, NCCL channels and the two-stream pipeline reach steady state before the clock starts (untimed, >= 100 ms)
     sync_all()
-    clocks = ClockSampler(local)
+    t_s = time.perf_counter()
+    n_settle = 0
+    while time.perf_counter() - t_s < 0.10:
+        for _ in range(8):
+            step(d_dirs, d_gt, d_cos)
+        torch.cuda.synchronize()
+        n_settle += 8
+    if world > 1:       # same number of settle steps on every rank (collectives inside)
+        import torch.distributed as dist
+        t_n = torch.tensor([n_settle], device=dev); dist.all_reduce(t_n, op=dist.ReduceOp.MAX)
+        for _ in range(int(t_n.item()) - n_settle):
+            step(d_dirs, d_gt, d_cos)
+        n_settle = int(t_n.item())
     l0 = nl._capi.LAUNCHES
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    samples = 0
-    e0.record()
-    for _ in range(args.steps):
-        step(d_dirs, d_gt, d_cos)
-    eng.join_side()      # deferred decoder work of the last iteration belongs to the timed region
-    e1.record()
-    sync_all()
-    ms_total = e0.elapsed_time(e1)
+    ms_total = timed(lambda: step(d_dirs, d_gt, d_cos), args.steps, eng.join_side)   # deferred decoder work of the last iteration is inside
     launches = nl._capi.LAUNCHES - l0
     st = eng.read_stats()
     n_local = st.n_samples
+    # ---------------- the same loop over >= 250 ms with one event per step: median / max (what a 32 ms window cannot show) ----------------
+    n_long = max(args.steps, int(0.25 / max(ms_total / args.steps * 1e-3, 1e-6)) + 1)
+    if world > 1:
+        import torch.distributed as dist
+        t_n = torch.tensor([n_long], device=dev); dist.all_reduce(t_n, op=dist.ReduceOp.MAX); n_long = int(t_n.item())
+    sync_all()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_long + 1)]
+    evs[0].record()
+    for i in range(n_long):
+        step(d_dirs, d_gt, d_cos)
+        evs[i + 1].record()
+    eng.join_side()
+    sync_all()
+    per_step = np.array([evs[i].elapsed_time(evs[i + 1]) for i in range(n_long)])
+    long_stats = {"steps": n_long, "ms_total": float(evs[0].elapsed_time(evs[-1])), "ms_median": float(np.median(per_step)),
+                  "ms_p90": float(np.percentile(per_step, 90)), "ms_max": float(per_step.max()), "ms_mean": float(per_step.mean())}
     # per-stage times for the roofline: a separate pass with CUDA events around the stages and the weight-gradient kernels
     # serialised on the main stream (in the timed loop above they overlap with the embedding scatter on a second stream)
     ov = eng.overlap_wgrad
@@ -188,14 +240,7 @@ def run_ours(args):
         step(d_dirs, d_gt, d_cos, update_decoder=False)
     sync_all()
     eng.events = {}
-    z0, z1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    z0.record()
-    for _ in range(args.steps):
-        step(d_dirs, d_gt, d_cos, update_decoder=False)
-    eng.join_side()      # deferred decoder work of the last iteration belongs to the timed region
-    z1.record()
-    sync_all()
-    ms_frozen = z0.elapsed_time(z1)
+    ms_frozen = timed(lambda: step(d_dirs, d_gt, d_cos, update_decoder=False), args.steps, eng.join_side)
     evf = eng.events
     eng.events = None
     t_mlp_frozen = float(np.mean([a.elapsed_time(b) for a, b in zip(evf["t_gather_fwd"], evf["t_mlp"])]))
@@ -243,25 +288,25 @@ def run_ours(args):
         loss_host.copy_(eng.stats, non_blocking=True)
     for _ in range(3):
         step_e2e()
-    sync_all()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for _ in range(args.steps):
-        step_e2e()
-    eng.join_side()      # deferred decoder work of the last iteration belongs to the timed region
-    f1.record()
-    sync_all()
-    ms_e2e = f0.elapsed_time(f1)
-    clk = clocks.stop()
+    ms_e2e = timed(step_e2e, args.steps, eng.join_side)
     loss_val = nl._capi.RenderStats.from_buffer_copy(loss_host.numpy().tobytes()).loss
+    ctl = eng.read_ctl()
+
+    # ---------------- north-star split (BASELINE.json config 5): ONE scan ray-sharded over the ranks (strong scaling) ----------------
+    strong = None
+    if world > 1:
+        strong = strong_scaling_block(nl, dev, rank, world, group, scans[0], ms, dec, args.steps, sync_all, timed)
+
+    clk = clocks.stop() if clocks is not None else None
 
     # ---------------- aggregate over ranks (max time, sum samples) ----------------
-    t = torch.tensor([ms_total, ms_e2e, float(n_local)], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, ms_e2e, float(n_local), long_stats["ms_total"], long_stats["ms_median"], long_stats["ms_max"]], dtype=torch.float64, device=dev)
     if world > 1:
         import torch.distributed as dist
         tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         ts = t.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
         ms_total, ms_e2e, n_total = float(tm[0]), float(tm[1]), float(ts[2])
+        long_stats.update(ms_total=float(tm[3]), ms_median=float(tm[4]), ms_max=float(tm[5]), note="max over ranks")
     else:
         n_total = float(n_local)
     if world > 1:
@@ -276,26 +321,31 @@ def run_ours(args):
     flops = n_local * FLOPS_PER_SAMPLE_MAP_DEC
     ach_tf = flops / (t_mlp * 1e-3) / 1e12
     gather_gbs = n_local * BYTES_PER_SAMPLE_MAP / ((t_gf + t_gb) * 1e-3) / 1e9
+    tc = nl.engine.mlp_impl(256) == "tc"
+    traffic, traffic_src = _traffic_record("k_mlp_tc_train" if tc else "k_mlp")
+    long_stats["value_from_median"] = n_total / (long_stats["ms_median"] * 1e-3)
     out = {
         "metric": "neural-SDF samples/sec per mapping iter", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "rays_per_gpu": R, "samples_per_gpu_step": n_local, "octree_nodes": ms.n_nodes,
-                   "embedding_rows": int(ms.emb.shape[0]), "decoder": "16-256-256-1, fp32 parity (%s)" % nl.engine.mlp_impl(256), "parallelism": f"ray-sharded dp{world}, map replicated",
+                   "embedding_rows": int(ms.emb.shape[0]), "decoder": "16-256-256-1, fp32 parity (%s)" % nl.engine.mlp_impl(256),
+                   "parallelism": f"ray-sharded dp{world}, map replicated" + ("" if world == 1 else
+                                  f": the batch is a window of {world} scans (all rays), split contiguously = one scan per rank; 3 collectives per step"),
                    "l2": "per-step working set (samples x ~2.2 KB activations+features) ~1.9 GB >> 126 MB L2; no flush needed",
-                   "sampler_noise": "in-kernel counter RNG", "loss": loss_val},
+                   "sampler_noise": "in-kernel counter RNG", "loss": loss_val,
+                   "untimed_before_clock": f"{W} warm-up steps + {n_settle} settle steps (>= 100 ms)",
+                   "kernel_error_bits_over_all_steps": ctl[nl._capi.CTL_ERROR], "skipped_steps": ctl[nl._capi.CTL_SKIPPED]},
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": int(R * 20 * world), "d2h_bytes_per_step": int(160 * world),
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
+        "steady_state": long_stats,
         "roofline": {"bound": "tensor",
                      "kernel": ("tc::k_mlp_tc_train<wgrad> + tc::k_dw1_tc + tc::k_dw0_tc (+ k_mask_colsum) (tcgen05.mma kind::tf32, 3-term hi/lo split; 2 terms where "
                                 "one operand is the exact 0/1 ReLU mask)"
-                                if nl.engine.mlp_impl(256) == "tc" else "k_mlp<256,train,wgrad> + k_dw1 (fp32 CUDA-core FMA)"),
+                                if tc else "k_mlp<256,train,wgrad> + k_dw1 (fp32 CUDA-core FMA)"),
                      "achieved": ach_tf, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach_tf / pk["bf16_sustained"],
-                     "traffic": 1.67e9 if nl.engine.mlp_impl(256) == "tc" else 1.63e9,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the main decoder kernel, one ncu --set full launch "
-                                       "(profiles/r01_ncu_final.md / r01_ncu_fp32_simt.md): 1.61 GB written (h1 and dh1 panels, mask bits, "
-                                       "dsdf for the weight-gradient GEMMs) + 0.06 GB read; the two weight-gradient kernels read 0.82 + 0.84 GB",
+                     "traffic": traffic, "traffic_source": traffic_src,
                      "peak_source": pk["src"] + " dense bf16 cuBLAS (sustained).  The fp32-parity path runs on kind::tf32 (half the bf16 rate); a "
                                     "pure 3xTF32 evaluation (3 passes everywhere) could reach at most 1/6 of this peak = %.0f TFLOP/s of algorithmic "
                                     "fp32 FLOPs; two of the five GEMMs here need only 2 passes (exact 0/1 mask operand), so that figure is a "
@@ -304,10 +354,17 @@ def run_ours(args):
                      "tf32_pipe": {"issued_flops_per_sample": ISSUED_TF32_FLOPS_PER_SAMPLE,
                                    "achieved": n_local * ISSUED_TF32_FLOPS_PER_SAMPLE / (t_mlp * 1e-3) / 1e12,
                                    "peak": pk["bf16_sustained"] / 2, "unit": "TFLOP/s",
-                                   "frac": n_local * ISSUED_TF32_FLOPS_PER_SAMPLE / (t_mlp * 1e-3) / 1e12 / (pk["bf16_sustained"] / 2)},
+                                   "frac": n_local * ISSUED_TF32_FLOPS_PER_SAMPLE / (t_mlp * 1e-3) / 1e12 / (pk["bf16_sustained"] / 2),
+                                   "note": "the 'sustained' cuBLAS peak was measured power-capped at ~1380 MHz while these kernels run at ~1965 MHz; "
+                                           "the clock-independent figure is ncu's sm__pipe_tensor_cycles_active (profiles/)"},
                      "ms_per_launch": t_mlp, "algorithmic_flops_per_sample": FLOPS_PER_SAMPLE_MAP_DEC},
         "roofline_gather": {"bound": "hbm", "kernel": "k_gather_fwd + k_gather_bwd", "achieved": gather_gbs, "peak": pk["hbm"], "unit": "GB/s",
-                            "frac": gather_gbs / pk["hbm"], "ms_fwd": t_gf, "ms_bwd": t_gb, "algorithmic_bytes_per_sample": BYTES_PER_SAMPLE_MAP},
+                            "frac": gather_gbs / pk["hbm"], "ms_fwd": t_gf, "ms_bwd": t_gb, "algorithmic_bytes_per_sample": BYTES_PER_SAMPLE_MAP,
+                            "note": "ALGORITHMIC bytes (no credit for cache reuse) over the HBM copy peak: an efficiency proxy.  The single-scan "
+                                    "table (0.8 MB) is L2-resident, so the DRAM traffic of these kernels is far below this figure (ncu: "
+                                    "gpu__dram_throughput ~6 %) -- not an HBM measurement"},
+        "roofline_chain": {"bound": "hbm", "what": "whole step against the north star's HBM-gather roofline", "achieved": value / world * BYTES_PER_SAMPLE_MAP / 1e9,
+                           "peak": pk["hbm"], "unit": "GB/s", "frac": value / world * BYTES_PER_SAMPLE_MAP / 1e9 / pk["hbm"]},
         "stage_ms": {"traverse_sample": t_smp, "gather_fwd": t_gf, "mlp_fwd_bwd": t_mlp, "gather_bwd": t_gb,
                      "note": "separate pass, stages serialised on one stream; in the timed loop the weight-gradient kernels run on a "
                              "second stream concurrently with the embedding scatter (overlap_wgrad=%s)" % eng.overlap_wgrad},
@@ -317,9 +374,260 @@ def run_ours(args):
         "clocks": clk,
         "tracking": track,
     }
+    if strong is not None:
+        out["strong_scaling"] = strong
+    if world == 1 and not os.environ.get("NL_BENCH_SKIP_REFGPU"):
+        # Baseline B + the drop-in at the reference's real iteration size, after every timed region of the product
+        try:
+            syn = nl.synthetic
+            window = [syn.make_scan(seed=777 + i, sensor_xyz=(1.0 * i, 0.0, 0.0)) for i in range(5)]     # config 2: 1 m spacing along +x
+            mu_w = nl.mapping.MapUpdater(CFG["voxel_size"], init_std=0.01, seed=777, device=dev)
+            for p_, c_, T_ in window:
+                mu_w.svo.insert(torch.from_numpy(syn.voxelize(p_, T_, CFG["voxel_size"])))
+            ms_w = mu_w.update_grid_features()
+            torch.manual_seed(777)
+            dec_w = nl.lidar.Decoder(depth=2, width=256, in_dim=16, skips=[], embedder="none", multires=0).to(dev)
+            out["real_size"] = ours_real_size(nl, dev, window, ms_w, dec_w)
+            del mu_w, ms_w, dec_w
+            torch.cuda.empty_cache()
+            rg = reference_gpu(nl, dev, args.steps, scans[0], window)
+            out["reference_gpu"] = rg
+            if "full_scan_iteration" in rg:
+                rg["speedup"] = {"samples_per_s_e2e_vs_reference": e2e / rg["full_scan_iteration"]["samples_per_s"],
+                                 "traverse_sample_front_end_vs_reference_kernels": (rg["kernels"]["svo_intersect_ms"] + rg["kernels"]["inverse_cdf_sampling_ms"]) / t_smp,
+                                 "bundle_adjust_frames_5x2048x25": rg["bundle_adjust_frames_5x2048x25"]["ms_per_call"] / out["real_size"]["ms_per_call_host_selection"],
+                                 "bundle_adjust_frames_5x2048x25_device_selection": rg["bundle_adjust_frames_5x2048x25"]["ms_per_call"] / out["real_size"]["ms_per_call_device_selection"],
+                                 "track_frame_2048x25": (rg["track_frame_2048x25"]["ms_per_scan"] / track["ms_per_scan_host_selection"]) if track and "ms_per_scan" in track else None,
+                                 "track_frame_2048x25_cuda_graph": (rg["track_frame_2048x25"]["ms_per_scan"] / track["ms_per_scan_cuda_graph"]) if track and "ms_per_scan" in track else None}
+        except Exception as exc:
+            out["reference_gpu"] = {"error": repr(exc)}
     if world == 1 and not os.environ.get("NL_BENCH_SKIP_CPU"):
         out["cpu_baseline"] = best_cpu_baseline(n_rays=4096, iters=3)
     print(json.dumps(out))
+
+
+def strong_scaling_block(nl, dev, rank, world, group, scan, ms, dec, steps, sync_all, timed):
+    """ONE scan, its rays split contiguously over the ranks (dist.shard_bounds), map / decoder / pose replicated, the three
+    collectives of nerf-loam_b200/dist.py per step.  Also checks the parity gate of SURVEY 8(d): the all-reduced gradients of the
+    sharded step equal those of an unsharded (1-rank) step over the same rays."""
+    import torch.distributed as dist
+    pts, cos, pose = scan
+    h_dirs, h_gt, h_cos = host_rays(pts, cos)
+    R = h_dirs.shape[0]
+    lo, hi = nl.dist.shard_bounds(R, rank, world)
+    dirs_all, gt_all, cos_all = h_dirs.to(dev), h_gt.to(dev), h_cos.to(dev)
+    dirs, gt, cosv = dirs_all[lo:hi].contiguous(), gt_all[lo:hi].contiguous(), cos_all[lo:hi].contiguous()
+    pose6 = nl.se3pose.OptimizablePose.from_matrix(torch.from_numpy(pose)).data.detach().reshape(1, 6).to(dev).contiguous()
+    bufs = nl.engine.DecoderBuffers(dec, dev)
+    Rl = hi - lo
+    eng = nl.engine.SDFEngine(Rl, Rl * 20, dev)
+    # ---- gradient equivalence (deterministic sampling, per-ray sampler tail: the reference's tail quirk depends on a ray's position
+    #      in the batch, DESIGN.md deviation 6) ----
+    kw = dict(n_frames=1, rng_seed=0, reference_compat=False, update_decoder=True, update_emb=True, update_pose=True, pose6=pose6)
+    eng.rays_from_poses(pose6, dirs, None)
+    eng.forward_backward(ms, bufs, Rl, CFG, gt, cosv, dir_local=dirs, ray_frame=None, group=group, **kw)
+    torch.cuda.synchronize()
+    g_sh = [eng.grad_emb.clone(), bufs.gradflat.clone(), eng.pose_grad.clone()]
+    loss_sh = eng.read_stats().loss
+    eng1 = nl.engine.SDFEngine(R, R * 20, dev)
+    bufs1 = nl.engine.DecoderBuffers(dec, dev)
+    eng1.rays_from_poses(pose6, dirs_all, None)
+    eng1.forward_backward(ms, bufs1, R, CFG, gt_all, cos_all, dir_local=dirs_all, ray_frame=None, group=None, **kw)
+    torch.cuda.synchronize()
+    g_1 = [eng1.grad_emb, bufs1.gradflat, eng1.pose_grad]
+    loss_1 = eng1.read_stats().loss
+    rel = [float((a - b).abs().max() / b.abs().max().clamp_min(1e-30)) for a, b in zip(g_sh, g_1)]
+    t = torch.tensor(rel + [abs(loss_sh - loss_1) / abs(loss_1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    del eng1, bufs1
+    torch.cuda.empty_cache()
+    # ---- timing ----
+    emb = ms.emb.clone()
+    ms_s = nl.engine.MapState(ms.centres, ms.structure, ms.vox2row, emb, dev)
+    opt = {"o": None}
+
+    def step():
+        eng.rays_from_poses(pose6, dirs, None)
+        eng.forward_backward(ms_s, bufs, Rl, CFG, gt, cosv, dir_local=dirs, ray_frame=None, n_frames=1, rng_seed=12345, update_decoder=True,
+                             update_emb=True, update_pose=True, pose6=pose6, group=group, defer_wgrad=eng.overlap_wgrad)
+        if opt["o"] is None:
+            opt["o"] = nl.engine.FusedAdam([dict(param=emb, grad=eng.grad_emb, lr=LR[0])] +
+                                           [dict(param=p.data.clone(), grad=g, lr=LR[1], side=True) for p, g in zip(bufs.params, bufs.grads)] +
+                                           [dict(param=pose6[0], grad=eng.pose_grad[0], lr=LR[2])], ctl=lambda: eng.ctl)
+        opt["o"].step(side_stream=eng.deferred_stream())
+    eng.begin_call()
+    for _ in range(10):
+        step()
+    ms_t = timed(step, steps, eng.join_side)
+    n_loc = eng.read_stats().n_samples
+    tt = torch.tensor([ms_t, float(n_loc)], dtype=torch.float64, device=dev)
+    tm = tt.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ts = tt.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+    return {"scaling": "strong", "what": "ONE 82.7k-ray scan, rays split contiguously over the ranks (BASELINE.json config 5)", "rays_total": R,
+            "samples_total": float(ts[1]), "ms_per_step": float(tm[0]) / steps, "value": float(ts[1]) * steps / (float(tm[0]) * 1e-3), "unit": "samples/s",
+            "grad_equiv_max_rel": {"embedding": float(t[0]), "decoder": float(t[1]), "pose": float(t[2]), "loss": float(t[3]),
+                                   "gate": 1e-5, "note": "max |g_sharded+allreduced - g_1rank| / max |g_1rank| over all ranks; deterministic noise, "
+                                                         "reference_compat=False (per-ray sampler tail)"}}
+
+
+# ======================================================================================================
+# Baseline B (BASELINE.md section 3): the UNMODIFIED reference on the same B200 -- its eager PyTorch loop
+# (oracle/_ref/src/variations/render_helpers.py, staged byte for byte) + its own CUDA extension (oracle/_ref/grid/grid_ref.so,
+# compiled for sm_100a from the sources where they lie).  Baseline legs only; never on the product path.
+# ======================================================================================================
+class _TimedExt:
+    """Proxy for the reference's `grid` extension that brackets its two live kernels with CUDA events."""
+
+    def __init__(self, ext):
+        self._ext, self.ev = ext, {"svo_intersect": [], "inverse_cdf_sampling": []}
+
+    def _wrap(self, name):
+        fn = getattr(self._ext, name)
+
+        def call(*a):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); out = fn(*a); e1.record()
+            self.ev[name].append((e0, e1))
+            return out
+        return call
+
+    def __getattr__(self, name):
+        return self._wrap(name) if name in self.ev else getattr(self._ext, name)
+
+    def ms(self, name):
+        torch.cuda.synchronize()
+        return float(sum(a.elapsed_time(b) for a, b in self.ev[name]))
+
+
+def _ref_frame(ref, index, pts, cos, pose, all_rays=False):
+    f = ref.LidarFrame(index, torch.from_numpy(pts), torch.from_numpy(cos),
+                       ref.OptimizablePose(ref.OptimizablePose.from_matrix(torch.from_numpy(pose.copy())).data.detach().clone()), new_keyframe=True)
+    if all_rays:    # the metric excludes host ray selection (SURVEY 8 d): every point is selected, the CPU Gumbel top-k is skipped
+        f.sample_mask = torch.ones((f.num_point, 1), dtype=torch.bool)
+        f.sample_rays = lambda *a, **k: None
+    return f
+
+
+def reference_gpu(nl, dev, steps, full_scan_pts, window_scans):
+    """Times the reference's own bundle_adjust_frames / track_frame / kernels on this GPU.  full_scan_pts = (pts, cos, pose) of the
+    headline scan; window_scans = list of scans of a 5-frame keyframe window (kitti.yaml: window_size 4 + current)."""
+    from oracle import ref_harness as H
+    if not H.available():
+        return {"unavailable": "oracle/_ref (grid_ref.so + staged reference Python) not present on this box"}
+    import copy
+    ref = H.load()
+    syn = nl.synthetic
+    vs = CFG["voxel_size"]
+    crit = ref.Criterion(H.args(CFG["max_depth"], CFG["truncation"], CFG["fs_weight"], CFG["sdf_weight"]))
+    out = {"what": "unmodified reference (src/variations/render_helpers.py + voxel_helpers.py + grid CUDA extension built for sm_100a), "
+                   "same B200, same synthetic scans; wall clock between torch.cuda.synchronize() (the reference syncs the host several "
+                   "times per iteration itself)"}
+
+    def build_map(scans):
+        o = nl.svo.Octree(); o.init(256 * 256 * 4, 16, vs)          # bit-exact stand-in for the reference svo (tests/test_host_cpu.py)
+        for pts, cos, pose in scans:
+            o.insert(torch.from_numpy(syn.voxelize(pts, pose, vs)))
+        v, c, f = o.get_centres_and_children()
+        return H.reference_map_states(v, c, f, vs, init_std=0.01, seed=777, device=dev)
+
+    def decoder():
+        torch.manual_seed(777)
+        return ref.Decoder(depth=2, width=256, in_dim=16, skips=[], embedder="none", multires=0).to(dev)
+
+    def wall(fn, n):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / n * 1e3
+
+    # ---- (1) headline workload: one mapping iteration on ALL rays of the scan, decoder + embeddings + pose updated ----
+    pts, cos, pose = full_scan_pts
+    ms1 = build_map([full_scan_pts])
+    dec1 = decoder()
+    fr = _ref_frame(ref, 1, pts, cos, pose, all_rays=True)
+    R = fr.num_point
+    kw = dict(voxel_size=vs, step_size=CFG["step_size"], N_rays=R, truncation=CFG["truncation"], max_voxel_hit=20,
+              max_distance=CFG["max_distance"], learning_rate=list(LR), update_pose=True, update_decoder=True)
+    with H.pinned(ref, deterministic=False, stable_sort=False):
+        # sample count of this workload from the reference's own renderer
+        T = torch.from_numpy(pose).to(dev)
+        P = torch.from_numpy(pts).to(dev)
+        rd = ((P / (P.norm(dim=-1, keepdim=True) + 1e-8)) @ T[:3, :3].T)[None].contiguous()
+        ro = T[:3, 3].reshape(1, 1, 3).expand_as(rd).contiguous()
+        with torch.no_grad():
+            o1 = ref.orig["render_rays"](ro, rd, ms1, dec1, CFG["step_size"], vs, CFG["truncation"], 20, CFG["max_distance"], chunk_size=-1)
+        M = int(o1["valid_mask"].sum())
+        del o1
+        run1 = lambda n: ref.orig["bundle_adjust_frames"]([fr], ms1["voxel_vertex_emb"], ms1, dec1, crit, num_iterations=n, **kw)
+        run1(2)
+        n_it = max(3, min(steps, 10))
+        t_it = wall(lambda: run1(n_it), 1) / n_it
+        # kernel-only time of the reference's two CUDA kernels inside one such iteration
+        proxy = _TimedExt(ref.VH._ext)
+        ref.VH._ext = proxy
+        try:
+            with torch.no_grad():
+                ref.orig["render_rays"](ro, rd, ms1, dec1, CFG["step_size"], vs, CFG["truncation"], 20, CFG["max_distance"], chunk_size=-1)
+            k_int, k_smp = proxy.ms("svo_intersect"), proxy.ms("inverse_cdf_sampling")
+        finally:
+            ref.VH._ext = proxy._ext
+    out["full_scan_iteration"] = {"rays": R, "samples": M, "ms_per_iter": t_it, "samples_per_s": M / (t_it * 1e-3), "iterations_timed": n_it,
+                                  "note": "bundle_adjust_frames([frame], N_rays = all points), host ray selection skipped (metric definition)"}
+    out["kernels"] = {"svo_intersect_ms": k_int, "inverse_cdf_sampling_ms": k_smp,
+                      "note": "CUDA events around the reference's own kernel launches (intersect_gpu.cu:193-272, sample_gpu.cu:133-239) "
+                              "for the full scan, inputs already materialised by its wrapper (octree copies not counted)"}
+    del ms1, dec1
+    torch.cuda.empty_cache()
+
+    # ---- (2) the reference's real iteration size: 5 frames x 2048 rays, 25 iterations (configs/kitti/kitti.yaml:19-33) ----
+    msw = build_map(window_scans)
+    decw = decoder()
+    frames = [_ref_frame(ref, i, *sc) for i, sc in enumerate(window_scans)]
+    kww = dict(voxel_size=vs, step_size=CFG["step_size"], N_rays=2048, num_iterations=25, truncation=CFG["truncation"], max_voxel_hit=20,
+               max_distance=CFG["max_distance"], learning_rate=list(LR), update_pose=True, update_decoder=True)
+    with H.pinned(ref, deterministic=False, stable_sort=False):
+        ba = lambda: ref.orig["bundle_adjust_frames"](frames, msw["voxel_vertex_emb"], msw, decw, crit, **kww)
+        ba()
+        t_ba = wall(ba, 2)
+        # ---- (3) tracking: 25 iterations x 2048 rays against the same map ----
+        ft = _ref_frame(ref, 5, *window_scans[-1])
+        tk = lambda: ref.orig["track_frame"](copy.deepcopy(ft.pose), ft, msw, decw, crit, vs, N_rays=2048, step_size=0.2 * vs, num_iterations=25,
+                                             truncation=CFG["truncation"], learning_rate=0.06, max_voxel_hit=20, max_distance=CFG["max_distance"],
+                                             depth_variance=True)
+        tk()
+        t_tk = wall(tk, 3)
+    out["bundle_adjust_frames_5x2048x25"] = {"ms_per_call": t_ba, "frames": len(frames), "rays_per_frame": 2048, "iterations": 25,
+                                             "includes": "the reference's per-iteration CPU ray selection (frame.sample_rays)"}
+    out["track_frame_2048x25"] = {"ms_per_scan": t_tk}
+    return out
+
+
+def ours_real_size(nl, dev, window_scans, ms, dec):
+    """The drop-in bundle_adjust_frames / track_frame at the reference's real iteration size, same scans as reference_gpu (2)/(3)."""
+    from types import SimpleNamespace
+    import copy
+    crit = nl.criterion.Criterion(SimpleNamespace(criteria={"eiko_weight": 0.1, "sdf_weight": CFG["sdf_weight"], "fs_weight": CFG["fs_weight"],
+                                                           "sdf_truncation": CFG["truncation"]}, data_specs={"max_depth": CFG["max_depth"]}))
+    vs = CFG["voxel_size"]
+    frames = []
+    for i, (pts, cos, pose) in enumerate(window_scans):
+        frames.append(nl.frame.LidarFrame(i, torch.from_numpy(pts), torch.from_numpy(cos),
+                                          nl.se3pose.OptimizablePose.from_matrix(torch.from_numpy(pose.copy())), new_keyframe=True))
+    res = {}
+    for mode in ("host", "device"):
+        def ba():
+            nl.render_helpers.bundle_adjust_frames(frames, ms.emb, ms, dec, crit, vs, CFG["step_size"], N_rays=2048, num_iterations=25,
+                                                   truncation=CFG["truncation"], max_voxel_hit=20, max_distance=CFG["max_distance"],
+                                                   learning_rate=list(LR), update_pose=True, update_decoder=True, ray_selection=mode)
+        ba(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            ba()
+        torch.cuda.synchronize()
+        res["ms_per_call_%s_selection" % mode] = (time.perf_counter() - t0) / 3 * 1e3
+    res.update(frames=len(frames), rays_per_frame=2048, iterations=25)
+    return res
 
 
 def cpu_baseline(n_rays=4096, iters=3, threads=None):
@@ -380,21 +688,83 @@ def best_cpu_baseline(n_rays, iters):
 
 
 def run_reference(args):
+    """Reference arm.  The reference's stock code path for this metric is a GPU path (eager PyTorch + its own CUDA extension), so when
+    the staged reference (oracle/_ref: grid_ref.so built for sm_100a + its unmodified Python) and a GPU are present the line's value
+    is THAT -- Baseline B of BASELINE.md, the same workload, same B200 -- and the CPU port of the path (Baseline A, host cores) is
+    reported beside it in `cpu_baseline`.  Without them the CPU port is the value."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    n_rays = 8192
     t0 = time.perf_counter()
+    n_rays = 8192
     probe = best_cpu_baseline(n_rays=2048, iters=1)
-    cb = cpu_baseline(n_rays=n_rays, iters=max(1, args.steps), threads=probe["cores"])
-    out = {"impl": "reference", "metric": "neural-SDF samples/sec per mapping iter", "value": cb["value"], "unit": "samples/s",
-           "n_gpus": args.gpus, "steps": args.steps, "warmup": 1, "ms_per_step": cb["ms_per_iter"], "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": WORKLOAD, "note": f"reference algorithm on host cores; each step = a bounded sample of {n_rays} rays"},
-           "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
-           "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+    cb = cpu_baseline(n_rays=n_rays, iters=max(1, min(args.steps, 10)), threads=probe["cores"])
+    gpu = None
+    try:
+        from oracle import ref_harness as H
+        if torch.cuda.is_available() and H.available():
+            import nerfloam_b200 as nl          # synthetic scan generator + the (bit-exact) octree builder only
+            dev = torch.device("cuda", 0)
+            torch.cuda.set_device(dev)
+            gpu = reference_gpu_headline(nl, dev, args.steps, args.warmup)
+    except Exception as exc:
+        gpu = {"error": repr(exc)}
+    out = {"impl": "reference", "metric": "neural-SDF samples/sec per mapping iter", "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "gpu_launches": 0, "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}}
+    if gpu and "value" in gpu:
+        out.update(value=gpu["value"], ms_per_step=gpu["ms_per_step"],
+                   config={"workload": WORKLOAD, "rays_per_gpu": gpu["rays"], "samples_per_gpu_step": gpu["samples"],
+                           "note": "UNMODIFIED reference (src/variations/render_helpers.py::bundle_adjust_frames + voxel_helpers.py + grid CUDA extension "
+                                   "compiled for sm_100a) on this box's GPU 0: one mapping iteration on all rays of the same scan per step, decoder + "
+                                   "embeddings + pose updated by torch.optim.Adam; host ray selection skipped (metric definition); wall clock between "
+                                   "torch.cuda.synchronize() calls.  cpu_baseline = the oracle's CPU port of the same path on host cores"},
+                   e2e={"value": gpu["value"], "unit": "samples/s", "h2d_bytes_per_step": gpu["h2d_bytes_per_step"], "d2h_bytes_per_step": 0,
+                        "note": "the reference uploads the frame's rays / points / cosines from host memory every iteration itself"},
+                   reference_kind="reference-gpu")
+    else:
+        out.update(value=cb["value"], ms_per_step=cb["ms_per_iter"],
+                   config={"workload": WORKLOAD, "note": f"reference algorithm on host cores (oracle port); each step = a bounded sample of {n_rays} rays",
+                           "gpu_reference": gpu},
+                   e2e={"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, reference_kind="cpu-port")
+    out["wall_s"] = time.perf_counter() - t0
     print(json.dumps(out))
+
+
+def reference_gpu_headline(nl, dev, steps, warmup):
+    """The reference's own bundle_adjust_frames on ALL rays of the headline scan: `warmup` + `steps` iterations, wall clock."""
+    from oracle import ref_harness as H
+    ref = H.load()
+    syn = nl.synthetic
+    vs = CFG["voxel_size"]
+    pts, cos, pose = syn.make_scan(seed=777)
+    o = nl.svo.Octree(); o.init(256 * 256 * 4, 16, vs)
+    o.insert(torch.from_numpy(syn.voxelize(pts, pose, vs)))
+    v, c, f = o.get_centres_and_children()
+    ms1 = H.reference_map_states(v, c, f, vs, init_std=0.01, seed=777, device=dev)
+    torch.manual_seed(777)
+    dec1 = ref.Decoder(depth=2, width=256, in_dim=16, skips=[], embedder="none", multires=0).to(dev)
+    crit = ref.Criterion(H.args(CFG["max_depth"], CFG["truncation"], CFG["fs_weight"], CFG["sdf_weight"]))
+    fr = _ref_frame(ref, 1, pts, cos, pose, all_rays=True)
+    R = fr.num_point
+    kw = dict(voxel_size=vs, step_size=CFG["step_size"], N_rays=R, truncation=CFG["truncation"], max_voxel_hit=20,
+              max_distance=CFG["max_distance"], learning_rate=list(LR), update_pose=True, update_decoder=True)
+    with H.pinned(ref, deterministic=False, stable_sort=False):
+        T = torch.from_numpy(pose).to(dev)
+        P = torch.from_numpy(pts).to(dev)
+        rd = ((P / (P.norm(dim=-1, keepdim=True) + 1e-8)) @ T[:3, :3].T)[None].contiguous()
+        ro = T[:3, 3].reshape(1, 1, 3).expand_as(rd).contiguous()
+        with torch.no_grad():
+            o1 = ref.orig["render_rays"](ro, rd, ms1, dec1, CFG["step_size"], vs, CFG["truncation"], 20, CFG["max_distance"], chunk_size=-1)
+        M = int(o1["valid_mask"].sum())
+        del o1
+        run = lambda n: ref.orig["bundle_adjust_frames"]([fr], ms1["voxel_vertex_emb"], ms1, dec1, crit, num_iterations=n, **kw)
+        run(max(1, warmup))
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        run(steps)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    return {"value": M * steps / dt, "ms_per_step": dt / steps * 1e3, "rays": R, "samples": M, "h2d_bytes_per_step": int(R * (12 + 12 + 4))}
 
 
 if __name__ == "__main__":

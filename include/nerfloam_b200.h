@@ -256,6 +256,43 @@ NL_API int nl_adam_bf16(int64_t n, uint16_t *d_param, const float *d_grad_f32, u
 NL_API int nl_adam_f32_devstep(int64_t n, float *d_param, const float *d_grad, float *d_m, float *d_v, double lr, double beta1,
                         double beta2, double eps, int32_t *d_step, void *stream);
 
+
+/* ============================================================================================
+ * 8. Device-side iteration control: lets a whole optimisation call (render_helpers.py:356-423 / :452-510) run without a
+ *    host synchronisation per iteration and still behave like the reference's loop.
+ *    ctl is int32[NL_CTL_WORDS] in device memory, zeroed by the caller before the first iteration (NL_CTL_MIN_HIT = INT32_MAX).
+ * ============================================================================================ */
+#define NL_CTL_ERROR 0      /* OR of nl_render_stats.error over all iterations (bit1 capacity, bit2 stack: the call must be redone / fails) */
+#define NL_CTL_SKIPPED 1    /* iterations the reference would have skipped (render_rays returned None, render_helpers.py:405-409)        */
+#define NL_CTL_SKIP_NOW 2   /* 1 while the current iteration is such an iteration: nl_adam_*_ctl then leave everything untouched           */
+#define NL_CTL_ADAM_STEP 3  /* optimiser steps taken so far including the current one (torch.optim.Adam's `step`)                         */
+#define NL_CTL_MIN_HIT 4    /* min over iterations of n_hit_rays                                                                           */
+#define NL_CTL_ITERS 5      /* iterations seen                                                                                             */
+#define NL_CTL_MAX_SAMPLES 6 /* max over iterations of n_samples (what the sample capacity has to hold)                                    */
+#define NL_CTL_WORDS 8
+/* after an iteration's nl_render_samples (and, multi-GPU, the statistics exchange): d_ctl = fold(d_ctl_prev, d_stats).
+ * d_ctl_prev may equal d_ctl (in place); two alternating blocks let work that was deferred to a second stream (the decoder's
+ * optimiser step of the previous iteration) keep reading the block of ITS iteration */
+NL_API int nl_iter_status(const nl_render_stats *d_stats, const int32_t *d_ctl_prev, int32_t *d_ctl, void *stream);
+/* nl_adam_f32 / nl_adam_bf16 with the step count and the skip flag read from the control block */
+NL_API int nl_adam_f32_ctl(int64_t n, float *d_param, const float *d_grad, float *d_m, float *d_v, double lr, double beta1, double beta2,
+                    double eps, const int32_t *d_ctl, void *stream);
+NL_API int nl_adam_bf16_ctl(int64_t n, uint16_t *d_param, const float *d_grad_f32, uint16_t *d_m, uint16_t *d_v, double lr, double beta1,
+                     double beta2, double eps, const int32_t *d_ctl, void *stream);
+
+/* ============================================================================================
+ * 9. Multi-GPU exchange helpers (SURVEY.md 8 e): the per-iteration statistics that make the loss global are packed into ONE
+ *    f64 vector that is all-reduced with SUM (counters and sums as they are; S_max and the error bits in one slot per rank, so
+ *    that SUM transports a MAX / OR), and unpacked again.  The collective itself is the caller's (NCCL).
+ * ============================================================================================ */
+#define NL_STATS_PACK_FIXED 10   /* 6 counters, 2 pad sums, n_hit_rays, reserved */
+/* phase 0 (before backward): d_buf = f64[NL_STATS_PACK_FIXED + 2 * world], the sample statistics.
+ * phase 1 (after backward):  d_buf = f32[4], the two squared-error sums as (hi, lo) float pairs -- they travel in the header
+ *                            of the fp32 gradient buffer, so the gradients and the loss need one collective together. */
+NL_API int nl_stats_pack(const nl_render_stats *d_stats, void *d_buf, int rank, int world, int phase, void *stream);
+/* phase 0 also re-derives the loss constants (nl_loss_prepare) from the now global statistics */
+NL_API int nl_stats_unpack(nl_render_stats *d_stats, const void *d_buf, int world, int phase, float fs_weight, float sdf_weight, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

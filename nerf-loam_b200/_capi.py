@@ -95,7 +95,16 @@ _SIGNATURES = {
     "nl_adam_f32": (C.c_int, [C.c_int64, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, vp]),
     "nl_adam_f32_devstep": (C.c_int, [C.c_int64, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, C.c_double, vp, vp]),
     "nl_adam_bf16": (C.c_int, [C.c_int64, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, vp]),
+    "nl_iter_status": (C.c_int, [vp, vp, vp, vp]),
+    "nl_adam_f32_ctl": (C.c_int, [C.c_int64, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, C.c_double, vp, vp]),
+    "nl_adam_bf16_ctl": (C.c_int, [C.c_int64, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, C.c_double, vp, vp]),
+    "nl_stats_pack": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "nl_stats_unpack": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, vp]),
 }
+
+# words of the device-side iteration control block (include/nerfloam_b200.h section 8)
+CTL_ERROR, CTL_SKIPPED, CTL_SKIP_NOW, CTL_ADAM_STEP, CTL_MIN_HIT, CTL_ITERS, CTL_MAX_SAMPLES, CTL_WORDS = 0, 1, 2, 3, 4, 5, 6, 8
+STATS_PACK_FIXED = 10
 
 EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))
 

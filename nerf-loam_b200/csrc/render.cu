@@ -576,7 +576,87 @@ __global__ void k_loss_finalize(nl_render_stats *s, float fs_weight, float sdf_w
     s->loss = fs_weight * s->fs_loss + sdf_weight * s->sdf_loss;
 }
 
+// Fold one iteration's statistics into the call-wide control block (include/nerfloam_b200.h section 8).
+__global__ void k_iter_status(const nl_render_stats *s, const int32_t *prev, int32_t *ctl) {
+    for (int i = 0; i < NL_CTL_WORDS; ++i) ctl[i] = prev[i];
+    const int err = s->error;
+    const int skip = (s->n_hit_rays <= 0) || (err & 1);   // render_rays -> None (render_helpers.py:216, voxel_helpers.py:579); global values
+                                                          // after the multi-GPU exchange, so every rank decides alike
+    ctl[NL_CTL_ERROR] |= err;
+    ctl[NL_CTL_SKIPPED] += skip;
+    ctl[NL_CTL_SKIP_NOW] = skip;
+    ctl[NL_CTL_ADAM_STEP] += skip ? 0 : 1;
+    ctl[NL_CTL_MIN_HIT] = min(ctl[NL_CTL_MIN_HIT], s->n_hit_rays);
+    ctl[NL_CTL_ITERS] += 1;
+    ctl[NL_CTL_MAX_SAMPLES] = max(ctl[NL_CTL_MAX_SAMPLES], s->n_samples);
+}
+
+// Statistics exchange, packed (section 9): every value that must become global travels in one f64 vector reduced with SUM.
+__global__ void k_stats_pack(const nl_render_stats *s, void *buf_, int rank, int world, int phase) {
+    if (phase == 0) {
+        double *b = (double *)buf_;
+        const int t = threadIdx.x;
+        if (t == 0) {
+            b[0] = (double)s->cnt_fs_valid; b[1] = (double)s->cnt_sdf_valid; b[2] = (double)s->pad_fs_rays; b[3] = (double)s->pad_fs_nsamp;
+            b[4] = (double)s->pad_sdf_rays; b[5] = (double)s->pad_sdf_nsamp; b[6] = s->pad_sdf_d2; b[7] = s->pad_sdf_d2_nsamp;
+            b[8] = (double)s->n_hit_rays; b[9] = 0.0;
+        }
+        for (int r = t; r < world; r += blockDim.x) {
+            b[NL_STATS_PACK_FIXED + r] = (r == rank) ? (double)s->max_samples : 0.0;          // SUM of one-hot slots, MAX on unpack
+            b[NL_STATS_PACK_FIXED + world + r] = (r == rank) ? (double)s->error : 0.0;        // OR on unpack
+        }
+    } else if (threadIdx.x == 0) {
+        float *b = (float *)buf_;
+        const float fh = (float)s->fs_sum, sh = (float)s->sdf_sum;
+        b[0] = fh; b[1] = (float)(s->fs_sum - (double)fh); b[2] = sh; b[3] = (float)(s->sdf_sum - (double)sh);
+    }
+}
+
+__global__ void k_stats_unpack(nl_render_stats *s, const void *buf_, int world, int phase) {
+    if (phase == 0) {
+        const double *b = (const double *)buf_;
+        s->cnt_fs_valid = (long long)b[0]; s->cnt_sdf_valid = (long long)b[1]; s->pad_fs_rays = (long long)b[2]; s->pad_fs_nsamp = (long long)b[3];
+        s->pad_sdf_rays = (long long)b[4]; s->pad_sdf_nsamp = (long long)b[5]; s->pad_sdf_d2 = b[6]; s->pad_sdf_d2_nsamp = b[7];
+        s->n_hit_rays = (int32_t)b[8];
+        int smax = 0, err = 0;
+        for (int r = 0; r < world; ++r) {
+            smax = max(smax, (int)b[NL_STATS_PACK_FIXED + r]);
+            err |= (int)b[NL_STATS_PACK_FIXED + world + r];
+        }
+        s->max_samples = smax;
+        s->error = err;
+    } else {
+        const float *b = (const float *)buf_;
+        s->fs_sum = (double)b[0] + (double)b[1];
+        s->sdf_sum = (double)b[2] + (double)b[3];
+    }
+}
+
 }  // namespace
+
+extern "C" int nl_iter_status(const nl_render_stats *d_stats, const int32_t *d_ctl_prev, int32_t *d_ctl, void *stream) {
+    if (!d_stats || !d_ctl || !d_ctl_prev) return nl_set_error("nl_iter_status: null pointer");
+    k_iter_status<<<1, 1, 0, (cudaStream_t)stream>>>(d_stats, d_ctl_prev, d_ctl);
+    NL_CHECK_LAUNCH("nl_iter_status");
+    return NL_OK;
+}
+
+extern "C" int nl_stats_pack(const nl_render_stats *d_stats, void *d_buf, int rank, int world, int phase, void *stream) {
+    if (!d_stats || !d_buf) return nl_set_error("nl_stats_pack: null pointer");
+    if (world < 1 || rank < 0 || rank >= world || (phase != 0 && phase != 1)) return nl_set_error("nl_stats_pack: bad rank / world / phase");
+    k_stats_pack<<<1, 32, 0, (cudaStream_t)stream>>>(d_stats, d_buf, rank, world, phase);
+    NL_CHECK_LAUNCH("nl_stats_pack");
+    return NL_OK;
+}
+
+extern "C" int nl_stats_unpack(nl_render_stats *d_stats, const void *d_buf, int world, int phase, float fs_weight, float sdf_weight, void *stream) {
+    if (!d_stats || !d_buf) return nl_set_error("nl_stats_unpack: null pointer");
+    if (world < 1 || (phase != 0 && phase != 1)) return nl_set_error("nl_stats_unpack: bad world / phase");
+    k_stats_unpack<<<1, 1, 0, (cudaStream_t)stream>>>(d_stats, d_buf, world, phase);
+    if (phase == 0) k_loss_prepare<<<1, 1, 0, (cudaStream_t)stream>>>(d_stats, fs_weight, sdf_weight);
+    NL_CHECK_LAUNCH("nl_stats_unpack");
+    return NL_OK;
+}
 
 extern "C" int64_t nl_octree_packed_bytes(int32_t n_nodes) { return n_nodes < 0 ? -1 : (int64_t)n_nodes * 128; }
 

@@ -1,53 +1,105 @@
 """Collectives of the ray-sharded data-parallel hot path (SURVEY.md section 8 e).
 
-Rays are independent up to the loss, whose normalisation is global (criterion.py:84-100): the mean runs
-over R_hit x S_max cells and the class-balance weights use global mask counts.  So one tiny exchange
-before the backward pass (raw counters SUM, S_max MAX) and one gradient reduction after it; the octree,
-embedding table and decoder are replicated and every rank applies the identical Adam step.
-The functions work on the raw nl_render_stats byte block (any device: NCCL on GPU, gloo in the CPU tests).
+Rays are independent up to the loss, whose normalisation is global (criterion.py:84-100): the mean runs over R_hit x S_max
+cells and the class-balance weights use global mask counts.  So per iteration there are exactly
+
+  1. ONE tiny all-reduce before the backward pass: every statistic that has to become global is packed into one f64 vector
+     reduced with SUM -- counters and sums as they are; S_max (needs MAX) and the kernel error bits (need OR) in one slot per
+     rank, so that a SUM transports them (nl_stats_pack / nl_stats_unpack, include/nerfloam_b200.h section 9);
+  2. ONE all-reduce after it over a flat fp32 buffer [loss sums (hi, lo) | pose accumulators | embedding-gradient table]
+     (engine.SDFEngine.gradflat);
+  3. while the decoder is trained, ONE more over its flat gradient buffer (engine.DecoderBuffers.gradflat), issued on the
+     side stream where the weight-gradient kernels run.
+
+The octree, embedding table and decoder are replicated and every rank applies the identical Adam step.
+On CUDA tensors packing runs as the C-ABI kernels; the same layout in torch ops serves CPU tensors (the gloo tests).
 """
+import ctypes as C
+
 import torch
 import torch.distributed as dist
 
-# byte offsets inside nl_render_stats (checked against the C struct at import of _capi)
-_I32_N_HIT, _I32_MAX_SAMPLES = 0, 2          # int32 slots
-_I64_COUNTERS = slice(4, 10)                 # cnt_fs_valid .. pad_sdf_nsamp
-_F64_PAD = slice(10, 12)                     # pad_sdf_d2, pad_sdf_d2_nsamp
-_F64_LOSS_SUMS = slice(16, 18)               # fs_sum, sdf_sum
+from . import _capi
+
+# slots inside nl_render_stats (checked against the C struct at import of _capi)
+_I32_N_HIT, _I32_MAX_SAMPLES, _I32_ERROR = 0, 2, 4   # int32 slots
+_I64_COUNTERS = slice(4, 10)                         # cnt_fs_valid .. pad_sdf_nsamp
+_F64_PAD = slice(10, 12)                             # pad_sdf_d2, pad_sdf_d2_nsamp
+_F64_LOSS_SUMS = slice(16, 18)                       # fs_sum, sdf_sum
+FIXED = _capi.STATS_PACK_FIXED
 
 
-def allreduce_sample_stats(stats_u8, group=None):
-    """Make the loss-mask statistics global: counters SUM, R_hit SUM, S_max MAX.  nl_loss_prepare must be
-    re-run afterwards."""
-    i32, i64, f64 = stats_u8.view(torch.int32), stats_u8.view(torch.int64), stats_u8.view(torch.float64)
-    dist.all_reduce(i64[_I64_COUNTERS], op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(f64[_F64_PAD], op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(i32[_I32_N_HIT:_I32_N_HIT + 1], op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(i32[_I32_MAX_SAMPLES:_I32_MAX_SAMPLES + 1], op=dist.ReduceOp.MAX, group=group)
+def stats_words(world):
+    return FIXED + 2 * world
 
 
-def allreduce_loss_sums(stats_u8, group=None):
-    dist.all_reduce(stats_u8.view(torch.float64)[_F64_LOSS_SUMS], op=dist.ReduceOp.SUM, group=group)
-
-
-def allreduce_grads(tensors, group=None):
-    """Gradient reduction: embedding-gradient table [V,16] fp32, decoder grads, pose accumulators [F,12] -- all fp32, one
-    coalesced all-reduce (a single grouped NCCL launch instead of eight latency-bound ones)."""
-    ts = [t for t in tensors if t is not None]
-    if not ts:
+def pack_stats(stats_u8, buf, rank, world, phase=0):
+    """phase 0: buf f64[stats_words(world)] <- sample statistics; phase 1: buf f32[4] <- squared-error sums as (hi, lo) pairs."""
+    if stats_u8.is_cuda:
+        _capi.check(_capi.lib().nl_stats_pack(_capi.ptr(stats_u8), _capi.ptr(buf), int(rank), int(world), int(phase), _capi.stream_ptr()),
+                    "nl_stats_pack")
+        _capi.LAUNCHES += 1
         return
-    if len(ts) > 1 and all(t.dtype == ts[0].dtype for t in ts):
-        try:
-            from torch.distributed.distributed_c10d import _coalescing_manager
-            with _coalescing_manager(group=group, async_ops=False):
-                for t in ts:
-                    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-            return
-        except (ImportError, RuntimeError, ValueError, NotImplementedError):
-            from torch.distributed import distributed_c10d as _c10d
-            _c10d._world.pg_coalesce_state.pop(group or _c10d._get_default_group(), None)   # leave no half-open coalescing state
-    for t in ts:
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    i32, i64, f64 = stats_u8.view(torch.int32), stats_u8.view(torch.int64), stats_u8.view(torch.float64)
+    if phase == 0:
+        buf.zero_()
+        buf[0:6] = i64[_I64_COUNTERS].double()
+        buf[6:8] = f64[_F64_PAD]
+        buf[8] = float(i32[_I32_N_HIT])
+        buf[FIXED + rank] = float(i32[_I32_MAX_SAMPLES])
+        buf[FIXED + world + rank] = float(i32[_I32_ERROR])
+    else:
+        s = f64[_F64_LOSS_SUMS]
+        hi = s.float()
+        buf[0], buf[2] = hi[0], hi[1]
+        lo = (s - hi.double()).float()
+        buf[1], buf[3] = lo[0], lo[1]
+
+
+def unpack_stats(stats_u8, buf, world, phase=0, fs_weight=0.0, sdf_weight=0.0):
+    """Inverse of pack_stats after the SUM all-reduce; phase 0 on CUDA also re-derives the loss constants (nl_loss_prepare)."""
+    if stats_u8.is_cuda:
+        _capi.check(_capi.lib().nl_stats_unpack(_capi.ptr(stats_u8), _capi.ptr(buf), int(world), int(phase), float(fs_weight), float(sdf_weight),
+                                                _capi.stream_ptr()), "nl_stats_unpack")
+        _capi.LAUNCHES += 2 if phase == 0 else 1
+        return
+    i32, i64, f64 = stats_u8.view(torch.int32), stats_u8.view(torch.int64), stats_u8.view(torch.float64)
+    if phase == 0:
+        i64[_I64_COUNTERS] = buf[0:6].long()
+        f64[_F64_PAD] = buf[6:8]
+        i32[_I32_N_HIT] = int(buf[8])
+        i32[_I32_MAX_SAMPLES] = int(buf[FIXED:FIXED + world].max())
+        err = 0
+        for e in buf[FIXED + world:FIXED + 2 * world].tolist():
+            err |= int(e)
+        i32[_I32_ERROR] = err
+    else:
+        f64[_F64_LOSS_SUMS] = torch.stack([buf[0].double() + buf[1].double(), buf[2].double() + buf[3].double()])
+
+
+def allreduce_sample_stats(stats_u8, group=None, buf=None, fs_weight=0.0, sdf_weight=0.0):
+    """Make the loss-mask statistics global with one collective (counters SUM, R_hit SUM, S_max MAX, error bits OR)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if buf is None:
+        buf = torch.empty(stats_words(world), dtype=torch.float64, device=stats_u8.device)
+    pack_stats(stats_u8, buf, rank, world, 0)
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    unpack_stats(stats_u8, buf, world, 0, fs_weight, sdf_weight)
+    return buf
+
+
+def allreduce_flat(flat, group=None):
+    """One SUM all-reduce over a flat gradient buffer."""
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+
+
+def allreduce_grads_with_loss(stats_u8, gradflat, group=None):
+    """Post-backward exchange: the squared-error sums ride in the 4-float header of the flat fp32 gradient buffer
+    [header(16) | pose accumulators | embedding-gradient table], so loss and gradients are ONE collective."""
+    world = dist.get_world_size(group)
+    pack_stats(stats_u8, gradflat[:4], 0, world, 1)
+    dist.all_reduce(gradflat, op=dist.ReduceOp.SUM, group=group)
+    unpack_stats(stats_u8, gradflat[:4], world, 1)
 
 
 def shard_bounds(n, rank, world):

@@ -111,16 +111,35 @@ class MapState:
             self._packed = pack_children(self.centres, self.structure)
         return self._packed
 
+    @staticmethod
+    def _fingerprint(map_states):
+        """Content fingerprint of the structural part of a reference map_states dict.  The dict is rebuilt (and, in the tracker
+        process, freshly unpickled) for every frame, so tensor identity / _version say nothing: a freed tensor's address is
+        readily reused and an update that only turns FEATURE leaves into SURFACE leaves keeps every shape.  CRC-32 of the three
+        structural tensors costs ~25 ms per 10^6 nodes on the host (they are CPU tensors in the reference), against a full
+        re-composition through the id table + upload + re-packing."""
+        import zlib
+        vidx = map_states["voxel_vertex_idx"].detach()
+        n = int(vidx.shape[0])
+
+        def h(t, dtype):
+            a = t.detach().to(device="cpu", dtype=dtype).contiguous().numpy()
+            return zlib.crc32(memoryview(a).cast("B"))
+        return (n, h(vidx, torch.int32), h(map_states["voxel_structure"], torch.int32), h(map_states["voxel_center_xyz"], torch.float32),
+                int(map_states["voxel_id2embedding_id"].shape[0]))
+
     @classmethod
     def from_map_states(cls, map_states, device="cuda"):
-        """map_states: the reference dict.  vox2row is cached on the identity/version of the index tensors."""
-        vidx = map_states["voxel_vertex_idx"]
-        id2 = map_states["voxel_id2embedding_id"]
-        key = (vidx.data_ptr(), vidx._version, tuple(vidx.shape), id2.data_ptr(), id2._version)
-        hit = cls._cache.get("key") == key
-        if not hit:
-            v = vidx.detach().cpu().long()
-            flat = id2.detach().cpu().reshape(-1)
+        """map_states: the reference dict (mapping.py:328-337).  A dict produced by mapping.MapUpdater carries the finished
+        MapState ("_mapstate") and is used as is; for the reference's own dict the derived arrays (voxel -> row table, device
+        copies, packed traversal image) are cached on a content fingerprint of its index tensors."""
+        own = map_states.get("_mapstate")
+        if isinstance(own, MapState) and own.centres.device == torch.device(device):
+            return own
+        key = cls._fingerprint(map_states)
+        if cls._cache.get("key") != key:
+            v = map_states["voxel_vertex_idx"].detach().cpu().long()
+            flat = map_states["voxel_id2embedding_id"].detach().cpu().reshape(-1)
             rows = torch.where(v >= 0, flat[v.clamp(min=0)].long(), torch.full_like(v, -1))
             cls._cache = {"key": key, "vox2row": rows.to(torch.int32).to(device).contiguous(),
                           "centres": map_states["voxel_center_xyz"].detach().to(device=device, dtype=torch.float32).contiguous(),
@@ -131,7 +150,7 @@ class MapState:
         obj.centres, obj.structure, obj.vox2row = c["centres"], c["structure"], c["vox2row"]
         obj._packed = c["packed"]
         emb = map_states["voxel_vertex_emb"]
-        obj.emb = emb if (emb.is_cuda and emb.dtype == torch.bfloat16 and emb.is_contiguous()) else \
+        obj.emb = emb.detach() if (emb.is_cuda and emb.dtype == torch.bfloat16 and emb.is_contiguous()) else \
             emb.detach().to(device=device, dtype=torch.bfloat16).contiguous()
         obj.n_nodes = obj.centres.shape[0]
         return obj
@@ -154,7 +173,13 @@ class DecoderBuffers:
         self.width = W
         self.W0t = torch.empty((16, W), device=device, dtype=torch.float32)
         self.W1t = torch.empty((W, W), device=device, dtype=torch.float32)
-        self.grads = [torch.zeros_like(p) for p in self.params]
+        # fp32 gradient accumulators as views into ONE flat buffer: a single zero-fill and, multi-GPU, a single all-reduce per iteration
+        offs, n = [], 0
+        for p in self.params:
+            offs.append(n)
+            n += (p.numel() + 63) // 64 * 64
+        self.gradflat = torch.zeros(n, dtype=torch.float32, device=device)
+        self.grads = [self.gradflat[o:o + p.numel()].view(p.shape) for o, p in zip(offs, self.params)]
         self.tc_panels = None
         if mlp_impl(W) == "tc":
             self.tc_panels = torch.empty(int(_capi.lib().nl_mlp_tc_panel_bytes()), dtype=torch.uint8, device=device)
@@ -207,10 +232,25 @@ class SDFEngine:
         self.act = None
         self._act_key = None
         self.want_decoder_grads = want_decoder_grads
+        # fp32 gradient accumulators as views into ONE flat buffer [header(16) | pose_acc F*12 (padded) | grad_emb V*16]: one zero-fill per
+        # iteration and, multi-GPU, one all-reduce that also carries the loss sums in the header (dist.allreduce_grads_with_loss)
+        self.gradflat = None
+        self._gradflat_key = None
         self.grad_emb = None          # fp32 [V,16]
         self.pose_acc = None          # fp32 [F,12]
         self.Rt12 = None
         self.pose_grad = None
+        # device-side iteration control block (include/nerfloam_b200.h section 8): sticky error bits, skipped-iteration bookkeeping,
+        # Adam's step count -- what lets a whole optimisation call run without a host synchronisation per iteration
+        # Two alternating blocks: the decoder's Adam of iteration i may still be running on the side stream while iteration i+1 folds
+        # its statistics, so iteration i+1 writes the other block (nl_iter_status copies forward).
+        self._ctl2 = torch.zeros((2, _capi.CTL_WORDS), dtype=torch.int32, device=d)
+        self._ctl_idx = 0
+        self._ctl_init = torch.zeros(_capi.CTL_WORDS, dtype=torch.int32, device=d)
+        self._ctl_init[_capi.CTL_MIN_HIT] = 2 ** 31 - 1
+        self._ctl2[0].copy_(self._ctl_init)
+        self._ctl_host = torch.empty(_capi.CTL_WORDS, dtype=torch.int32).pin_memory() if torch.cuda.is_available() else None
+        self._xbuf = None             # packed statistics vector of the multi-GPU exchange
         self._stats_host = torch.empty(STATS_BYTES, dtype=torch.uint8).pin_memory() if torch.cuda.is_available() else None
         self.events = None            # set to {} to record CUDA events around the main kernels (bench.py)
         # the weight-gradient kernels of the decoder run on a second stream, concurrently with the embedding scatter
@@ -240,6 +280,42 @@ class SDFEngine:
         self._stats_host.copy_(self.stats, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return RenderStats.from_buffer_copy(self._stats_host.numpy().tobytes())
+
+    @property
+    def ctl(self):
+        """The control block of the current iteration (int32[CTL_WORDS] view)."""
+        return self._ctl2[self._ctl_idx]
+
+    def begin_call(self):
+        """Reset the iteration control block (start of a bundle_adjust_frames / track_frame call)."""
+        self.join_side()
+        self.ctl.copy_(self._ctl_init)
+
+    def _iter_status(self, alternate):
+        prev = self.ctl
+        if alternate:
+            self._ctl_idx ^= 1
+        _capi.check(_capi.lib().nl_iter_status(C.c_void_p(self.stats.data_ptr()), _capi.ptr(prev), _capi.ptr(self.ctl), _capi.stream_ptr()),
+                    "nl_iter_status")
+        _capi.LAUNCHES += 1
+
+    def read_ctl(self):
+        """Device -> host copy of the control block (synchronises the stream): list of CTL_WORDS ints."""
+        self._ctl_host.copy_(self.ctl, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self._ctl_host.tolist()
+
+    def _ensure_grads(self, V, n_frames):
+        key = (int(V), int(n_frames))
+        if self._gradflat_key != key:
+            npose = (n_frames * 12 + 15) // 16 * 16
+            self.gradflat = torch.zeros(16 + npose + V * 16, dtype=torch.float32, device=self.device)
+            self.pose_acc = self.gradflat[16:16 + n_frames * 12].view(n_frames, 12)
+            self.grad_emb = self.gradflat[16 + npose:].view(V, 16)
+            self.pose_grad = torch.zeros((n_frames, 6), dtype=torch.float32, device=self.device)
+            self._gradflat_key = key
+            return True
+        return False
 
     def _ensure_act(self, width):
         key = (width, mlp_impl(width))
@@ -341,12 +417,10 @@ class SDFEngine:
             self._flip_buffers()     # the deferred kernels still read the previous iteration's sample count and features
         self._mark("t0")
         self.render_samples(m, R, cfg, ray_o, ray_d, gt_depth, cos, noise, rng_seed, reference_compat, rng_seed_dev)
-        if group is not None:   # the loss normalisation is global (criterion.py:84-100): one tiny exchange before backward
+        if group is not None:   # the loss normalisation is global (criterion.py:84-100): ONE tiny exchange before backward
             from . import dist as nldist
-            nldist.allreduce_sample_stats(self.stats, group)
-            _capi.check(lib.nl_loss_prepare(C.c_void_p(self.stats.data_ptr()), float(cfg["fs_weight"]), float(cfg["sdf_weight"]), st),
-                        "nl_loss_prepare")
-            _capi.LAUNCHES += 1
+            self._xbuf = nldist.allreduce_sample_stats(self.stats, group, self._xbuf, cfg["fs_weight"], cfg["sdf_weight"])
+        self._iter_status(alternate=defer_wgrad)      # captured CUDA graphs (tracking) keep one block: fixed pointers
         self._mark("t_samples")
         self.gather_forward(m)
         self.join_side()             # decoder weights (and gradient buffers) of the previous iteration are final from here on
@@ -355,8 +429,7 @@ class SDFEngine:
         self._mark("t_gather_fwd")
         if update_decoder:
             self._ensure_act(dec.width)
-            for g in dec.grads:
-                g.zero_()
+            dec.gradflat.zero_()
         side = None
         if update_decoder and self.overlap_wgrad and mlp_impl(dec.width) == "tc":
             if self._side is None:
@@ -366,18 +439,10 @@ class SDFEngine:
                   s_flag=self.s_flag, s_depth=self.s_depth, s_ray=self.s_ray, cos=cos, gt_depth=gt_depth,
                   stats_ptr=C.c_void_p(self.stats.data_ptr()), truncation=cfg["truncation"], wgrad_stream=side)
         self._mark("t_mlp")
-        if update_emb:
-            if self.grad_emb is None or self.grad_emb.shape[0] != m.emb.shape[0]:
-                self.grad_emb = torch.zeros((m.emb.shape[0], 16), dtype=torch.float32, device=self.device)
-            else:
-                self.grad_emb.zero_()
         want_pose = update_pose and dir_local is not None
-        if want_pose:
-            if self.pose_acc is None or self.pose_acc.shape[0] != n_frames:
-                self.pose_acc = torch.zeros((n_frames, 12), dtype=torch.float32, device=self.device)
-                self.pose_grad = torch.zeros((n_frames, 6), dtype=torch.float32, device=self.device)
-            else:
-                self.pose_acc.zero_()
+        if update_emb or want_pose:
+            if not self._ensure_grads(m.emb.shape[0] if update_emb else 0, n_frames):
+                self.gradflat.zero_()
         if update_emb or want_pose:
             _capi.check(lib.nl_gather_trilinear_bwd(
                 self.max_samples, self.n_samples_dev, _capi.ptr(self.s_xyz), _capi.ptr(self.s_vox), _capi.ptr(m.centres),
@@ -392,12 +457,12 @@ class SDFEngine:
         self._mark("t_gather_bwd")
         if group is not None:
             from . import dist as nldist
-            nldist.allreduce_loss_sums(self.stats, group)
-            nldist.allreduce_grads([self.grad_emb if update_emb else None] + (list(dec.grads) if (update_decoder and not defer) else []) +
-                                   [self.pose_acc if want_pose else None], group)
-            if defer:                # the decoder's gradients are reduced where they are produced
-                with torch.cuda.stream(side):
-                    nldist.allreduce_grads(list(dec.grads), group)
+            if self.gradflat is None:
+                self._ensure_grads(0, n_frames)
+            nldist.allreduce_grads_with_loss(self.stats, self.gradflat, group)     # loss sums + pose accumulators + embedding gradients
+            if update_decoder:       # the decoder's gradients are reduced where they are produced
+                with (torch.cuda.stream(side) if defer else contextlib.nullcontext()):
+                    nldist.allreduce_flat(dec.gradflat, group)
         if defer:
             self._pending = True
         if want_pose:
@@ -411,12 +476,16 @@ class SDFEngine:
 
 class FusedAdam:
     """torch.optim.Adam semantics (fresh state per construction, like render_helpers.py:353 / :448) with one
-    fused kernel per tensor.  groups: list of dict(param=tensor, grad=tensor(fp32), lr=float)."""
+    fused kernel per tensor.  groups: list of dict(param=tensor, grad=tensor(fp32), lr=float).
+    ctl: the engine's device-side iteration control block (SDFEngine.ctl, or a callable returning the current one).  With it the step count lives on the device and an
+    iteration the reference would have skipped (no hits: `continue` before optim.step(), render_helpers.py:405-409) leaves
+    parameters, moments and the step count untouched -- without a host synchronisation."""
 
-    def __init__(self, groups, betas=(0.9, 0.999), eps=1e-8):
+    def __init__(self, groups, betas=(0.9, 0.999), eps=1e-8, ctl=None):
         self.groups = groups
         self.betas, self.eps = betas, eps
         self.step_count = 0
+        self.ctl = ctl
         for g in groups:
             p = g["param"]
             g["m"] = torch.zeros_like(p)
@@ -433,7 +502,13 @@ class FusedAdam:
                 st = _capi.stream_ptr()
                 for g in gs:
                     p = g["param"]
-                    fn = lib.nl_adam_bf16 if p.dtype == torch.bfloat16 else lib.nl_adam_f32
+                    bf = p.dtype == torch.bfloat16
+                    if self.ctl is not None:
+                        fn = lib.nl_adam_bf16_ctl if bf else lib.nl_adam_f32_ctl
+                        last = _capi.ptr(self.ctl() if callable(self.ctl) else self.ctl)
+                    else:
+                        fn = lib.nl_adam_bf16 if bf else lib.nl_adam_f32
+                        last = self.step_count
                     _capi.check(fn(p.numel(), _capi.ptr(p), _capi.ptr(g["grad"]), _capi.ptr(g["m"]), _capi.ptr(g["v"]), float(g["lr"]),
-                                   self.betas[0], self.betas[1], self.eps, self.step_count, st), "nl_adam")
+                                   self.betas[0], self.betas[1], self.eps, last, st), "nl_adam")
                     _capi.LAUNCHES += 1

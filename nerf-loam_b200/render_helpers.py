@@ -21,6 +21,10 @@ from . import _capi
 from .engine import DecoderBuffers, FusedAdam, MapState, SDFEngine, alloc_act, mlp_forward, mlp_train
 
 MAX_DEPTH = 80.0
+# initial sample capacity per ray of the fused loops (measured averages: ~10.5 mapping, ~19 tracking on the KITTI-shape scan); a call
+# that exceeds it is undone and redone with a larger engine (bundle_adjust_frames / track_frame below), never silently truncated
+SAMPLES_PER_RAY_MAP = 40
+SAMPLES_PER_RAY_TRACK = 64
 
 _ENGINES = {}
 
@@ -43,9 +47,12 @@ def _seed_from_torch():
 
 
 def _cfg(step_size, voxel_size, max_distance, crit=None):
+    """Kernel configuration.  `crit` is duck-typed on the attributes src/criterion.py:7-14 sets (truncation, fs_weight,
+    sdf_weight, max_dpeth (sic)), so the reference's own Criterion instance works as well as nerfloam_b200's."""
     c = dict(step_size=float(step_size), voxel_size=float(voxel_size), max_distance=float(max_distance))
     if crit is not None:
-        c.update(crit.kernel_config())
+        c.update(truncation=float(crit.truncation), max_depth=float(crit.max_dpeth), fs_weight=float(crit.fs_weight),
+                 sdf_weight=float(crit.sdf_weight))
     return c
 
 
@@ -56,6 +63,8 @@ def _run_with_capacity(fn, n_rays, device, samples_per_ray=40):
         eng = _engine(n_rays, cap, device)
         fn(eng)
         st = eng.read_stats()
+        if st.error & 4:
+            _check_ctl([4], "render_rays")
         if st.error & 2:
             cap = max(cap * 2, st.n_samples + 1)
             continue
@@ -221,12 +230,28 @@ class _FrameBatch:
         return torch.cat(d).contiguous(), torch.cat(g).contiguous(), torch.cat(c).contiguous(), torch.cat(fid).contiguous()
 
 
+def _check_ctl(ctl, what):
+    """Kernel error bits accumulated over a whole call (include/nerfloam_b200.h section 8).  Bit 2 (traversal stack) cannot be
+    repaired by retrying; bit 1 (sample capacity) is handled by the callers (restore + redo with a larger engine)."""
+    if ctl[_capi.CTL_ERROR] & 4:
+        raise _capi.NerfLoamError(f"{what}: octree traversal stack overflow (octree deeper than the 18 levels of octree.cpp:39?)")
+
+
+def _grown_capacity(cap, ctl):
+    return max(2 * cap, int(ctl[_capi.CTL_MAX_SAMPLES] * 1.25) + 1024)
+
+
 def bundle_adjust_frames(keyframe_graph, embeddings, map_states, sdf_network, loss_criteria, voxel_size, step_size,
                          N_rays=512, num_iterations=10, truncation=0.1, max_voxel_hit=10, max_distance=10,
                          learning_rate=[1e-2, 1e-2, 5e-3], update_pose=True, update_decoder=True, profiler=None,
                          deterministic=False, noise_per_iter=None, loss_log=None, ray_selection="host"):
     """render_helpers.py:321-425.  Mutates `embeddings` (bf16 CUDA table), the decoder parameters and the
-    frame poses in place, like the reference.  Returns None.  ray_selection: see _FrameBatch.select."""
+    frame poses in place, like the reference.  Returns None.  ray_selection: see _FrameBatch.select.
+
+    No host synchronisation per iteration: kernel error bits, "nothing was hit" iterations (which the reference skips,
+    :405-409) and Adam's step count are tracked in a device-side control block that the Adam kernels read; the host looks at it
+    once at the end of the call.  If the sample capacity was exceeded in any iteration the parameters and the RNG state are
+    restored and the whole call is redone with a larger engine, so a truncated sample set never reaches the parameters."""
     if ray_selection not in ("host", "device"):
         raise ValueError("ray_selection must be 'host' or 'device'")
     dev = embeddings.device
@@ -242,42 +267,66 @@ def bundle_adjust_frames(keyframe_graph, embeddings, map_states, sdf_network, lo
     cfg = _cfg(step_size, voxel_size, max_distance, loss_criteria)
     bufs = DecoderBuffers(sdf_network, dev)
     R = N_rays * F
-    eng = _engine(R, R * 40, dev)
     batch = _FrameBatch(frames, dev)
     pose6 = torch.stack([f.pose.data.detach().float().cpu() for f in frames]).to(dev).contiguous()
     pose_opt = [(f.index != 0 and update_pose) for f in frames]   # render_helpers.py:346-351
     for f, po in zip(frames, pose_opt):
         if po:
             f.pose.requires_grad_(True)
-    groups = [dict(param=emb, grad=None, lr=learning_rate[0])]
-    if update_decoder:
-        groups += [dict(param=p.data, grad=g, lr=learning_rate[1], side=True) for p, g in zip(bufs.params, bufs.grads)]
     # decoder weight gradients + the decoder's Adam stay on the engine's side stream and are joined right before the next
     # iteration's decoder (engine.SDFEngine.forward_backward, defer_wgrad): same arithmetic, shorter critical path
     pipeline = update_decoder and os.environ.get("NL_PIPELINE", "1") != "0"
     pose_rows = [i for i, po in enumerate(pose_opt) if po]
     pose_params = [pose6[i] for i in pose_rows]                    # views into pose6 (contiguous rows)
-    opt = None
-    for it in range(num_iterations):
-        dirs, gt, cos, fid = batch.select(N_rays, dev, mode=ray_selection)
-        eng.rays_from_poses(pose6, dirs, fid)
-        noise = noise_per_iter[it] if noise_per_iter is not None else None
-        seed = 0 if (deterministic or noise is not None) else _seed_from_torch()
-        eng.forward_backward(m, bufs, dirs.shape[0], cfg, gt, cos, dir_local=dirs, ray_frame=fid, n_frames=F, noise=noise,
-                             rng_seed=seed, update_decoder=update_decoder, update_emb=True, update_pose=any(pose_opt), pose6=pose6,
-                             defer_wgrad=pipeline)
-        if opt is None:
-            groups[0]["grad"] = eng.grad_emb
-            pg = [dict(param=pose_params[k], grad=eng.pose_grad[i], lr=learning_rate[2]) for k, i in enumerate(pose_rows)]
-            opt = FusedAdam(groups + pg)
-        st = eng.read_stats() if (loss_log is not None) else None
-        if st is not None:
-            if st.n_hit_rays <= 0 or (st.error & 1):
-                print("Encouter a bug while Mapping, currently not be fixed, Continue!!")  # render_helpers.py:407-409
-                continue
-            loss_log.append(st.loss)
-        opt.step(side_stream=eng.deferred_stream())
-    eng.join_side()
+
+    def run(eng):
+        eng.begin_call()
+        groups = [dict(param=emb, grad=None, lr=learning_rate[0])]
+        if update_decoder:
+            groups += [dict(param=p.data, grad=g, lr=learning_rate[1], side=True) for p, g in zip(bufs.params, bufs.grads)]
+        opt = None
+        for it in range(num_iterations):
+            dirs, gt, cos, fid = batch.select(N_rays, dev, mode=ray_selection)
+            eng.rays_from_poses(pose6, dirs, fid)
+            noise = noise_per_iter[it] if noise_per_iter is not None else None
+            seed = 0 if (deterministic or noise is not None) else _seed_from_torch()
+            eng.forward_backward(m, bufs, dirs.shape[0], cfg, gt, cos, dir_local=dirs, ray_frame=fid, n_frames=F, noise=noise,
+                                 rng_seed=seed, update_decoder=update_decoder, update_emb=True, update_pose=any(pose_opt), pose6=pose6,
+                                 defer_wgrad=pipeline)
+            if opt is None:
+                groups[0]["grad"] = eng.grad_emb
+                pg = [dict(param=pose_params[k], grad=eng.pose_grad[i], lr=learning_rate[2]) for k, i in enumerate(pose_rows)]
+                opt = FusedAdam(groups + pg, ctl=lambda: eng.ctl)
+            if loss_log is not None:                    # diagnostic path: one read-back per iteration
+                st = eng.read_stats()
+                if not (st.n_hit_rays <= 0 or (st.error & 1)):
+                    loss_log.append(st.loss)
+            opt.step(side_stream=eng.deferred_stream())
+        eng.join_side()
+        return eng.read_ctl()
+
+    cap = R * SAMPLES_PER_RAY_MAP
+    while True:
+        eng = _engine(R, cap, dev)
+        snap = (emb.clone(), [p.data.clone() for p in bufs.params] if update_decoder else None, pose6.clone(),
+                torch.get_rng_state(), torch.cuda.get_rng_state(dev))
+        n_log = len(loss_log) if loss_log is not None else 0
+        ctl = run(eng)
+        _check_ctl(ctl, "bundle_adjust_frames")
+        if not (ctl[_capi.CTL_ERROR] & 2):
+            break
+        # sample capacity exceeded somewhere in the call: undo it and redo it with room for the largest iteration seen
+        with torch.no_grad():
+            emb.copy_(snap[0]); pose6.copy_(snap[2])
+            if snap[1] is not None:
+                for p, q in zip(bufs.params, snap[1]):
+                    p.data.copy_(q)
+        torch.set_rng_state(snap[3]); torch.cuda.set_rng_state(snap[4], dev)
+        if loss_log is not None:
+            del loss_log[n_log:]
+        cap = _grown_capacity(cap, ctl)
+    for _ in range(ctl[_capi.CTL_SKIPPED]):
+        print("Encouter a bug while Mapping, currently not be fixed, Continue!!")  # render_helpers.py:407-409 (the step was skipped)
     with torch.no_grad():
         host = pose6.cpu()
         for i, f in enumerate(frames):
@@ -292,11 +341,11 @@ class _TrackGraph:
 
     _cache = {}
 
-    def __init__(self, key, m, sdf_network, cfg, N_rays, lr, deterministic, cap):
+    def __init__(self, key, m, sdf_network, cfg, N_rays, lr, deterministic, cap, samples_per_ray=64):
         dev = m.centres.device
         # a private engine: the shared ones may re-allocate buffers (pose accumulators, scratch) between scans, which would leave
         # the captured graph with dangling pointers
-        eng = SDFEngine(N_rays, N_rays * 64, dev)
+        eng = SDFEngine(N_rays, N_rays * samples_per_ray, dev)
         bufs = DecoderBuffers(sdf_network, dev)
         self.key, self.eng, self.cap, self.N = key, eng, cap, N_rays
         self.m, self.bufs, self.packed = m, bufs, m.packed_children()   # keep the captured tensors alive
@@ -307,10 +356,7 @@ class _TrackGraph:
         self.arange = torch.arange(cap, device=dev)
         self.pose6 = torch.zeros((1, 6), device=dev)
         self.seed_dev = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.min_hits = torch.zeros(1, dtype=torch.int32, device=dev)
         self.adam_m, self.adam_v = torch.zeros(6, device=dev), torch.zeros(6, device=dev)
-        stats_i32 = eng.stats.view(torch.int32)
         lib = _capi.lib()
 
         def body():
@@ -321,10 +367,11 @@ class _TrackGraph:
             eng.forward_backward(m, bufs, N_rays, cfg, gt, cos, dir_local=dirs, ray_frame=None, n_frames=1, update_decoder=False,
                                  update_emb=False, update_pose=True, pose6=self.pose6, refresh_weights=False,
                                  rng_seed_dev=None if deterministic else self.seed_dev)
-            torch.minimum(self.min_hits, stats_i32[0:1], out=self.min_hits)      # n_hit_rays is the first field of nl_render_stats
-            _capi.check(lib.nl_adam_f32_devstep(6, _capi.ptr(self.pose6), _capi.ptr(eng.pose_grad), _capi.ptr(self.adam_m),
-                                                _capi.ptr(self.adam_v), float(lr), 0.9, 0.999, 1e-8, _capi.ptr(self.step_dev),
-                                                _capi.stream_ptr()), "nl_adam_f32_devstep")
+            # Adam's step count, the "nothing hit" skip and the sticky error bits live in the engine's control block (one fixed
+            # block: forward_backward folds this iteration's statistics into it in place)
+            _capi.check(lib.nl_adam_f32_ctl(6, _capi.ptr(self.pose6), _capi.ptr(eng.pose_grad), _capi.ptr(self.adam_m),
+                                            _capi.ptr(self.adam_v), float(lr), 0.9, 0.999, 1e-8, _capi.ptr(eng.ctl),
+                                            _capi.stream_ptr()), "nl_adam_f32_ctl")
             self.seed_dev.add_(0x3779B1)
 
         # one throw-away eager iteration on a side stream (allocations, one-time kernel attributes), then the capture
@@ -339,18 +386,18 @@ class _TrackGraph:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             body()
-        self.launches_per_iter = _capi.LAUNCHES - l0 + 2
+        self.launches_per_iter = _capi.LAUNCHES - l0 + 1
 
     @classmethod
-    def get(cls, m, sdf_network, cfg, N_rays, lr, deterministic, n_points):
+    def get(cls, m, sdf_network, cfg, N_rays, lr, deterministic, n_points, samples_per_ray=64):
         cap = max(1 << 17, 1 << (int(n_points) - 1).bit_length())
-        key = (N_rays, float(lr), bool(deterministic), cap, m.centres.data_ptr(), m.structure.data_ptr(), m.vox2row.data_ptr(),
+        key = (N_rays, float(lr), bool(deterministic), cap, int(samples_per_ray), m.centres.data_ptr(), m.structure.data_ptr(), m.vox2row.data_ptr(),
                m.packed_children().data_ptr(), m.emb.data_ptr(), m.n_nodes, int(m.emb.shape[0]),
                tuple(p.data_ptr() for p in _decoder_params(sdf_network)), tuple(sorted(cfg.items())))
         g = cls._cache.get("g")
         if g is None or g.key != key:
             cls._cache = {}                                     # one live graph: a new map / decoder version replaces it
-            g = cls(key, m, sdf_network, cfg, N_rays, lr, deterministic, cap)
+            g = cls(key, m, sdf_network, cfg, N_rays, lr, deterministic, cap, samples_per_ray)
             cls._cache = {"g": g}
         return g
 
@@ -366,13 +413,12 @@ class _TrackGraph:
         self.n_dev.fill_(n)
         self.pose6.copy_(pose6_init)
         self.seed_dev.fill_(seed if seed < 2 ** 31 else seed - 2 ** 32)
-        self.step_dev.zero_(); self.adam_m.zero_(); self.adam_v.zero_()
-        self.min_hits.fill_(2 ** 30)
+        self.adam_m.zero_(); self.adam_v.zero_()
+        self.eng.begin_call()
         for _ in range(num_iterations):
             self.graph.replay()
         _capi.LAUNCHES += self.launches_per_iter * num_iterations
-        st = self.eng.read_stats()
-        return st, int(self.min_hits.item())
+        return self.eng.read_stats(), self.eng.read_ctl()
 
 
 def _track_frame_graph(frame_pose, curr_frame, map_states, sdf_network, loss_criteria, voxel_size, N_rays, step_size, num_iterations,
@@ -386,13 +432,19 @@ def _track_frame_graph(frame_pose, curr_frame, map_states, sdf_network, loss_cri
     n_points = curr_frame.points.shape[0]
     if n_points < N_rays:
         raise ValueError("cuda_graph=True needs at least N_rays points in the scan")
-    g = _TrackGraph.get(m, sdf_network, cfg, N_rays, lr, deterministic, n_points)
-    eng = g.eng
     seed = 0 if deterministic else _seed_from_torch()
-    st, min_hits = g.run(curr_frame, init_pose.data.detach().reshape(1, 6), num_iterations, seed)
+    spr = SAMPLES_PER_RAY_TRACK
+    while True:
+        g = _TrackGraph.get(m, sdf_network, cfg, N_rays, lr, deterministic, n_points, spr)
+        eng = g.eng
+        st, ctl = g.run(curr_frame, init_pose.data.detach().reshape(1, 6), num_iterations, seed)
+        _check_ctl(ctl, "track_frame")
+        if not (ctl[_capi.CTL_ERROR] & 2):
+            break
+        spr = -(-_grown_capacity(N_rays * spr, ctl) // N_rays)       # sample capacity exceeded: re-capture with a larger engine, redo the scan
     with torch.no_grad():
         init_pose.data.copy_(g.pose6.reshape(init_pose.data.shape))
-    if min_hits <= 0 or (st.error & 1) or st.n_samples == 0:
+    if ctl[_capi.CTL_SKIPPED] > 0 or st.n_samples == 0:
         print("Encouter a bug while Tracking, currently not be fixed, Restarting!!")  # render_helpers.py:488-491
         return init_pose, None
     return init_pose, (eng.hit_rank[:N_rays] >= 0).clone()
@@ -423,7 +475,9 @@ def track_frame(frame_pose, curr_frame, map_states, sdf_network, loss_criteria, 
     init_pose.requires_grad_(True)
     pose6 = init_pose.data.detach().reshape(1, 6).contiguous()     # shares storage with the parameter
     lr = learning_rate * 2 if curr_frame.index < 2 else learning_rate / 3   # render_helpers.py:448-450
-    eng = _engine(N_rays, N_rays * 64, dev)
+    cap = N_rays * SAMPLES_PER_RAY_TRACK
+    eng = _engine(N_rays, cap, dev)
+    eng.begin_call()
     batch = _FrameBatch([curr_frame], dev)
     opt = None
     hit_mask = None
@@ -431,13 +485,23 @@ def track_frame(frame_pose, curr_frame, map_states, sdf_network, loss_criteria, 
     bufs.refresh_transposes()           # the decoder is frozen while tracking: derive the kernel-side weight images once
     for it in range(num_iterations):
         dirs, gt, cos, fid = batch.select(N_rays, dev, track=True, mode=ray_selection)
-        eng.rays_from_poses(pose6, dirs, None)
         noise = noise_per_iter[it] if noise_per_iter is not None else None
         seed = 0 if (deterministic or noise is not None) else _seed_from_torch()
-        eng.forward_backward(m, bufs, dirs.shape[0], cfg, gt, cos, dir_local=dirs, ray_frame=None, n_frames=1, noise=noise,
-                             rng_seed=seed, update_decoder=False, update_emb=False, update_pose=True, pose6=pose6,
-                             refresh_weights=False)
-        st = eng.read_stats()   # the reference syncs here too (hit_mask, None checks)
+        while True:
+            eng.rays_from_poses(pose6, dirs, None)
+            eng.forward_backward(m, bufs, dirs.shape[0], cfg, gt, cos, dir_local=dirs, ray_frame=None, n_frames=1, noise=noise,
+                                 rng_seed=seed, update_decoder=False, update_emb=False, update_pose=True, pose6=pose6,
+                                 refresh_weights=False)
+            st = eng.read_stats()   # the reference syncs here too (hit_mask, None checks)
+            if st.error & 4:
+                _check_ctl([4], "track_frame")
+            if not (st.error & 2):
+                break
+            # sample capacity exceeded: nothing has been applied yet (the optimiser step follows) -- redo this iteration on a larger engine
+            cap = max(2 * cap, int(st.n_samples * 1.25) + 1024)
+            eng = _engine(N_rays, cap, dev)
+            if opt is not None:
+                opt.groups[0]["grad"] = None
         if st.n_hit_rays <= 0 or (st.error & 1) or st.n_samples == 0:
             print("Encouter a bug while Tracking, currently not be fixed, Restarting!!")  # render_helpers.py:488-491
             n_last = 0
@@ -447,6 +511,7 @@ def track_frame(frame_pose, curr_frame, map_states, sdf_network, loss_criteria, 
             loss_log.append(st.loss)
         if opt is None:
             opt = FusedAdam([dict(param=pose6[0], grad=eng.pose_grad[0], lr=lr)])
+        opt.groups[0]["grad"] = eng.pose_grad[0]
         opt.step()
     if n_last:
         hit_mask = (eng.hit_rank[:n_last] >= 0).clone()   # of the last iteration, like the reference's return value

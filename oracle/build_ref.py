@@ -8,7 +8,13 @@ oracle/_ref/ (git-ignored, but shipped to the GPU box by gpurun).  The reference
 NOT run; this is a direct torch.utils.cpp_extension.load() of the few source files.
 The one missing dependency (Eigen, used for a 3-int return type) is satisfied by oracle/shim/.
 
-Usage:  python oracle/build_ref.py [svo] [grid]
+The reference's hot-path PYTHON (render_helpers / voxel_helpers / lidar / criterion / se3pose / lidarFrame /
+sample_util, ~1500 lines) is *staged* by stage_src() into oracle/_ref/src/ the same way: a build product in the
+git-ignored oracle/_ref/ (never committed, never imported by the product) that travels to the GPU box with the
+snapshot, so that the B200 tests and bench.py can run the UNMODIFIED reference loop (with grid_ref.so) beside the
+product on the same GPU (oracle/ref_harness.py).
+
+Usage:  python oracle/build_ref.py [svo] [grid] [src]
 """
 import os
 import sys
@@ -42,11 +48,26 @@ def build_grid():
     return os.path.join(bdir, "grid_ref.so")
 
 
+REF_PY = ["criterion.py", "se3pose.py", "lidarFrame.py", "utils/__init__.py", "utils/sample_util.py",
+          "variations/render_helpers.py", "variations/voxel_helpers.py", "variations/lidar.py"]
+
+
+def stage_src():
+    """Stage the reference's hot-path Python files, byte for byte, under oracle/_ref/src (git-ignored build product)."""
+    import shutil
+    dst = os.path.join(OUT, "src")
+    for rel in REF_PY:
+        s, d = os.path.join(REF, "src", rel), os.path.join(dst, rel)
+        os.makedirs(os.path.dirname(d), exist_ok=True)
+        shutil.copyfile(s, d)
+    return dst
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         print("reference tree not present; nothing to build")
         sys.exit(0)
-    what = sys.argv[1:] or ["svo", "grid"]
+    what = sys.argv[1:] or ["svo", "grid", "src"]
     for w in what:
-        p = {"svo": build_svo, "grid": build_grid}[w]()
+        p = {"svo": build_svo, "grid": build_grid, "src": stage_src}[w]()
         print("built", p)

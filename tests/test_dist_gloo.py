@@ -78,18 +78,22 @@ def _worker(rank, world, port, q):
     st.cnt_fs_valid, st.cnt_sdf_valid = rc["cnt_fs"], rc["cnt_sdf"]
     st.pad_fs_rays, st.pad_fs_nsamp, st.pad_sdf_rays, st.pad_sdf_nsamp = rc["pad_fs_rays"], rc["pad_fs_nsamp"], rc["pad_sdf_rays"], rc["pad_sdf_nsamp"]
     st.pad_sdf_d2, st.pad_sdf_d2_nsamp = rc["pad_sdf_d2"], rc["pad_sdf_d2_nsamp"]
-    st.fs_sum, st.sdf_sum = 1.5 + rank, 2.25 * (rank + 1)
+    st.fs_sum, st.sdf_sum = 1.5 + rank + 1e-9 * (rank + 1), 2.25 * (rank + 1)
+    st.error = 2 if rank == 1 else 0                     # one rank ran out of sample capacity: every rank must learn it (OR)
     buf = torch.frombuffer(bytearray(bytes(st)), dtype=torch.uint8).clone()
-    nldist.allreduce_sample_stats(buf)
-    nldist.allreduce_loss_sums(buf)
-    g = torch.full((7, 16), float(rank + 1))
-    nldist.allreduce_grads([g, None])
-    # the per-iteration set: embedding table, six decoder tensors, pose accumulators -- one coalesced reduction
-    many = [torch.full(shape, float(rank + 1) * (i + 1)) for i, shape in enumerate([(50, 16), (256, 16), (256,), (256, 256), (256,), (1, 256), (1,), (3, 12)])]
-    nldist.allreduce_grads([many[0], None] + many[1:])
-    ok_many = all(bool((t == 3.0 * (i + 1)).all()) for i, t in enumerate(many))
+    # exchange 1: ONE collective for every statistic (counters SUM, R_hit SUM, S_max MAX, error bits OR)
+    xbuf = nldist.allreduce_sample_stats(buf)
+    assert xbuf.numel() == nldist.stats_words(world)
+    # exchange 2: ONE collective for the flat fp32 gradient buffer, the loss sums riding in its 4-float header as (hi, lo) pairs
+    gradflat = torch.full((16 + 16 + 7 * 16,), float(rank + 1))
+    gradflat[:16] = 0
+    nldist.allreduce_grads_with_loss(buf, gradflat)
+    ok_flat = bool((gradflat[16:] == 3.0).all())
+    dec_flat = torch.full((70464,), float(rank + 1) * 0.5)
+    nldist.allreduce_flat(dec_flat)
+    ok_flat = ok_flat and bool((dec_flat == 1.5).all())
     out = nl._capi.RenderStats.from_buffer_copy(buf.numpy().tobytes())
-    q.put((rank, _prepare(out), out.fs_sum, out.sdf_sum, float(g[0, 0]) if ok_many else -1.0, (lo, hi)))
+    q.put((rank, _prepare(out), out.fs_sum, out.sdf_sum, 3.0 if ok_flat else -1.0, (lo, hi), out.error))
     dist.destroy_process_group()
 
 
@@ -114,9 +118,10 @@ def test_sharded_statistics_equal_unsharded():
     S = int(valid.sum(-1).max())
     sdf = torch.ones(valid.shape).masked_scatter(valid, sdf_v)[hit][:, :S]
     loss, parts = OC.sdf_loss(zh[:, :S], sdf, valid[hit][:, :S], pts[hit], cos[hit], 0.3, 40.0, 1.0, 10000.0)
-    for rank, (n_fs, n_sdf, N), fs_sum, sdf_sum, g00, (lo, hi) in res:
+    for rank, (n_fs, n_sdf, N), fs_sum, sdf_sum, g00, (lo, hi), err in res:
         assert n_fs == int(parts["n_fs"]) and n_sdf == int(parts["n_sdf"])       # global mask counts
         assert N == int(hit.sum()) * S                                            # global mean denominator
-        assert fs_sum == 1.5 + 2.5 and sdf_sum == 2.25 + 4.5
+        assert abs(fs_sum - (1.5 + 2.5 + 3e-9)) < 1e-12 and sdf_sum == 2.25 + 4.5   # (hi, lo) float pairs keep ~48 bits of the f64 sums
         assert g00 == 3.0
+        assert err == 2
     assert res[0][5][1] == res[1][5][0] and res[0][5][0] == 0 and res[1][5][1] == pts.shape[0]   # contiguous cover

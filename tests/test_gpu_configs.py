@@ -265,3 +265,85 @@ def test_track_frame_device_selection_and_cuda_graph(nl):
                                             learning_rate=0.03, max_voxel_hit=20, max_distance=40.0, ray_selection="device", cuda_graph=True,
                                             deterministic=True)
     torch.testing.assert_close(out2.data.detach().cpu(), outs[1], rtol=0, atol=2e-5)
+
+
+def _ba_case(nl, far=False):
+    syn = nl.synthetic
+    scans = [syn.make_scan(n_beams=32, n_az=300, seed=200 + i, sensor_xyz=(1.0 * i, 0.0, 0.0)) for i in range(2)]
+    mu = nl.mapping.MapUpdater(0.3, init_std=0.01, seed=2)
+    for pts, cos, pose in scans:
+        ms = mu.insert_voxels(torch.from_numpy(syn.voxelize(pts, pose, 0.3)))
+    torch.manual_seed(5)
+    dec = nl.lidar.Decoder(depth=2, width=256, in_dim=16, skips=[], embedder="none", multires=0).cuda()
+    frames = []
+    for i, (pts, cos, pose) in enumerate(scans):
+        T = torch.from_numpy(pose.copy())
+        if far:
+            T[:3, 3] += 500.0                     # the sensor is nowhere near the map: no ray hits anything
+        frames.append(nl.frame.LidarFrame(i, torch.from_numpy(pts), torch.from_numpy(cos), nl.se3pose.OptimizablePose.from_matrix(T), new_keyframe=True))
+    return ms, dec, frames
+
+
+def _run_ba(nl, ms, dec, frames, n_it=3, **kw):
+    emb = ms.emb.clone()
+    torch.manual_seed(9)
+    nl.render_helpers.bundle_adjust_frames(frames, emb, ms, dec, nl.criterion.Criterion(Args()), 0.3, 0.15, N_rays=512, num_iterations=n_it,
+                                           truncation=0.3, max_voxel_hit=20, max_distance=40.0, learning_rate=[0.01, 0.005, 0.001],
+                                           deterministic=True, **kw)
+    torch.cuda.synchronize()
+    return emb, {k: v.detach().clone() for k, v in dec.state_dict().items()}, torch.stack([f.pose.data.detach().cpu() for f in frames])
+
+
+def test_sample_capacity_overflow_is_undone_and_redone(nl, monkeypatch):
+    """A call whose sample capacity is exceeded must not train on a truncated sample set: the parameters and the RNG state are
+    restored and the call is redone with a larger engine -- same result as with enough capacity from the start."""
+    rh = nl.render_helpers
+    ms, dec, frames = _ba_case(nl)
+    e_ok, d_ok, p_ok = _run_ba(nl, ms, dec, frames)
+    rh._ENGINES.clear()
+    monkeypatch.setattr(rh, "SAMPLES_PER_RAY_MAP", 1)       # ~10 samples per ray are needed: every iteration overflows
+    small = {"n": 0}
+    real_engine = rh._engine
+
+    def tiny_engine(n_rays, min_samples, device):             # bypass the 2^16-sample floor of the engine cache for this test
+        if min_samples <= n_rays:
+            small["n"] += 1
+            return nl.engine.SDFEngine(n_rays, min_samples, device)
+        return real_engine(n_rays, min_samples, device)
+    monkeypatch.setattr(rh, "_engine", tiny_engine)
+    ms2, dec2, frames2 = _ba_case(nl)
+    e2, d2, p2 = _run_ba(nl, ms2, dec2, frames2)
+    assert small["n"] == 1                                     # the first attempt really ran on the too-small engine
+    torch.testing.assert_close(p2, p_ok, rtol=0, atol=2e-5)
+    for k in d_ok:
+        torch.testing.assert_close(d2[k], d_ok[k], rtol=0, atol=2e-5)
+    assert float((e2.float() - e_ok.float()).abs().gt(2e-3).float().mean()) < 1e-3
+
+
+def test_iterations_without_hits_skip_the_optimiser_step(nl, capsys):
+    """render_helpers.py:405-409: when nothing is hit the reference `continue`s -- no optimiser step, no change of Adam's state.
+    Here the Adam kernels read a device-side skip flag; nothing may move and the reference's message is printed per skipped iteration."""
+    ms, dec, frames = _ba_case(nl, far=True)
+    emb0 = ms.emb.clone()
+    dec0 = {k: v.detach().clone() for k, v in dec.state_dict().items()}
+    p0 = torch.stack([f.pose.data.detach().cpu() for f in frames])
+    e, d, p = _run_ba(nl, ms, dec, frames, n_it=4)
+    assert torch.equal(e, emb0) and torch.equal(p, p0)
+    assert all(torch.equal(d[k], dec0[k]) for k in d)
+    assert capsys.readouterr().out.count("Encouter a bug while Mapping") == 4
+
+
+def test_mapstate_cache_is_keyed_on_content(nl):
+    """a reference-format map_states dict whose tensors changed in place (or were re-created at the same address with the
+    same shapes) must not hit the cache."""
+    syn = nl.synthetic
+    pts, cos, pose = syn.make_scan(n_beams=16, n_az=200, seed=3)
+    mu = nl.mapping.MapUpdater(0.3)
+    mu.insert_voxels(torch.from_numpy(syn.voxelize(pts, pose, 0.3)))
+    ms = {k: v for k, v in mu.map_states.items() if k != "_mapstate"}
+    a = nl.engine.MapState.from_map_states(ms, "cuda")
+    b = nl.engine.MapState.from_map_states(ms, "cuda")
+    assert a.vox2row.data_ptr() == b.vox2row.data_ptr()                      # unchanged content: cache hit
+    ms["voxel_structure"][0, 0] = -1                                         # in-place edit, same address, same shape
+    c = nl.engine.MapState.from_map_states(ms, "cuda")
+    assert int(c.structure[0, 0]) == -1 and c.structure.data_ptr() != a.structure.data_ptr()

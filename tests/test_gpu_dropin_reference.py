@@ -1,0 +1,188 @@
+"""The drop-in boundary, proven with the REFERENCE'S OWN objects on the B200.
+
+On the GPU box oracle/_ref/ holds the compiled, unmodified reference `grid` extension and the reference's hot-path Python
+files, staged byte for byte by oracle/build_ref.py (git-ignored build products, like grid_ref.so).  These tests
+
+  1. run the reference's own bundle_adjust_frames / track_frame (render_helpers.py:321-514: eager PyTorch + grid_ref +
+     autograd + torch.optim.Adam) on the GPU, and
+  2. run the functions `nerfloam_b200.dropin.install()` binds in their place,
+
+both times with objects built from the reference's own classes -- Criterion, LidarFrame, OptimizablePose, Decoder and a
+`map_states` dict in mapping.py's exact format (CPU index tensors, [N,1] int32 voxel_id2embedding_id, duplicate-row bf16 CUDA
+leaf table) -- on identical inputs, seeds and (pinned) sampling noise, and compare the parameters after 3 optimiser steps.
+"""
+import copy
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+VS, MD, TR = 0.3, 40.0, 0.3          # configs/kitti/kitti.yaml
+LR = [0.01, 0.005, 0.001]
+
+
+@pytest.fixture(scope="module")
+def ref():
+    from oracle import ref_harness as H
+    if not H.available():
+        pytest.skip("oracle/_ref (compiled reference grid + staged reference Python) not present")
+    assert torch.cuda.is_available()
+    return H.load()
+
+
+@pytest.fixture(scope="module")
+def nl():
+    import nerfloam_b200 as nl
+    return nl
+
+
+def _scene(nl, n_scans=3):
+    syn = nl.synthetic
+    scans = [syn.make_scan(n_beams=32, n_az=600, seed=100 + i, sensor_xyz=(1.0 * i, 0.1 * i, 0.0), yaw=0.02 * i) for i in range(n_scans)]
+    o = nl.svo.Octree()
+    o.init(256 * 256 * 4, 16, VS)
+    for pts, cos, pose in scans:
+        o.insert(torch.from_numpy(syn.voxelize(pts, pose, VS)))
+    return scans, o.get_centres_and_children()
+
+
+def _ref_frames(ref, scans, perturb=True):
+    """The reference's LidarFrame / OptimizablePose objects (lidarFrame.py:10-25 with new_keyframe=True adopts the pose object)."""
+    frames = []
+    g = torch.Generator().manual_seed(5)
+    for i, (pts, cos, pose) in enumerate(scans):
+        p6 = ref.OptimizablePose.from_matrix(torch.from_numpy(pose.copy())).data.detach().clone()
+        if perturb and i > 0:
+            p6 = p6 + torch.cat([torch.randn(3, generator=g) * 0.02, torch.randn(3, generator=g) * 0.002])
+        frames.append(ref.LidarFrame(i, torch.from_numpy(pts), torch.from_numpy(cos), ref.OptimizablePose(p6.float()), new_keyframe=True))
+    return frames
+
+
+def _state(ref, nl, table_rows=None):
+    from oracle import ref_harness as H
+    scans, (voxels, children, features) = _scene(nl)
+    ms = H.reference_map_states(voxels, children, features, VS, table_rows=table_rows, init_std=0.01, seed=3)
+    torch.manual_seed(777)
+    dec = ref.Decoder(depth=2, width=256, in_dim=16, skips=[], embedder="none", multires=0).cuda()
+    return scans, ms, dec
+
+
+def _clone_ms(ms):
+    out = dict(ms)
+    out["voxel_vertex_emb"] = ms["voxel_vertex_emb"].detach().clone().requires_grad_()
+    return out
+
+
+def _rel(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("update_decoder", [True, False])
+def test_bundle_adjust_frames_reference_objects_through_dropin(ref, nl, update_decoder):
+    from oracle import ref_harness as H
+    scans, ms0, dec0 = _state(ref, nl, table_rows=4_000_000)
+    crit = ref.Criterion(H.args(MD, TR))
+    kw = dict(voxel_size=VS, step_size=0.5 * VS, N_rays=1024, num_iterations=3, truncation=TR, max_voxel_hit=20, max_distance=MD,
+              learning_rate=LR, update_pose=True, update_decoder=update_decoder)
+
+    # ---- (1) the reference's own loop on the GPU ----
+    ms_r, dec_r, fr_r = _clone_ms(ms0), copy.deepcopy(dec0), _ref_frames(ref, scans)
+    torch.manual_seed(11)
+    with H.pinned(ref):
+        ref.orig["bundle_adjust_frames"](fr_r, ms_r["voxel_vertex_emb"], ms_r, dec_r, crit, **kw)
+    torch.cuda.synchronize()
+
+    # ---- (2) the same call through dropin.install(), same reference objects ----
+    import nerfloam_b200.dropin as dropin
+    dropin.install(reference_src=ref.src)
+    assert ref.RH.bundle_adjust_frames is nl.render_helpers.bundle_adjust_frames       # what mapping.py:179 now calls
+    ms_p, dec_p, fr_p = _clone_ms(ms0), copy.deepcopy(dec0), _ref_frames(ref, scans)
+    torch.manual_seed(11)
+    ref.RH.bundle_adjust_frames(fr_p, ms_p["voxel_vertex_emb"], ms_p, dec_p, crit, deterministic=True, **kw)
+    torch.cuda.synchronize()
+
+    # poses: frame 0 frozen, the others moved and agree
+    p_r = torch.stack([f.pose.data.detach().cpu() for f in fr_r])
+    p_p = torch.stack([f.pose.data.detach().cpu() for f in fr_p])
+    p_0 = torch.stack([f.pose.data.detach().cpu() for f in _ref_frames(ref, scans)])
+    assert torch.equal(p_p[0], p_0[0]) and torch.equal(p_r[0], p_0[0])
+    assert float((p_r[1:] - p_0[1:]).abs().max()) > 1e-3
+    # 3 Adam steps of lr 1e-3: the first step moves every coordinate by exactly +-lr, so agreement to a small fraction of lr
+    # means the gradient signs and the later normalised steps agree
+    np.testing.assert_allclose(p_p.numpy(), p_r.numpy(), atol=1e-4)
+    # decoder
+    for (k, a), (_, b) in zip(dec_p.state_dict().items(), dec_r.state_dict().items()):
+        if update_decoder:
+            assert float((b - dec0.state_dict()[k]).abs().max()) > 1e-3
+            np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), atol=2e-4, err_msg=k)
+        else:
+            assert torch.equal(a, dec0.state_dict()[k]) and torch.equal(b, dec0.state_dict()[k])
+    # embeddings (bf16, same row numbering: both sides use the reference's table): all but a sliver of entries identical to
+    # within one Adam step's worth of bf16 rounding
+    e_r, e_p, e_0 = (t["voxel_vertex_emb"].detach().float().cpu() for t in (ms_r, ms_p, ms0))
+    moved = (e_r - e_0).abs() > 1e-3
+    assert float(moved.float().mean()) > 0.01
+    assert bool(((e_p - e_0).abs() > 1e-3)[moved].float().mean() > 0.99)                # the same rows moved
+    assert float(((e_p - e_r).abs() > 2e-3).float().mean()) < 5e-3
+
+
+def test_track_frame_reference_objects_through_dropin(ref, nl):
+    from oracle import ref_harness as H
+    scans, ms0, dec0 = _state(ref, nl)
+    crit = ref.Criterion(H.args(MD, TR))
+    kw = dict(voxel_size=VS, N_rays=1024, step_size=0.2 * VS, num_iterations=3, truncation=TR, learning_rate=0.06, max_voxel_hit=20,
+              max_distance=MD, depth_variance=True)
+
+    def frame():
+        f = _ref_frames(ref, scans)[1]
+        f.index = 5                                            # lr/3 branch of render_helpers.py:448-450
+        return f
+
+    f_r = frame()
+    pose_in = copy.deepcopy(f_r.pose)
+    torch.manual_seed(21)
+    with H.pinned(ref):
+        pose_r, hit_r = ref.orig["track_frame"](pose_in, f_r, _clone_ms(ms0), copy.deepcopy(dec0), crit, **kw)
+    torch.cuda.synchronize()
+
+    import nerfloam_b200.dropin as dropin
+    dropin.install(reference_src=ref.src)
+    f_p = frame()
+    torch.manual_seed(21)
+    pose_p, hit_p = ref.RH.track_frame(copy.deepcopy(f_p.pose), f_p, _clone_ms(ms0), copy.deepcopy(dec0), crit, deterministic=True, **kw)
+    assert type(pose_p).__name__ == "OptimizablePose" and pose_p.data.is_cuda
+    assert hit_p is not None and hit_r is not None
+    assert torch.equal(hit_p.cpu(), hit_r.cpu())
+    assert float((pose_r.data.detach().cpu() - pose_in.data.detach()).abs().max()) > 1e-3
+    np.testing.assert_allclose(pose_p.data.detach().cpu().numpy(), pose_r.data.detach().cpu().numpy(), atol=3e-4)   # lr = 0.06/3 per step
+
+
+def test_render_rays_and_criterion_reference_objects(ref, nl):
+    """render_rays through the drop-in feeding the REFERENCE'S Criterion.forward + autograd: same loss, same ray mask and
+    sample layout as the reference's own render_rays."""
+    from oracle import ref_harness as H
+    scans, ms0, dec0 = _state(ref, nl)
+    crit = ref.Criterion(H.args(MD, TR))
+    pts, cos, pose = scans[0]
+    sel = np.sort(np.random.default_rng(0).choice(pts.shape[0], 2048, replace=False))
+    P, Cn = torch.from_numpy(pts[sel]).cuda(), torch.from_numpy(cos[sel]).cuda()
+    T = torch.from_numpy(pose).cuda()
+    rd = ((P / (P.norm(dim=-1, keepdim=True) + 1e-8)) @ T[:3, :3].T)[None].contiguous()
+    ro = T[:3, 3].reshape(1, 1, 3).expand_as(rd).contiguous()
+    args = (0.5 * VS, VS, TR, 20, MD)
+    with H.pinned(ref):
+        out_r = ref.orig["render_rays"](ro, rd, _clone_ms(ms0), copy.deepcopy(dec0), *args, chunk_size=-1)
+        loss_r, _ = crit(out_r, P[None], Cn[None, :, None])
+    out_p = nl.render_helpers.render_rays(ro, rd, _clone_ms(ms0), copy.deepcopy(dec0), *args, chunk_size=-1, deterministic=True)
+    loss_p, _ = crit(out_p, P[None], Cn[None, :, None])
+    assert torch.equal(out_p["ray_mask"].view(-1), out_r["ray_mask"].view(-1))
+    assert torch.equal(out_p["valid_mask"], out_r["valid_mask"])
+    np.testing.assert_allclose(out_p["z_vals"].cpu().numpy(), out_r["z_vals"].cpu().numpy(), rtol=2e-6)
+    np.testing.assert_allclose(out_p["sdf"].detach().cpu().numpy(), out_r["sdf"].detach().cpu().numpy(), atol=1e-5)
+    np.testing.assert_allclose(float(loss_p), float(loss_r), rtol=1e-5)

@@ -206,3 +206,90 @@ def test_fused_adam_vs_torch(nl, dtype):
         else:   # same rounding points: identical up to rare 1-ulp flips from reciprocal-vs-division inside torch
             assert np.mean(a != b) < 2e-2
             np.testing.assert_allclose(a, b, rtol=1e-2, atol=1e-4)
+
+
+def test_adam_ctl_reads_step_and_skip_from_the_device(nl):
+    """nl_adam_*_ctl: the step count comes from the control block; a skipped iteration leaves parameter AND moments untouched
+    (the reference `continue`s before optim.step(), render_helpers.py:405-409)."""
+    dev = "cuda"
+    cap, lib = nl._capi, nl._capi.lib()
+    torch.manual_seed(3)
+    n = 1000
+    for dtype in (torch.float32, torch.bfloat16):
+        p0 = (torch.randn(n, device=dev) * 0.05).to(dtype)
+        g = torch.randn(n, device=dev)
+        ctl = torch.zeros(cap.CTL_WORDS, dtype=torch.int32, device=dev)
+        a = nl.engine.FusedAdam([dict(param=p0.clone(), grad=g, lr=0.01)])
+        b = nl.engine.FusedAdam([dict(param=p0.clone(), grad=g, lr=0.01)], ctl=ctl)
+        for step in (1, 2, 3):
+            a.step()
+            ctl[cap.CTL_ADAM_STEP] = step
+            b.step()
+            if step == 2:                      # an iteration without hits in between: nothing may move, the step count stays
+                ctl[cap.CTL_SKIP_NOW] = 1
+                before = [b.groups[0][k].clone() for k in ("param", "m", "v")]
+                b.step()
+                assert all(torch.equal(x, b.groups[0][k]) for x, k in zip(before, ("param", "m", "v")))
+                ctl[cap.CTL_SKIP_NOW] = 0
+        assert torch.equal(a.groups[0]["param"], b.groups[0]["param"])
+        assert torch.equal(a.groups[0]["m"], b.groups[0]["m"]) and torch.equal(a.groups[0]["v"], b.groups[0]["v"])
+
+
+def test_iter_status_folds_statistics(nl):
+    cap, lib = nl._capi, nl._capi.lib()
+    dev = "cuda"
+    ctl = torch.zeros((2, cap.CTL_WORDS), dtype=torch.int32, device=dev)
+    ctl[0, cap.CTL_MIN_HIT] = 2 ** 31 - 1
+    seq = [dict(n_hit_rays=50, n_samples=700, error=0), dict(n_hit_rays=0, n_samples=0, error=0), dict(n_hit_rays=40, n_samples=900, error=2),
+           dict(n_hit_rays=45, n_samples=100, error=1)]
+    cur = 0
+    for s in seq:
+        st = cap.RenderStats()
+        for k, v in s.items():
+            setattr(st, k, v)
+        d = torch.frombuffer(bytearray(bytes(st)), dtype=torch.uint8).to(dev)
+        cap.check(lib.nl_iter_status(cap.ptr(d), cap.ptr(ctl[cur]), cap.ptr(ctl[cur ^ 1]), cap.stream_ptr()))
+        cur ^= 1
+    c = ctl[cur].tolist()
+    assert c[cap.CTL_ERROR] == 3 and c[cap.CTL_SKIPPED] == 2 and c[cap.CTL_SKIP_NOW] == 1 and c[cap.CTL_ADAM_STEP] == 2
+    assert c[cap.CTL_MIN_HIT] == 0 and c[cap.CTL_ITERS] == 4 and c[cap.CTL_MAX_SAMPLES] == 900
+
+
+def test_stats_pack_kernels_match_the_host_layout(nl):
+    """The CUDA pack/unpack kernels of the multi-GPU statistics exchange and the torch restatement used on CPU tensors (gloo tests)
+    produce the same vector and the same unpacked struct."""
+    cap = nl._capi
+    nld = nl.dist
+    world, rank = 4, 2
+    st = cap.RenderStats()
+    st.n_hit_rays, st.max_samples, st.error = 12345, 37, 2
+    st.cnt_fs_valid, st.cnt_sdf_valid, st.pad_fs_rays, st.pad_fs_nsamp, st.pad_sdf_rays, st.pad_sdf_nsamp = 10 ** 10, 987654321, 77, 1234, 55, 999
+    st.pad_sdf_d2, st.pad_sdf_d2_nsamp, st.fs_sum, st.sdf_sum = 1234.5678, 98765.4321, 3.14159265358979, 2.718281828459045e-3
+    host = torch.frombuffer(bytearray(bytes(st)), dtype=torch.uint8).clone()
+    devs = host.cuda()
+    b_h = torch.empty(nld.stats_words(world), dtype=torch.float64)
+    b_d = torch.empty(nld.stats_words(world), dtype=torch.float64, device="cuda")
+    nld.pack_stats(host, b_h, rank, world, 0)
+    nld.pack_stats(devs, b_d, rank, world, 0)
+    assert torch.equal(b_h, b_d.cpu())
+    # pretend the other ranks contributed: a larger S_max in slot 0, error bit 0 in slot 3
+    for b in (b_h, b_d):
+        b[:9] *= 3
+        b[nld.FIXED + 0] = 41.0
+        b[nld.FIXED + world + 3] = 1.0
+    nld.unpack_stats(host, b_h, world, 0)
+    nld.unpack_stats(devs, b_d, world, 0, 1.0, 10000.0)
+    a, b = cap.RenderStats.from_buffer_copy(host.numpy().tobytes()), cap.RenderStats.from_buffer_copy(devs.cpu().numpy().tobytes())
+    for k in ("n_hit_rays", "max_samples", "error", "cnt_fs_valid", "cnt_sdf_valid", "pad_fs_rays", "pad_fs_nsamp", "pad_sdf_rays", "pad_sdf_nsamp",
+              "pad_sdf_d2", "pad_sdf_d2_nsamp"):
+        assert getattr(a, k) == getattr(b, k), k
+    assert b.max_samples == 41 and b.error == 3 and b.n_hit_rays == 3 * 12345
+    assert b.g_fs > 0 and b.w_fs > 0                                    # the CUDA unpack re-derived the loss constants
+    h_h, h_d = torch.zeros(4), torch.zeros(4, device="cuda")
+    host2, dev2 = torch.frombuffer(bytearray(bytes(st)), dtype=torch.uint8).clone(), torch.frombuffer(bytearray(bytes(st)), dtype=torch.uint8).cuda()
+    nld.pack_stats(host2, h_h, 0, world, 1)
+    nld.pack_stats(dev2, h_d, 0, world, 1)
+    assert torch.equal(h_h, h_d.cpu())
+    nld.unpack_stats(dev2, h_d, world, 1)
+    c = cap.RenderStats.from_buffer_copy(dev2.cpu().numpy().tobytes())
+    assert abs(c.fs_sum - st.fs_sum) < 1e-13 * st.fs_sum + 1e-15 and abs(c.sdf_sum - st.sdf_sum) < 1e-13
