@@ -491,12 +491,9 @@ __global__ void k_transpose(int rows, int cols, const float *__restrict__ in, fl
 template <int W, bool TRAIN, bool WGRAD>
 int launch_mlp(const MlpParams &p, cudaStream_t stream) {
     const size_t smem = Cfg<W>::smem_floats(WGRAD) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_mlp<W, TRAIN, WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return nl_set_error_code(NL_ERR_CUDA, cudaGetErrorString(e));
-        configured = true;
-    }
+    static NlPerDevice configured;
+    const cudaError_t e = configured.once([&] { return cudaFuncSetAttribute(k_mlp<W, TRAIN, WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
+    if (e != cudaSuccess) return nl_set_error_code(NL_ERR_CUDA, cudaGetErrorString(e));
     const long long ntiles = (p.M_host + T_TILE - 1) / T_TILE;
     const int grid = (int)(ntiles < (long long)nl_num_sms() ? ntiles : (long long)nl_num_sms());
     k_mlp<W, TRAIN, WGRAD><<<grid, NTHREADS, smem, stream>>>(p);

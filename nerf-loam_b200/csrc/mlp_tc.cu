@@ -16,6 +16,7 @@
 // Layer 1 (K = 16) runs through the same ring as one extra K-block with 2 k-steps.
 // Shared memory: 2 x 64 KB weight stages + 2 x 32 KB activation stages = 192 KB.
 #include <cstdlib>
+#include <mutex>
 
 #include "nl_cuda.cuh"
 
@@ -410,17 +411,25 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
-// One 128 B row (32 fp32) of an A-operand K-block: the raw fp32 bits are the "hi" operand (the tensor core reads the top
-// 19 bits = truncation to tf32), lo = x - trunc(x) is exact in fp32 and is itself truncated by the hardware (|error| <
-// 2^-20 |x|).  off[c] = swizzled byte offset of chunk c for this thread's row (loop invariant).
+// tf32 hi/lo split of an A-operand value computed in the epilogue.  The tensor core TRUNCATES its fp32 inputs to tf32.  "hi" is
+// therefore simply the raw fp32 bits (which also keeps the stored activation panels exact: the hi tile is what gets bulk-copied
+// to HBM for the weight-gradient kernels), and lo = x - trunc(x), exact in fp32.  What matters is how lo reaches 11 bits: left
+// to the hardware it is truncated too -- an error of up to 2^-21 |x| that always points towards zero, i.e. a BIAS shared by every
+// sample.  Gradients that are sums of 10^4..10^5 strongly cancelling per-sample terms (the pose gradient near convergence:
+// cancellation ~10^4) turned that into 10^-3 relative error, 100x what fp32 arithmetic gives (measured against an fp64 run of
+// the same function, tests/test_gpu_pipeline.py).  Rounding lo to nearest instead (integer add of half an ulp, then mask) makes
+// the hardware truncation of lo a no-op and the residual <= 2^-22 |x| with random sign.
+__device__ __forceinline__ float tf32_lo_part(float x) {
+    const float lo = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    return __uint_as_float((__float_as_uint(lo) + 0x1000u) & 0xffffe000u);
+}
+// One 128 B row (32 fp32) of an A-operand K-block as hi and lo tiles.  off[c] = swizzled byte offset of chunk c for this thread's
+// row (loop invariant).
 __device__ __forceinline__ void store_a_row_fast(uint32_t stage, const uint32_t (&off)[8], const float (&h)[32]) {
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-        float lo[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) lo[i] = h[c * 4 + i] - __uint_as_float(__float_as_uint(h[c * 4 + i]) & 0xffffe000u);
         st_shared_v4(stage + off[c], h[c * 4], h[c * 4 + 1], h[c * 4 + 2], h[c * 4 + 3]);
-        st_shared_v4(stage + PANEL_A + off[c], lo[0], lo[1], lo[2], lo[3]);
+        st_shared_v4(stage + PANEL_A + off[c], tf32_lo_part(h[c * 4]), tf32_lo_part(h[c * 4 + 1]), tf32_lo_part(h[c * 4 + 2]), tf32_lo_part(h[c * 4 + 3]));
     }
 }
 
@@ -779,7 +788,7 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
                 for (int i = 0; i < 32; ++i) h[i] = ((mask1[kk] >> i) & 1u) ? dsdf * __uint_as_float(v[i]) : 0.f;
                 if (q == 0 && lane == 0) NL_STAMP(2 + g, 17 + kb, 1);
                 if (TS) {
-                    // hi = the fp32 bits (the tensor core truncates to tf32), lo = x - trunc(x); both into this group's TMEM slot
+                    // hi = the fp32 bits (the tensor core truncates to tf32), lo = x - trunc(x) rounded to tf32 (tf32_lo_part); both into this group's TMEM slot
                     const uint32_t u = tl * 4u + (uint32_t)kk;
                     mbar_wait(BAR(16 + g), (u & 1) ^ 1);               // the MMAs of this group's previous chunk retired
                     if (q == 0 && lane == 0) NL_STAMP(2 + g, 17 + kb, 2);
@@ -788,7 +797,7 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
                     for (int i = 0; i < 32; ++i) w[i] = __float_as_uint(h[i]);
                     tmem_st32(SLOT(g) + lane_addr, w);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) w[i] = __float_as_uint(h[i] - __uint_as_float(__float_as_uint(h[i]) & 0xffffe000u));
+                    for (int i = 0; i < 32; ++i) w[i] = __float_as_uint(tf32_lo_part(h[i]));
                     tmem_st32(SLOT(g) + lane_addr + 32, w);
                     tmem_wait_st();
                     tc_fence_before();
@@ -1320,12 +1329,9 @@ extern "C" int nl_mlp_tc_forward(int64_t M, const int32_t *d_M_dev, const float 
     if (M < 0) return nl_set_error("nl_mlp_tc_forward: negative M");
     if (M == 0) return NL_OK;
     if (!feats || !panels || !b0 || !b1 || !w2 || !b2 || !sdf) return nl_set_error("nl_mlp_tc_forward: null pointer");
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc::k_mlp_tc_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL);
-        if (e != cudaSuccess) return nl_set_error_code(NL_ERR_CUDA, cudaGetErrorString(e));
-        configured = true;
-    }
+    static NlPerDevice configured;
+    const cudaError_t e0 = configured.once([] { return cudaFuncSetAttribute(tc::k_mlp_tc_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL); });
+    if (e0 != cudaSuccess) return nl_set_error_code(NL_ERR_CUDA, cudaGetErrorString(e0));
     tc::FwdParams p;
     p.M_host = M; p.M_dev = d_M_dev; p.feats = feats; p.panels = (const uint8_t *)panels;
     p.b0 = b0; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.sdf = sdf;
@@ -1352,7 +1358,15 @@ extern "C" int nl_mlp_tc_train(int64_t M, const int32_t *d_M_dev, const float *f
         return nl_set_error("nl_mlp_tc_train: the loss needs s_flag, s_depth, s_ray, gt_depth and stats");
     if (grads && (!grads->gW0 || !grads->gb0 || !grads->gW1 || !grads->gb1 || !grads->gW2 || !grads->gb2 || !act))
         return nl_set_error("nl_mlp_tc_train: decoder gradients requested but a buffer is null");
-    static bool configured = false;
+    // per-device one-time state (kernel attributes are per device; so is the event that orders the weight-gradient stream)
+    constexpr int NL_MAX_DEV = 64;
+    static std::mutex dev_mu;
+    static bool configured_dev[NL_MAX_DEV] = {};
+    static cudaEvent_t ev_dev[NL_MAX_DEV] = {};
+    int cur_dev = 0;
+    if (cudaGetDevice(&cur_dev) != cudaSuccess || cur_dev < 0 || cur_dev >= NL_MAX_DEV) return nl_set_error_code(NL_ERR_CUDA, "nl_mlp_tc_train: cudaGetDevice");
+    std::lock_guard<std::mutex> dev_lock(dev_mu);
+    bool &configured = configured_dev[cur_dev];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(tc::k_mlp_tc_train<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::k_mlp_tc_train<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL);
@@ -1397,10 +1411,10 @@ extern "C" int nl_mlp_tc_train(int64_t M, const int32_t *d_M_dev, const float *f
         // caller enqueues next on `stream` (the embedding scatter, which is L2-atomic bound and leaves the SMs mostly idle).
         cudaStream_t ws = wgrad_stream_ ? (cudaStream_t)wgrad_stream_ : stream;
         if (ws != stream) {
-            static cudaEvent_t ev = nullptr;
+            cudaEvent_t &ev = ev_dev[cur_dev];
             if (!ev && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return nl_set_error_code(NL_ERR_CUDA, "cudaEventCreate");
-            cudaEventRecord(ev, stream);
-            cudaStreamWaitEvent(ws, ev, 0);
+            if (cudaEventRecord(ev, stream) != cudaSuccess || cudaStreamWaitEvent(ws, ev, 0) != cudaSuccess)
+                return nl_set_error_code(NL_ERR_CUDA, "nl_mlp_tc_train: could not order the weight-gradient stream behind the decoder kernel");
         }
         // ring depths (raw, converted): "deep" (4,3)/(4,4) = 219 KB of shared memory per CTA, "mid" (3,3)/(4,3) = 201/183 KB,
         // "shallow" (3,2)/(3,3) = 149/161 KB -- the smaller ones leave room for blocks of other kernels on the same SM when

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
 
 #include "nl_error.h"
 
@@ -17,6 +18,26 @@
     } while (0)
 
 static inline int nl_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// One-time per-DEVICE initialisation (cudaFuncSetAttribute is per device): `flag` is a function-local static of the caller.
+// Returns true when the calling thread has to (and may) run the initialisation for the current device; thread-safe.
+struct NlPerDevice {
+    static constexpr int MAX_DEV = 64;
+    std::mutex mu;
+    bool done[MAX_DEV] = {};
+    template <class F>
+    cudaError_t once(F &&init) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev < 0 || dev >= MAX_DEV) return cudaErrorInvalidDevice;
+        std::lock_guard<std::mutex> lock(mu);
+        if (done[dev]) return cudaSuccess;
+        e = init();
+        if (e == cudaSuccess) done[dev] = true;
+        return e;
+    }
+};
 
 // Number of SMs of the current device (148 on B200); cached.
 static inline int nl_num_sms() {

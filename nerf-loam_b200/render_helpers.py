@@ -203,6 +203,24 @@ def get_scores(sdf_network, map_states, voxel_size, bits=8):
 # ======================================================================================================
 # optimisation loops
 # ======================================================================================================
+class _few_threads:
+    """The reference's host-side ray selection is a handful of small element-wise CPU ops + a top-k over ~10^5 values; on a
+    many-core host torch fans each of them out over every core and the fork/join costs far more than the work (measured on the
+    128-CPU B200 box: 11 ms per frame and iteration, vs ~2 ms with 8 threads).  Same arithmetic, same RNG stream."""
+
+    def __init__(self, n=8):
+        self.n = n
+
+    def __enter__(self):
+        self.prev = torch.get_num_threads()
+        if self.prev > self.n:
+            torch.set_num_threads(self.n)
+
+    def __exit__(self, *a):
+        if torch.get_num_threads() != self.prev:
+            torch.set_num_threads(self.prev)
+
+
 class _FrameBatch:
     """Device copies of the per-frame point data (uploaded once per call instead of per iteration)."""
 
@@ -223,8 +241,9 @@ class _FrameBatch:
                 n = self.dirs[i].shape[0]
                 idx = torch.rand(n, device=dev).topk(min(N_rays, n)).indices.sort().values
             else:
-                f.sample_rays(N_rays, track=True) if track else f.sample_rays(N_rays)
-                idx = f.sample_mask.view(-1).nonzero().view(-1).to(dev, non_blocking=True)
+                with _few_threads():
+                    f.sample_rays(N_rays, track=True) if track else f.sample_rays(N_rays)
+                    idx = f.sample_mask.view(-1).nonzero().view(-1).to(dev, non_blocking=True)
             d.append(self.dirs[i][idx]); g.append(self.gt[i][idx]); c.append(self.cos[i][idx])
             fid.append(torch.full((idx.shape[0],), i, dtype=torch.int32, device=dev))
         return torch.cat(d).contiguous(), torch.cat(g).contiguous(), torch.cat(c).contiguous(), torch.cat(fid).contiguous()
@@ -241,12 +260,115 @@ def _grown_capacity(cap, ctl):
     return max(2 * cap, int(ctl[_capi.CTL_MAX_SAMPLES] * 1.25) + 1024)
 
 
+class _MapGraph:
+    """One captured mapping iteration (per-frame ray selection -> rays -> traversal -> sampling -> gather -> decoder fwd/bwd ->
+    embedding scatter / pose gradients -> Adam on embeddings, decoder and poses) with every per-call input in static device
+    buffers.  At the reference's real iteration size (5 x 2048 rays, ~10^5 samples) an iteration is ~40 kernel launches of a
+    few microseconds each: issued one by one from Python it is host-bound (1.3 ms), replayed as a graph it is not.
+    Captured once per (map version, table, decoder, window shape); every call is num_iterations replays + ONE read-back."""
+
+    _cache = {}
+
+    def __init__(self, key, m, emb, sdf_network, cfg, F, N_rays, lrs, update_decoder, pose_rows, deterministic, cap, spr):
+        dev = emb.device
+        R = F * N_rays
+        eng = SDFEngine(R, R * spr, dev)            # private: captured pointers must stay valid
+        bufs = DecoderBuffers(sdf_network, dev)
+        self.key, self.eng, self.bufs, self.m, self.emb, self.F, self.N, self.cap = key, eng, bufs, m, emb, F, N_rays, cap
+        self.packed = m.packed_children()
+        self.dirs = torch.tensor([0.0, 0.0, -1.0], device=dev).repeat(F, cap, 1).contiguous()
+        self.gt = torch.ones((F, cap), device=dev)
+        self.cos = torch.ones((F, cap), device=dev)
+        self.n_dev = torch.full((F, 1), cap, dtype=torch.int64, device=dev)
+        self.arange = torch.arange(cap, device=dev)[None, :]
+        self.fid = torch.arange(F, dtype=torch.int32, device=dev).repeat_interleave(N_rays).contiguous()
+        self.pose6 = torch.zeros((F, 6), device=dev)
+        self.seed_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        any_pose = len(pose_rows) > 0
+        groups = [dict(param=emb, grad=None, lr=lrs[0])]
+        if update_decoder:
+            groups += [dict(param=p.data, grad=g, lr=lrs[1]) for p, g in zip(bufs.params, bufs.grads)]
+        state = {"opt": None}
+
+        def body():
+            keys = torch.where(self.arange < self.n_dev, torch.rand((F, cap), device=dev), torch.full((), -1.0, device=dev))
+            idx = keys.topk(N_rays, dim=1).indices.sort(dim=1).values          # uniform without replacement among each scan's points
+            dirs = torch.gather(self.dirs, 1, idx[..., None].expand(-1, -1, 3)).reshape(R, 3).contiguous()
+            gt = torch.gather(self.gt, 1, idx).reshape(R).contiguous()
+            cos = torch.gather(self.cos, 1, idx).reshape(R).contiguous()
+            eng.rays_from_poses(self.pose6, dirs, self.fid)
+            eng.forward_backward(m, bufs, R, cfg, gt, cos, dir_local=dirs, ray_frame=self.fid, n_frames=F, update_decoder=update_decoder,
+                                 update_emb=True, update_pose=any_pose, pose6=self.pose6,
+                                 rng_seed_dev=None if deterministic else self.seed_dev)
+            if state["opt"] is None:
+                groups[0]["grad"] = eng.grad_emb
+                pg = [dict(param=self.pose6[i], grad=eng.pose_grad[i], lr=lrs[2]) for i in pose_rows]
+                state["opt"] = FusedAdam(groups + pg, ctl=eng.ctl)     # one fixed control block: forward_backward folds in place
+            state["opt"].step()
+            self.seed_dev.add_(0x3779B1)
+
+        # one throw-away eager iteration on a side stream (allocations, one-time kernel attributes), then the capture; the
+        # parameters it touches are put back afterwards
+        keep = (emb.clone(), [p.data.clone() for p in bufs.params])
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            eng.begin_call()
+            body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        l0 = _capi.LAUNCHES
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            body()
+        self.launches_per_iter = _capi.LAUNCHES - l0 + 1
+        self.opt = state["opt"]
+        with torch.no_grad():
+            emb.copy_(keep[0])
+            for p, q in zip(bufs.params, keep[1]):
+                p.data.copy_(q)
+
+    @classmethod
+    def get(cls, m, emb, sdf_network, cfg, F, N_rays, lrs, update_decoder, pose_rows, deterministic, n_points, spr):
+        cap = max(1 << 17, 1 << (int(n_points) - 1).bit_length())
+        key = (F, N_rays, tuple(float(x) for x in lrs), bool(update_decoder), tuple(pose_rows), bool(deterministic), cap, int(spr),
+               m.centres.data_ptr(), m.structure.data_ptr(), m.vox2row.data_ptr(), m.packed_children().data_ptr(), emb.data_ptr(),
+               m.n_nodes, int(emb.shape[0]), tuple(p.data_ptr() for p in _decoder_params(sdf_network)), tuple(sorted(cfg.items())))
+        g = cls._cache.get("g")
+        if g is None or g.key != key:
+            cls._cache = {}
+            g = cls(key, m, emb, sdf_network, cfg, F, N_rays, lrs, update_decoder, pose_rows, deterministic, cap, spr)
+            cls._cache = {"g": g}
+        return g
+
+    def run(self, frames, pose6_init, num_iterations, seed):
+        dev = self.dirs.device
+        for i, f in enumerate(frames):
+            rd = f.rays_d.reshape(-1, 3).float()
+            n = rd.shape[0]
+            self.dirs[i, :n].copy_(rd, non_blocking=True)
+            cosv = f.pointsCos.float().view(-1).to(dev, non_blocking=True)
+            self.cos[i, :n].copy_(cosv)
+            self.gt[i, :n].copy_(torch.norm(f.points.float().to(dev, non_blocking=True), 2, -1) * cosv)       # criterion.py:30-32
+            self.n_dev[i].fill_(n)
+        self.pose6.copy_(pose6_init)
+        self.seed_dev.fill_(seed if seed < 2 ** 31 else seed - 2 ** 32)
+        for g in self.opt.groups:
+            g["m"].zero_(); g["v"].zero_()
+        self.eng.begin_call()
+        for _ in range(num_iterations):
+            self.graph.replay()
+        _capi.LAUNCHES += self.launches_per_iter * num_iterations
+        return self.eng.read_ctl()
+
+
 def bundle_adjust_frames(keyframe_graph, embeddings, map_states, sdf_network, loss_criteria, voxel_size, step_size,
                          N_rays=512, num_iterations=10, truncation=0.1, max_voxel_hit=10, max_distance=10,
                          learning_rate=[1e-2, 1e-2, 5e-3], update_pose=True, update_decoder=True, profiler=None,
-                         deterministic=False, noise_per_iter=None, loss_log=None, ray_selection="host"):
+                         deterministic=False, noise_per_iter=None, loss_log=None, ray_selection="device", cuda_graph=None):
     """render_helpers.py:321-425.  Mutates `embeddings` (bf16 CUDA table), the decoder parameters and the
-    frame poses in place, like the reference.  Returns None.  ray_selection: see _FrameBatch.select.
+    frame poses in place, like the reference.  Returns None.  ray_selection: see _FrameBatch.select ("device" by default;
+    "host" reproduces the reference's CPU RNG stream ray for ray).  cuda_graph (default: on whenever ray_selection="device" and no
+    per-iteration host inputs/outputs are requested): the iteration is captured once per map version and replayed (_MapGraph).
 
     No host synchronisation per iteration: kernel error bits, "nothing was hit" iterations (which the reference skips,
     :405-409) and Adam's step count are tracked in a device-side control block that the Adam kernels read; the host looks at it
@@ -305,13 +427,25 @@ def bundle_adjust_frames(keyframe_graph, embeddings, map_states, sdf_network, lo
         eng.join_side()
         return eng.read_ctl()
 
+    graph_ok = ray_selection == "device" and noise_per_iter is None and loss_log is None and \
+        all(f.points.shape[0] >= N_rays for f in frames) and os.environ.get("NL_MAP_GRAPH", "1") != "0"
+    if cuda_graph is None:
+        cuda_graph = graph_ok
+    elif cuda_graph and not graph_ok:
+        raise ValueError("cuda_graph=True needs ray_selection='device', no per-iteration host inputs/outputs and >= N_rays points per scan")
     cap = R * SAMPLES_PER_RAY_MAP
     while True:
-        eng = _engine(R, cap, dev)
         snap = (emb.clone(), [p.data.clone() for p in bufs.params] if update_decoder else None, pose6.clone(),
                 torch.get_rng_state(), torch.cuda.get_rng_state(dev))
         n_log = len(loss_log) if loss_log is not None else 0
-        ctl = run(eng)
+        if cuda_graph:
+            g = _MapGraph.get(m, emb, sdf_network, cfg, F, N_rays, learning_rate, update_decoder, pose_rows, deterministic,
+                              max(f.points.shape[0] for f in frames), -(-cap // R))
+            ctl = g.run(frames, pose6, num_iterations, 0 if deterministic else _seed_from_torch())
+            pose6.copy_(g.pose6)
+        else:
+            eng = _engine(R, cap, dev)
+            ctl = run(eng)
         _check_ctl(ctl, "bundle_adjust_frames")
         if not (ctl[_capi.CTL_ERROR] & 2):
             break
@@ -452,8 +586,8 @@ def _track_frame_graph(frame_pose, curr_frame, map_states, sdf_network, loss_cri
 
 def track_frame(frame_pose, curr_frame, map_states, sdf_network, loss_criteria, voxel_size, N_rays=512, step_size=0.05,
                 num_iterations=10, truncation=0.1, learning_rate=1e-3, max_voxel_hit=10, max_distance=10, profiler=None,
-                depth_variance=False, deterministic=False, noise_per_iter=None, loss_log=None, ray_selection="host",
-                cuda_graph=False):
+                depth_variance=False, deterministic=False, noise_per_iter=None, loss_log=None, ray_selection="device",
+                cuda_graph=None):
     """render_helpers.py:428-514: optimise the 6-vector pose of one scan against a frozen map.
     Returns (OptimizablePose on the GPU, hit_mask bool[N_rays]) or (pose, None) if nothing was hit.
     ray_selection: see _FrameBatch.select.  cuda_graph=True (needs ray_selection="device"): the iteration -- ray selection,
@@ -462,9 +596,12 @@ def track_frame(frame_pose, curr_frame, map_states, sdf_network, loss_criteria, 
     every iteration (an iteration without hits makes the call return (pose, None) like the reference, just later)."""
     if ray_selection not in ("host", "device"):
         raise ValueError("ray_selection must be 'host' or 'device'")
+    graph_ok = ray_selection == "device" and noise_per_iter is None and loss_log is None and curr_frame.points.shape[0] >= N_rays
+    if cuda_graph is None:          # default: the fast path whenever nothing asks for per-iteration host interaction
+        cuda_graph = graph_ok and os.environ.get("NL_TRACK_GRAPH", "1") != "0"
     if cuda_graph:
-        if ray_selection != "device" or noise_per_iter is not None or loss_log is not None:
-            raise ValueError("cuda_graph=True needs ray_selection='device' and no per-iteration host inputs/outputs")
+        if not graph_ok:
+            raise ValueError("cuda_graph=True needs ray_selection='device', no per-iteration host inputs/outputs and >= N_rays points")
         return _track_frame_graph(frame_pose, curr_frame, map_states, sdf_network, loss_criteria, voxel_size, N_rays, step_size,
                                   num_iterations, learning_rate, max_distance, deterministic)
     dev = torch.device("cuda")

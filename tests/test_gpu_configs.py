@@ -289,7 +289,7 @@ def _run_ba(nl, ms, dec, frames, n_it=3, **kw):
     torch.manual_seed(9)
     nl.render_helpers.bundle_adjust_frames(frames, emb, ms, dec, nl.criterion.Criterion(Args()), 0.3, 0.15, N_rays=512, num_iterations=n_it,
                                            truncation=0.3, max_voxel_hit=20, max_distance=40.0, learning_rate=[0.01, 0.005, 0.001],
-                                           deterministic=True, **kw)
+                                           deterministic=True, **{"ray_selection": "host", **kw})
     torch.cuda.synchronize()
     return emb, {k: v.detach().clone() for k, v in dec.state_dict().items()}, torch.stack([f.pose.data.detach().cpu() for f in frames])
 
@@ -347,3 +347,37 @@ def test_mapstate_cache_is_keyed_on_content(nl):
     ms["voxel_structure"][0, 0] = -1                                         # in-place edit, same address, same shape
     c = nl.engine.MapState.from_map_states(ms, "cuda")
     assert int(c.structure[0, 0]) == -1 and c.structure.data_ptr() != a.structure.data_ptr()
+
+
+def test_bundle_adjust_frames_cuda_graph_equals_eager(nl):
+    """The captured + replayed mapping iteration (_MapGraph, the default path) against the eager loop.  With N_rays == number of
+    points of every scan (all rays selected in both modes) and deterministic sampling the two run the same arithmetic."""
+    syn = nl.synthetic
+    pts, cos, pose = syn.make_scan(n_beams=16, n_az=160, seed=12)
+    N = pts.shape[0]
+    res = []
+    for graph in (False, True):
+        mu = nl.mapping.MapUpdater(0.3, init_std=0.01, seed=2)
+        ms = mu.insert_voxels(torch.from_numpy(syn.voxelize(pts, pose, 0.3)))
+        torch.manual_seed(5)
+        dec = nl.lidar.Decoder(depth=2, width=256, in_dim=16, skips=[], embedder="none", multires=0).cuda()
+        frames = []
+        for i in range(2):
+            T = torch.from_numpy(pose.copy())
+            T[:3, 3] += torch.tensor([0.03 * i, -0.02 * i, 0.01 * i])
+            frames.append(nl.frame.LidarFrame(i, torch.from_numpy(pts), torch.from_numpy(cos), nl.se3pose.OptimizablePose.from_matrix(T), new_keyframe=True))
+        emb = ms.emb.clone()
+        for call in range(2):             # the second call goes through the cached graph
+            nl.render_helpers.bundle_adjust_frames(frames, emb, ms, dec, nl.criterion.Criterion(Args()), 0.3, 0.15, N_rays=N, num_iterations=3,
+                                                   truncation=0.3, max_voxel_hit=20, max_distance=40.0, learning_rate=[0.01, 0.005, 0.001],
+                                                   deterministic=True, ray_selection="device", cuda_graph=graph)
+        torch.cuda.synchronize()
+        res.append((emb.float().cpu(), {k: v.detach().cpu().clone() for k, v in dec.state_dict().items()},
+                    torch.stack([f.pose.data.detach().cpu() for f in frames])))
+    (e0, d0, p0), (e1, d1, p1) = res
+    assert torch.equal(p0[0], p1[0])                                       # frame index 0 stays frozen in both
+    torch.testing.assert_close(p1, p0, rtol=0, atol=1e-4)
+    for k in d0:
+        torch.testing.assert_close(d1[k], d0[k], rtol=0, atol=1e-4)
+    assert float((e1 - e0).abs().gt(2e-3).float().mean()) < 2e-3
+    assert float((e0 - ms.emb.float().cpu()).abs().max()) > 1e-3          # and it did train
