@@ -66,6 +66,13 @@ NL_API int nl_octree_export(const nl_octree *t, float *h_voxels, float *h_childr
 /* The same export already in the layout the hot path consumes (src/mapping.py:320-326):
  * centres f32[n,3] = (xyz + side/2) * voxel_size, structure i32[n,9] = 8 child ids + side, vertex i32[n,8]. */
 NL_API int nl_octree_export_map(const nl_octree *t, float *h_centres, int32_t *h_structure, int32_t *h_vertex);
+/* Incremental export (the reference re-exports the whole tree every frame, octree.cpp:293-342 is O(total nodes)):
+ * only the rows that changed since the last call with clear != 0 -- new nodes, nodes that got a child, leaves that became
+ * SURFACE and their parents.  ids i32[m] ascending (m = nl_octree_dirty_count), the three arrays hold row ids[o] at row o, in the
+ * hot-path layout of nl_octree_export_map.  Rows never move (row = node id), so scattering them into the previous export
+ * reproduces a full export bit for bit. */
+NL_API int64_t nl_octree_dirty_count(const nl_octree *t);
+NL_API int nl_octree_export_dirty(nl_octree *t, int32_t *h_ids, float *h_centres, int32_t *h_structure, int32_t *h_vertex, int clear);
 NL_API int64_t nl_octree_get_voxels(const nl_octree *t, float *h_out, int64_t cap_rows);       /* get_voxels      octree.cpp:228-252 : [n,4] preorder */
 NL_API int64_t nl_octree_get_leaf_voxels(const nl_octree *t, float *h_out, int64_t cap_rows);  /* get_leaf_voxels octree.cpp:212-226 : [n,3] */
 NL_API uint64_t nl_morton_encode(int x, int y, int z);                                         /* svo.encode      utils.h:106-109    */
@@ -74,6 +81,11 @@ NL_API uint64_t nl_morton_encode(int x, int y, int z);                          
  * per distinct vertex id, numbered by first appearance in vertex.reshape(-1)).  vertex2row i32[n_nodes]
  * (-1 = no row yet) is updated in place; returns the new number of rows (>= n_rows_before). */
 NL_API int64_t nl_assign_embedding_rows(const int32_t *h_vertex, int64_t n_nodes, int32_t *h_vertex2row, int64_t n_rows_before);
+/* The same over a subset of vertex rows (the dirty rows of nl_octree_export_dirty, ascending node id -- which is the order in
+ * which a full pass meets the not-yet-numbered vertices, so the numbering is identical); also writes the composed
+ * voxel -> embedding-row table for those rows, vox2row_rows i32[n_rows_in, 8]. */
+NL_API int64_t nl_assign_embedding_rows_subset(const int32_t *h_vertex_rows, int64_t n_rows_in, int64_t n_nodes, int32_t *h_vertex2row,
+                                        int64_t n_rows_before, int32_t *h_vox2row_rows);
 
 /* ============================================================================================
  * 2. Drop-ins for the two live `grid` kernels (third_party/sparse_voxels/src/binding.cpp:12-20)
@@ -166,6 +178,9 @@ NL_API int64_t nl_render_workspace_bytes(int32_t n_rays);
  * Requires what the reference's octree guarantees: a child's side is half its parent's. */
 NL_API int64_t nl_octree_packed_bytes(int32_t n_nodes);
 NL_API int nl_octree_pack_children(int32_t n_nodes, const float *d_centres, const int32_t *d_structure, void *d_packed, void *stream);
+/* re-pack only the listed nodes (d_ids i32[n_ids]: the dirty rows of an incremental map update) */
+NL_API int nl_octree_pack_children_rows(int32_t n_ids, const int32_t *d_ids, const float *d_centres, const int32_t *d_structure, void *d_packed,
+                                 void *stream);
 NL_API int nl_render_samples(const nl_render_args *args, void *stream);
 
 /* ============================================================================================
@@ -292,6 +307,29 @@ NL_API int nl_adam_bf16_ctl(int64_t n, uint16_t *d_param, const float *d_grad_f3
 NL_API int nl_stats_pack(const nl_render_stats *d_stats, void *d_buf, int rank, int world, int phase, void *stream);
 /* phase 0 also re-derives the loss constants (nl_loss_prepare) from the now global statistics */
 NL_API int nl_stats_unpack(nl_render_stats *d_stats, const void *d_buf, int world, int phase, float fs_weight, float sdf_weight, void *stream);
+
+
+/* ============================================================================================
+ * 10. Sparse marching cubes over the per-voxel SDF lattices of get_scores -- replaces MeshExtractor.marching_cubes
+ *     (src/utils/mesh_util.py:145-169: a Python loop calling skimage.measure.marching_cubes once per voxel on the host).
+ *     d_sdf f32[n_vox, res, res, res] (lattice point (i,j,k) of voxel v at ((v*res + i)*res + j)*res + k, the layout of
+ *     get_scores, render_helpers.py:97-153); level 0.  Like skimage the mesh of a voxel is welded (one vertex per crossed
+ *     lattice edge); voxels are independent (vertices on shared voxel faces are not merged, exactly like the reference's loop,
+ *     which offsets each voxel's faces by the running vertex count, mesh_util.py:160-163).
+ *     Two calls: nl_mc_count fills per-voxel counts, their exclusive scans and d_totals = {n_vertices, n_triangles} (int64[2]);
+ *     the caller allocates the outputs and calls nl_mc_emit.
+ *     vertex = ((lattice position) / (res - 1) - 0.5) * voxel_size + centres[vox_ids ? vox_ids[v] : v]   (mesh_util.py:149-161)
+ *     Triangles are wound so that the normal points towards increasing SDF.
+ * ============================================================================================ */
+NL_API int nl_mc_count(int32_t n_vox, int32_t res, const float *d_sdf, int32_t *d_nvert, int32_t *d_ntri, int32_t *d_voff, int32_t *d_toff,
+                int64_t *d_totals, void *stream);
+NL_API int nl_mc_emit(int32_t n_vox, int32_t res, float voxel_size, const float *d_sdf, const float *d_centres, const int32_t *d_vox_ids,
+               const int32_t *d_voff, const int32_t *d_toff, int64_t vert_capacity, int64_t tri_capacity, float *d_verts, int32_t *d_faces,
+               void *stream);
+/* The 256-case table the kernels use (host call, no GPU needed): tri u8[256][16] = up to 5 edge triples terminated by 255,
+ * ntri u8[256], edge_corner u8[12][2].  Corner i sits at (i&1, (i>>1)&1, (i>>2)&1); bit i of the case index is set when the
+ * SDF at corner i is negative.  The table is derived (face tracing), not hand-made; see csrc/mc.cu. */
+NL_API int nl_mc_case_table(uint8_t *h_tri, uint8_t *h_ntri, uint8_t *h_edge_corner);
 
 #ifdef __cplusplus
 }

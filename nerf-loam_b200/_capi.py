@@ -64,6 +64,10 @@ _SIGNATURES = {
     "nl_octree_has_voxel": (C.c_int, [vp, vp]),
     "nl_octree_export": (C.c_int, [vp, vp, vp, vp]),
     "nl_octree_export_map": (C.c_int, [vp, vp, vp, vp]),
+    "nl_octree_dirty_count": (C.c_int64, [vp]),
+    "nl_octree_export_dirty": (C.c_int, [vp, vp, vp, vp, vp, C.c_int]),
+    "nl_assign_embedding_rows_subset": (C.c_int64, [vp, C.c_int64, C.c_int64, vp, C.c_int64, vp]),
+    "nl_octree_pack_children_rows": (C.c_int, [C.c_int32, vp, vp, vp, vp, vp]),
     "nl_octree_get_voxels": (C.c_int64, [vp, vp, C.c_int64]),
     "nl_octree_get_leaf_voxels": (C.c_int64, [vp, vp, C.c_int64]),
     "nl_morton_encode": (C.c_uint64, [C.c_int, C.c_int, C.c_int]),
@@ -100,6 +104,9 @@ _SIGNATURES = {
     "nl_adam_bf16_ctl": (C.c_int, [C.c_int64, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, C.c_double, vp, vp]),
     "nl_stats_pack": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "nl_stats_unpack": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, vp]),
+    "nl_mc_count": (C.c_int, [C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp]),
+    "nl_mc_emit": (C.c_int, [C.c_int32, C.c_int32, C.c_float, vp, vp, vp, vp, vp, C.c_int64, C.c_int64, vp, vp, vp]),
+    "nl_mc_case_table": (C.c_int, [vp, vp, vp]),
 }
 
 # words of the device-side iteration control block (include/nerfloam_b200.h section 8)

@@ -70,13 +70,23 @@ struct nl_octree {
     std::vector<int8_t> type;
     std::unordered_set<uint64_t> corner_keys;  // all_keys (octree.h:118) -- used by try_insert only
     std::unordered_set<uint64_t> seen_points;
+    // Incremental export (nl_octree_export_dirty): ids of the nodes whose exported row may differ from the last export.  A row
+    // changes only when the node is created, when one of its child slots is filled, when a FEATURE leaf becomes SURFACE (its
+    // own row appears) or when one of its children does (the child id shows up in the parent's row, octree.cpp:333-337).
+    std::vector<int32_t> dirty;
+    std::vector<uint8_t> dirty_flag;
 
+    void mark(int32_t id) {
+        if (!dirty_flag[(size_t)id]) { dirty_flag[(size_t)id] = 1; dirty.push_back(id); }
+    }
     int32_t new_node(uint64_t c, uint32_t s, int8_t t) {
         int32_t id = (int32_t)type.size();
         child.insert(child.end(), 8, -1);
         code.push_back(c);
         side.push_back(s);
         type.push_back(t);
+        dirty_flag.push_back(0);
+        mark(id);
         return id;
     }
     int32_t find(int x, int y, int z) const {  // find_octant, octree.cpp:151-171
@@ -137,8 +147,11 @@ int nl_octree_insert(nl_octree *t, const int32_t *vox, int64_t n) {
                     const bool leaf = (d == t->max_level);
                     c = t->new_node(key & lvl_mask[d], edge, leaf ? (j == 0 ? kSurface : kFeature) : kNonLeaf);
                     t->child[(size_t)node * 8 + slot] = c;
+                    t->mark(node);
                 } else if (j == 0 && t->type[c] == kFeature) {
                     t->type[c] = kSurface;  // octree.cpp:102-106
+                    t->mark(c);
+                    t->mark(node);
                 }
                 node = c;
             }
@@ -175,11 +188,20 @@ int nl_octree_has_voxel(const nl_octree *t, const int32_t xyz[3]) {
     return t->find(xyz[0], xyz[1], xyz[2]) >= 0;
 }
 
+// exports node `i` into row `o` of the output arrays
+static void export_row(const nl_octree *t, int64_t i, int64_t o, float *voxels4, float *children_f, int32_t *children_i9, float *centres,
+                       int32_t *features);
+
 static void export_rows(const nl_octree *t, float *voxels4, float *children_f, int32_t *children_i9, float *centres,
                         int32_t *features) {
     const int64_t n = (int64_t)t->type.size();
+    for (int64_t i = 0; i < n; ++i) export_row(t, i, i, voxels4, children_f, children_i9, centres, features);
+}
+
+static void export_row(const nl_octree *t, int64_t i, int64_t o, float *voxels4, float *children_f, int32_t *children_i9, float *centres,
+                       int32_t *features) {
     const float vs = (float)t->voxel_size;
-    for (int64_t i = 0; i < n; ++i) {
+    {
         const bool visited = t->type[i] != kFeature;  // BFS reaches every non-FEATURE node (octree.cpp:330-338)
         float xyz[3] = {0.f, 0.f, 0.f}, sd = 0.f;
         if (visited) {
@@ -188,23 +210,23 @@ static void export_rows(const nl_octree *t, float *voxels4, float *children_f, i
             xyz[2] = (float)(int)squeeze3(t->code[i] >> 2);
             sd = (float)t->side[i];
         }
-        if (voxels4) { voxels4[i * 4 + 0] = xyz[0]; voxels4[i * 4 + 1] = xyz[1]; voxels4[i * 4 + 2] = xyz[2]; voxels4[i * 4 + 3] = sd; }
+        if (voxels4) { voxels4[o * 4 + 0] = xyz[0]; voxels4[o * 4 + 1] = xyz[1]; voxels4[o * 4 + 2] = xyz[2]; voxels4[o * 4 + 3] = sd; }
         if (centres) {  // mapping.py:322: (voxels[:, :3] + voxels[:, -1:] / 2) * voxel_size, all fp32
             const float h = sd / 2.0f;
-            for (int a = 0; a < 3; ++a) centres[i * 3 + a] = (xyz[a] + h) * vs;
+            for (int a = 0; a < 3; ++a) centres[o * 3 + a] = (xyz[a] + h) * vs;
         }
         for (int s = 0; s < 8; ++s) {
             const int32_t c = t->child[(size_t)i * 8 + s];
             const int32_t v = (visited && c >= 0 && t->type[c] != kFeature) ? c : -1;
-            if (children_f) children_f[i * 8 + s] = (float)v;
-            if (children_i9) children_i9[i * 9 + s] = v;
+            if (children_f) children_f[o * 8 + s] = (float)v;
+            if (children_i9) children_i9[o * 9 + s] = v;
         }
-        if (children_i9) children_i9[i * 9 + 8] = (int32_t)sd;  // mapping.py:323-326
+        if (children_i9) children_i9[o * 9 + 8] = (int32_t)sd;  // mapping.py:323-326
         for (int k = 0; k < 8; ++k) {
             int32_t f = -1;
             if (t->type[i] == kSurface)
                 f = t->find((int)(xyz[0] + (float)kIncX[k]), (int)(xyz[1] + (float)kIncY[k]), (int)(xyz[2] + (float)kIncZ[k]));
-            features[i * 8 + k] = f;
+            features[o * 8 + k] = f;
         }
     }
 }
@@ -218,6 +240,22 @@ int nl_octree_export(const nl_octree *t, float *voxels, float *children, int32_t
 int nl_octree_export_map(const nl_octree *t, float *centres, int32_t *structure, int32_t *vertex) {
     if (!t || !centres || !structure || !vertex) return nl_set_error("nl_octree_export_map: null argument");
     export_rows(t, nullptr, nullptr, structure, centres, vertex);
+    return NL_OK;
+}
+
+int64_t nl_octree_dirty_count(const nl_octree *t) { return t ? (int64_t)t->dirty.size() : -1; }
+
+int nl_octree_export_dirty(nl_octree *t, int32_t *ids, float *centres, int32_t *structure, int32_t *vertex, int clear) {
+    if (!t || !ids || !centres || !structure || !vertex) return nl_set_error("nl_octree_export_dirty: null argument");
+    std::sort(t->dirty.begin(), t->dirty.end());       // ascending node id: the order in which a full export lists them
+    for (size_t o = 0; o < t->dirty.size(); ++o) {
+        ids[o] = t->dirty[o];
+        export_row(t, t->dirty[o], (int64_t)o, nullptr, nullptr, structure, centres, vertex);
+    }
+    if (clear) {
+        for (int32_t id : t->dirty) t->dirty_flag[(size_t)id] = 0;
+        t->dirty.clear();
+    }
     return NL_OK;
 }
 
@@ -257,6 +295,18 @@ int64_t nl_assign_embedding_rows(const int32_t *vertex, int64_t n_nodes, int32_t
     for (int64_t i = 0; i < n_nodes * 8; ++i) {
         const int32_t v = vertex[i];
         if (v >= 0 && v < n_nodes && vertex2row[v] < 0) vertex2row[v] = (int32_t)n_rows++;
+    }
+    return n_rows;
+}
+
+int64_t nl_assign_embedding_rows_subset(const int32_t *vertex_rows, int64_t n_rows_in, int64_t n_nodes, int32_t *vertex2row, int64_t n_rows,
+                                        int32_t *vox2row_rows) {
+    if (!vertex_rows || !vertex2row || !vox2row_rows || n_rows_in < 0 || n_nodes < 0 || n_rows < 0)
+        return nl_set_error("nl_assign_embedding_rows_subset: bad arguments");
+    for (int64_t i = 0; i < n_rows_in * 8; ++i) {
+        const int32_t v = vertex_rows[i];
+        if (v >= 0 && v < n_nodes && vertex2row[v] < 0) vertex2row[v] = (int32_t)n_rows++;
+        vox2row_rows[i] = (v >= 0 && v < n_nodes) ? vertex2row[v] : -1;
     }
     return n_rows;
 }

@@ -245,13 +245,14 @@ __global__ void __launch_bounds__(256) k_traverse_coop(int R, float voxel_size, 
     }
 }
 
-__global__ void k_pack_children(int n_nodes, const float *__restrict__ centres, const int32_t *__restrict__ structure,
-                                float4 *__restrict__ packed) {
+__global__ void k_pack_children(int n_nodes, const int32_t *__restrict__ ids, const float *__restrict__ centres,
+                                const int32_t *__restrict__ structure, float4 *__restrict__ packed) {
     // one thread per node: the existing children compacted to the front of the node's 8 records (terminated by id -1), in
     // ascending slot order for inner nodes (push order) and DESCENDING slot order for nodes of side 2, whose children are
     // leaves and are recorded in the order the reference pops them
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= n_nodes) return;
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_nodes) return;
+    const int n = ids ? ids[slot] : slot;        // ids: re-pack only the listed nodes (incremental map update)
     const int32_t *st = structure + (size_t)n * 9;
     const bool leaf_parent = st[8] == 2;
     float4 *rec = packed + (size_t)n * 8;
@@ -665,8 +666,19 @@ extern "C" int nl_octree_pack_children(int32_t n_nodes, const float *d_centres, 
     if (n_nodes >= (1 << 26)) return nl_set_error("nl_octree_pack_children: at most 2^26 nodes (the traversal stack packs id and level)");
     if (!d_centres || !d_structure || !d_packed) return nl_set_error("nl_octree_pack_children: null pointer");
     if (((uintptr_t)d_packed & 15u) != 0) return nl_set_error("nl_octree_pack_children: d_packed must be 16-byte aligned");
-    k_pack_children<<<nl_div_up(n_nodes, 128), 128, 0, (cudaStream_t)stream>>>(n_nodes, d_centres, d_structure, (float4 *)d_packed);
+    k_pack_children<<<nl_div_up(n_nodes, 128), 128, 0, (cudaStream_t)stream>>>(n_nodes, nullptr, d_centres, d_structure, (float4 *)d_packed);
     NL_CHECK_LAUNCH("nl_octree_pack_children");
+    return NL_OK;
+}
+
+extern "C" int nl_octree_pack_children_rows(int32_t n_ids, const int32_t *d_ids, const float *d_centres, const int32_t *d_structure, void *d_packed,
+                                            void *stream) {
+    if (n_ids < 0) return nl_set_error("nl_octree_pack_children_rows: negative count");
+    if (n_ids == 0) return NL_OK;
+    if (!d_ids || !d_centres || !d_structure || !d_packed) return nl_set_error("nl_octree_pack_children_rows: null pointer");
+    if (((uintptr_t)d_packed & 15u) != 0) return nl_set_error("nl_octree_pack_children_rows: d_packed must be 16-byte aligned");
+    k_pack_children<<<nl_div_up(n_ids, 128), 128, 0, (cudaStream_t)stream>>>(n_ids, d_ids, d_centres, d_structure, (float4 *)d_packed);
+    NL_CHECK_LAUNCH("nl_octree_pack_children_rows");
     return NL_OK;
 }
 

@@ -109,6 +109,8 @@ class MapState:
         """Traversal image of the octree (nl_octree_pack_children), built once per map version."""
         if getattr(self, "_packed", None) is None:
             self._packed = pack_children(self.centres, self.structure)
+            if getattr(self, "_cache_ref", None) is not None:
+                self._cache_ref["packed"] = self._packed
         return self._packed
 
     @staticmethod
@@ -125,7 +127,8 @@ class MapState:
         def h(t, dtype):
             a = t.detach().to(device="cpu", dtype=dtype).contiguous().numpy()
             return zlib.crc32(memoryview(a).cast("B"))
-        return (n, h(vidx, torch.int32), h(map_states["voxel_structure"], torch.int32), h(map_states["voxel_center_xyz"], torch.float32),
+        stru = map_states.get("voxel_structure")      # absent in the encoder_states dict of Mapping.extract_mesh (mapping.py:363-371)
+        return (n, h(vidx, torch.int32), h(stru, torch.int32) if stru is not None else -1, h(map_states["voxel_center_xyz"], torch.float32),
                 int(map_states["voxel_id2embedding_id"].shape[0]))
 
     @classmethod
@@ -141,14 +144,17 @@ class MapState:
             v = map_states["voxel_vertex_idx"].detach().cpu().long()
             flat = map_states["voxel_id2embedding_id"].detach().cpu().reshape(-1)
             rows = torch.where(v >= 0, flat[v.clamp(min=0)].long(), torch.full_like(v, -1))
+            stru = map_states.get("voxel_structure")
+            if stru is None:      # meshing-only dict (mapping.py:363-371): rows are SURFACE voxels, nothing is ever traversed
+                stru = torch.cat([torch.full((v.shape[0], 8), -1, dtype=torch.int32), torch.ones((v.shape[0], 1), dtype=torch.int32)], 1)
             cls._cache = {"key": key, "vox2row": rows.to(torch.int32).to(device).contiguous(),
                           "centres": map_states["voxel_center_xyz"].detach().to(device=device, dtype=torch.float32).contiguous(),
-                          "structure": map_states["voxel_structure"].detach().to(device=device, dtype=torch.int32).contiguous()}
-            cls._cache["packed"] = pack_children(cls._cache["centres"], cls._cache["structure"])
+                          "structure": stru.detach().to(device=device, dtype=torch.int32).contiguous(), "packed": None}
         c = cls._cache
         obj = cls.__new__(cls)
         obj.centres, obj.structure, obj.vox2row = c["centres"], c["structure"], c["vox2row"]
         obj._packed = c["packed"]
+        obj._cache_ref = c                     # packed_children() stores the traversal image back into the shared cache entry
         emb = map_states["voxel_vertex_emb"]
         obj.emb = emb.detach() if (emb.is_cuda and emb.dtype == torch.bfloat16 and emb.is_contiguous()) else \
             emb.detach().to(device=device, dtype=torch.bfloat16).contiguous()

@@ -165,39 +165,59 @@ def render_rays(rays_o, rays_d, map_states, sdf_network, step_size, voxel_size, 
             "sampled_xyz": pack["xyz"]}
 
 
+def _lattice_offsets(res, voxel_size, dev):
+    lin = torch.linspace(-0.5, 0.5, res)                      # render_helpers.py:109-117
+    xx, yy, zz = torch.meshgrid(lin, lin, lin, indexing="ij")
+    return (torch.stack([xx, yy, zz], dim=-1).float().to(dev) * voxel_size).reshape(1, -1, 3)
+
+
 @torch.no_grad()
-def get_scores(sdf_network, map_states, voxel_size, bits=8):
-    """render_helpers.py:97-153: SDF on a res^3 lattice inside every voxel -> f32[n,res,res,res,1] (CPU)."""
+def scores_device(sdf_network, map_states, voxel_size, bits=8, nodes=None, chunk=65536):
+    """SDF on the res^3 lattice of the given octree nodes (default: every node that owns embeddings, i.e. the SURFACE leaves)
+    -> (f32[len(nodes), res^3] on the device, nodes i64).  Same arithmetic as get_scores_once (render_helpers.py:104-146): lattice
+    point = centre + linspace(-0.5, 0.5, res) * voxel_size, trilinear gather, decoder forward.  No host synchronisation."""
     dev = torch.device("cuda")
     m = map_states if isinstance(map_states, MapState) else MapState.from_map_states(map_states, dev)
-    res = bits
-    lin = torch.linspace(-0.5, 0.5, res)
-    xx, yy, zz = torch.meshgrid(lin, lin, lin, indexing="ij")
-    offs = (torch.stack([xx, yy, zz], dim=-1).float().to(dev) * voxel_size).reshape(1, -1, 3)
+    res = int(bits)
+    if nodes is None:
+        nodes = (m.vox2row[:, 0] >= 0).nonzero().view(-1)
+    offs = _lattice_offsets(res, voxel_size, dev)
     bufs = DecoderBuffers(sdf_network, dev)
     bufs.refresh_transposes()
-    n = m.n_nodes
-    out = []
-    chunk = 10000
-    import ctypes as C
-    for i in range(0, n, chunk):
-        c = m.centres[i:i + chunk]
-        xyz = (offs + c.unsqueeze(1)).reshape(-1, 3).contiguous()
-        vox = torch.arange(i, i + c.shape[0], device=dev, dtype=torch.int32)[:, None].expand(-1, res ** 3).reshape(-1).contiguous()
+    out = torch.empty((nodes.shape[0], res ** 3), dtype=torch.float32, device=dev)
+    chunk = max(1, chunk // (res ** 3) * 8)                   # voxels per launch (~0.5 M lattice points)
+    for i in range(0, nodes.shape[0], chunk):
+        idx = nodes[i:i + chunk]
+        xyz = (offs + m.centres[idx].unsqueeze(1)).reshape(-1, 3).contiguous()
+        vox = idx.to(torch.int32)[:, None].expand(-1, res ** 3).reshape(-1).contiguous()
         M = xyz.shape[0]
-        if M == 0:
-            continue
         feats = torch.empty((M, 16), dtype=torch.float32, device=dev)
-        sdf = torch.empty(M, dtype=torch.float32, device=dev)
-        # voxels without embeddings (interior / FEATURE rows) have vox2row = -1: they are never meshed (mesh_util only
-        # uses SURFACE voxels); the gather treats a missing row as zeros
         _capi.check(_capi.lib().nl_gather_trilinear_fwd(M, None, _capi.ptr(xyz), _capi.ptr(vox), _capi.ptr(m.centres),
                                                         _capi.ptr(m.vox2row), _capi.ptr(m.emb), float(voxel_size), _capi.ptr(feats),
                                                         _capi.stream_ptr()), "nl_gather_trilinear_fwd")
         _capi.LAUNCHES += 1
-        mlp_forward(bufs, M, None, feats, sdf)
-        out.append(sdf.reshape(-1, res ** 3, 1).cpu())
-    return torch.cat(out, 0).view(-1, res, res, res, 1)
+        mlp_forward(bufs, M, None, feats, out[i:i + idx.shape[0]].view(-1))
+    return out, nodes
+
+
+@torch.no_grad()
+def get_scores(sdf_network, map_states, voxel_size, bits=8):
+    """render_helpers.py:97-153: SDF on a res^3 lattice inside every voxel -> f32[n,res,res,res,1] (CPU).
+    Nodes without embeddings (interior nodes, FEATURE-only leaves: vox2row = -1) gather an all-zero feature vector, so their whole
+    lattice is the single value decoder(0) (the reference evaluates all res^3 points of each of them to get that constant): it is
+    evaluated once and broadcast.  One device -> host copy at the end instead of one blocking .cpu() per 10 k-voxel chunk."""
+    dev = torch.device("cuda")
+    m = map_states if isinstance(map_states, MapState) else MapState.from_map_states(map_states, dev)
+    res = int(bits)
+    lat, nodes = scores_device(sdf_network, m, voxel_size, res)
+    bufs = DecoderBuffers(sdf_network, dev)
+    bufs.refresh_transposes()
+    zero = torch.zeros((1, 16), dtype=torch.float32, device=dev)
+    const = torch.empty(1, dtype=torch.float32, device=dev)
+    mlp_forward(bufs, 1, None, zero, const)
+    full = const.expand(m.n_nodes, res ** 3).clone()
+    full[nodes] = lat
+    return full.cpu().view(-1, res, res, res, 1)
 
 
 # ======================================================================================================
@@ -274,6 +294,10 @@ class _MapGraph:
         R = F * N_rays
         eng = SDFEngine(R, R * spr, dev)            # private: captured pointers must stay valid
         bufs = DecoderBuffers(sdf_network, dev)
+        mg = MapState.__new__(MapState)              # the map as the graph sees it: same arrays, the table at the size that is optimised
+        mg.__dict__.update(m.__dict__)
+        mg.emb = emb
+        m = mg
         self.key, self.eng, self.bufs, self.m, self.emb, self.F, self.N, self.cap = key, eng, bufs, m, emb, F, N_rays, cap
         self.packed = m.packed_children()
         self.dirs = torch.tensor([0.0, 0.0, -1.0], device=dev).repeat(F, cap, 1).contiguous()
@@ -330,9 +354,16 @@ class _MapGraph:
     @classmethod
     def get(cls, m, emb, sdf_network, cfg, F, N_rays, lrs, update_decoder, pose_rows, deterministic, n_points, spr):
         cap = max(1 << 17, 1 << (int(n_points) - 1).bit_length())
+        stable = getattr(m, "stable", False)
+        if stable and getattr(m, "emb_full", None) is not None and emb.data_ptr() == m.emb_full.data_ptr():
+            # a mapping.MapUpdater map: every array sits in a capacity-sized buffer at a fixed address, so the captured graph stays
+            # valid across map updates; the table is optimised at its full capacity (rows not yet handed out are zero, receive zero
+            # gradients and therefore do not move under Adam)
+            emb = m.emb_full
         key = (F, N_rays, tuple(float(x) for x in lrs), bool(update_decoder), tuple(pose_rows), bool(deterministic), cap, int(spr),
                m.centres.data_ptr(), m.structure.data_ptr(), m.vox2row.data_ptr(), m.packed_children().data_ptr(), emb.data_ptr(),
-               m.n_nodes, int(emb.shape[0]), tuple(p.data_ptr() for p in _decoder_params(sdf_network)), tuple(sorted(cfg.items())))
+               -1 if stable else m.n_nodes, int(emb.shape[0]), tuple(p.data_ptr() for p in _decoder_params(sdf_network)),
+               tuple(sorted(cfg.items())))
         g = cls._cache.get("g")
         if g is None or g.key != key:
             cls._cache = {}
@@ -430,7 +461,9 @@ def bundle_adjust_frames(keyframe_graph, embeddings, map_states, sdf_network, lo
     graph_ok = ray_selection == "device" and noise_per_iter is None and loss_log is None and \
         all(f.points.shape[0] >= N_rays for f in frames) and os.environ.get("NL_MAP_GRAPH", "1") != "0"
     if cuda_graph is None:
-        cuda_graph = graph_ok
+        # automatic only for maps whose arrays keep their addresses across map updates (mapping.MapUpdater): a capture costs about
+        # as much as 1.5 eager calls, so re-capturing for every new map (the reference's per-frame dicts) would be a net loss
+        cuda_graph = graph_ok and getattr(m, "stable", False)
     elif cuda_graph and not graph_ok:
         raise ValueError("cuda_graph=True needs ray_selection='device', no per-iteration host inputs/outputs and >= N_rays points per scan")
     cap = R * SAMPLES_PER_RAY_MAP
@@ -525,8 +558,9 @@ class _TrackGraph:
     @classmethod
     def get(cls, m, sdf_network, cfg, N_rays, lr, deterministic, n_points, samples_per_ray=64):
         cap = max(1 << 17, 1 << (int(n_points) - 1).bit_length())
+        stable = getattr(m, "stable", False)      # mapping.MapUpdater map: fixed base addresses, the graph survives map updates
         key = (N_rays, float(lr), bool(deterministic), cap, int(samples_per_ray), m.centres.data_ptr(), m.structure.data_ptr(), m.vox2row.data_ptr(),
-               m.packed_children().data_ptr(), m.emb.data_ptr(), m.n_nodes, int(m.emb.shape[0]),
+               m.packed_children().data_ptr(), m.emb.data_ptr(), -1 if stable else m.n_nodes, -1 if stable else int(m.emb.shape[0]),
                tuple(p.data_ptr() for p in _decoder_params(sdf_network)), tuple(sorted(cfg.items())))
         g = cls._cache.get("g")
         if g is None or g.key != key:
@@ -597,8 +631,9 @@ def track_frame(frame_pose, curr_frame, map_states, sdf_network, loss_criteria, 
     if ray_selection not in ("host", "device"):
         raise ValueError("ray_selection must be 'host' or 'device'")
     graph_ok = ray_selection == "device" and noise_per_iter is None and loss_log is None and curr_frame.points.shape[0] >= N_rays
-    if cuda_graph is None:          # default: the fast path whenever nothing asks for per-iteration host interaction
-        cuda_graph = graph_ok and os.environ.get("NL_TRACK_GRAPH", "1") != "0"
+    if cuda_graph is None:          # default: the captured path for maps with stable addresses (mapping.MapUpdater), see bundle_adjust_frames
+        stable = getattr(map_states, "stable", False) or getattr(map_states.get("_mapstate") if isinstance(map_states, dict) else None, "stable", False)
+        cuda_graph = graph_ok and stable and os.environ.get("NL_TRACK_GRAPH", "1") != "0"
     if cuda_graph:
         if not graph_ok:
             raise ValueError("cuda_graph=True needs ray_selection='device', no per-iteration host inputs/outputs and >= N_rays points")

@@ -124,6 +124,24 @@ class Octree:
                     "nl_octree_export_map")
         return torch.from_numpy(centres), torch.from_numpy(structure), torch.from_numpy(vertex)
 
+    def export_dirty(self, clear=True):
+        """Incremental export: (ids i32[m] ascending, centres f32[m,3], structure i32[m,9], vertex i32[m,8]) of the rows that
+        changed since the last clearing call -- scattering them into the previous export gives the full export bit for bit."""
+        self._check()
+        m = int(_capi.lib().nl_octree_dirty_count(self._h))
+        ids = np.empty(m, np.int32)
+        centres = np.empty((m, 3), np.float32)
+        structure = np.empty((m, 9), np.int32)
+        vertex = np.empty((m, 8), np.int32)
+        _capi.check(_capi.lib().nl_octree_export_dirty(self._h, ids.ctypes.data_as(C.c_void_p), centres.ctypes.data_as(C.c_void_p),
+                                                       structure.ctypes.data_as(C.c_void_p), vertex.ctypes.data_as(C.c_void_p), int(bool(clear))),
+                    "nl_octree_export_dirty")
+        return ids, centres, structure, vertex
+
+    def count_export_nodes(self):
+        self._check()
+        return int(_capi.lib().nl_octree_count_export_nodes(self._h))
+
     # -- pickle (bindings.cpp:23-31): state = (size, feat_dim, voxel_size, all inserted tensors), replayed on load
     def __getstate__(self):
         return {"init": self._init_args, "all_pts": self._all_pts}

@@ -289,3 +289,38 @@ def test_c_abi_rejects_bad_arguments_without_touching_the_gpu(nl):
     assert L.nl_octree_create(0, 16, 0.3) is None and err() != ""                                        # grid_dim must be positive
     with pytest.raises(nl._capi.NerfLoamError):
         nl._capi.check(L.nl_svo_intersect(1, 1, 1, 0.3, 20, None, None, None, None, None, None, None, None), "nl_svo_intersect")
+
+
+def test_incremental_octree_export_equals_full_export():
+    """nl_octree_export_dirty: scattering only the rows an insertion touched into the previous export reproduces the
+    full export bit for bit, and the incremental vertex numbering equals the full-pass numbering."""
+    import ctypes as C
+    import nerfloam_b200 as nl
+    syn = nl.synthetic
+    o = nl.svo.Octree(); o.init(256 * 256 * 4, 16, 0.3)
+    acc = [np.zeros((0, 3), np.float32), np.zeros((0, 9), np.int32), np.zeros((0, 8), np.int32)]
+    v2r_inc, v2r_full, rows_inc, rows_full = np.full(0, -1, np.int32), np.full(0, -1, np.int32), 0, 0
+    touched = []
+    for i in range(4):
+        pts, cos, pose = syn.make_scan(n_beams=16, n_az=150, seed=50 + i, sensor_xyz=(1.0 * i, 0.2 * i, 0.0))
+        o.insert(torch.from_numpy(syn.voxelize(pts, pose, 0.3)))
+        ids, c, s, v = o.export_dirty()
+        n = o.count_export_nodes()
+        assert np.all(np.diff(ids) > 0) and o.export_dirty()[0].shape[0] == 0            # ascending, and cleared by the call
+        k = acc[0].shape[0]
+        acc = [np.concatenate([acc[0], np.zeros((n - k, 3), np.float32)]), np.concatenate([acc[1], np.full((n - k, 9), -1, np.int32)]),
+               np.concatenate([acc[2], np.full((n - k, 8), -1, np.int32)])]
+        acc[0][ids], acc[1][ids], acc[2][ids] = c, s, v
+        fc, fs, fv = [t.numpy() for t in o.export_map()]
+        assert np.array_equal(acc[0], fc) and np.array_equal(acc[1], fs) and np.array_equal(acc[2], fv)
+        touched.append(ids.shape[0])
+        v2r_inc = np.concatenate([v2r_inc, np.full(n - v2r_inc.shape[0], -1, np.int32)])
+        v2r_full = np.concatenate([v2r_full, np.full(n - v2r_full.shape[0], -1, np.int32)])
+        sub = np.empty((ids.shape[0], 8), np.int32)
+        rows_inc = nl._capi.lib().nl_assign_embedding_rows_subset(v.ctypes.data_as(C.c_void_p), ids.shape[0], n, v2r_inc.ctypes.data_as(C.c_void_p),
+                                                                  rows_inc, sub.ctypes.data_as(C.c_void_p))
+        rows_full = nl._capi.lib().nl_assign_embedding_rows(fv.ctypes.data_as(C.c_void_p), n, v2r_full.ctypes.data_as(C.c_void_p), rows_full)
+        assert rows_inc == rows_full and np.array_equal(v2r_inc, v2r_full)
+        assert np.array_equal(sub, np.where(v >= 0, v2r_full[np.clip(v, 0, None)], -1))
+    assert touched[0] == acc[0].shape[0] - sum(0 for _ in ()) or touched[0] > 0
+    assert all(t < 0.6 * acc[0].shape[0] for t in touched[1:])                            # later scans touch a fraction of the tree
