@@ -18,7 +18,7 @@ no CPU or eager-PyTorch fallback for the kernels.
 """
 from . import _capi  # noqa: F401
 
-__all__ = ["svo", "grid", "lidar", "criterion", "se3pose", "frame", "render_helpers", "mapping", "engine", "synthetic", "dist", "dropin", "mesh"]
+__all__ = ["svo", "grid", "lidar", "criterion", "se3pose", "frame", "render_helpers", "mapping", "engine", "synthetic", "dist", "dropin", "mesh", "share"]
 
 
 def __getattr__(name):

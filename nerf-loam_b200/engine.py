@@ -128,8 +128,10 @@ class MapState:
             a = t.detach().to(device="cpu", dtype=dtype).contiguous().numpy()
             return zlib.crc32(memoryview(a).cast("B"))
         stru = map_states.get("voxel_structure")      # absent in the encoder_states dict of Mapping.extract_mesh (mapping.py:363-371)
+        # the id table is hashed over the entries a vertex id can address (vertex ids are node ids < n; the reference allocates 2e9)
+        id2 = map_states["voxel_id2embedding_id"].detach().reshape(-1)
         return (n, h(vidx, torch.int32), h(stru, torch.int32) if stru is not None else -1, h(map_states["voxel_center_xyz"], torch.float32),
-                int(map_states["voxel_id2embedding_id"].shape[0]))
+                int(id2.shape[0]), h(id2[:max(n, int(vidx.max()) + 1 if vidx.numel() else 0)], torch.int32))
 
     @classmethod
     def from_map_states(cls, map_states, device="cuda"):

@@ -64,6 +64,9 @@ class Decoder(nn.Module):
             raise NotImplementedError("fused decoder supports depth=2, skips=[], in_dim=16, width in {32,64,128,256} "
                                       f"(got depth={depth}, skips={skips}, in_dim={in_dim}, width={width})")
         self.D, self.W, self.skips, self.point_dim = depth, width, list(skips), point_dim
+        # how to rebuild this module on the other side of a hand-off (share.ShareData sends the parameters as one flat device tensor)
+        self.ctor_kwargs = dict(depth=depth, width=width, in_dim=in_dim, sdf_dim=sdf_dim, skips=list(skips), multires=multires, embedder=embedder,
+                                point_dim=point_dim, local_coord=local_coord)
         self.pe = Same(in_dim)
         self.pts_linears = nn.ModuleList([nn.Linear(in_dim, width)] + [nn.Linear(width, width) for _ in range(depth - 1)])
         self.sdf_out = nn.Linear(width, 1)

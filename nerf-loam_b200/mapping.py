@@ -50,6 +50,7 @@ class MapUpdater:
         self._host = None            # host mirrors (centres, structure, vertex) for the reference-format dict
         self.generation = 0
         self.last_update = {}
+        self.readers = None          # optional share.SharedMap: in-place updates wait (on the stream) for its readers
 
     @property
     def embeddings(self):
@@ -111,6 +112,9 @@ class MapUpdater:
             raise _capi.NerfLoamError(_capi.lib().nl_last_error().decode())
         self._grow_rows(new_rows)
         self._grow_nodes(n)
+        if self.readers is not None:      # a tracker on another stream may still traverse the arrays that are patched below
+            for ev in self.readers.reader_events():
+                torch.cuda.current_stream(self.device).wait_event(ev)
         if m:
             d = self.device
             idx = torch.from_numpy(ids).to(d, non_blocking=True)

