@@ -402,6 +402,11 @@ def run_ours(args):
                                  "track_frame_2048x25_cuda_graph": (rg["track_frame_2048x25"]["ms_per_scan"] / track["ms_per_scan_cuda_graph"]) if track and "ms_per_scan" in track else None}
         except Exception as exc:
             out["reference_gpu"] = {"error": repr(exc)}
+    if world == 1 and not os.environ.get("NL_BENCH_SKIP_CONFIGS"):
+        try:
+            out["configs"] = configs_real_size(nl, dev)
+        except Exception as exc:
+            out["configs"] = {"error": repr(exc)}
     if world == 1 and not os.environ.get("NL_BENCH_SKIP_CPU"):
         out["cpu_baseline"] = best_cpu_baseline(n_rays=4096, iters=3)
     print(json.dumps(out))
@@ -632,6 +637,67 @@ def ours_real_size(nl, dev, window_scans, ms, dec):
         res["ms_per_call_%s" % name] = (time.perf_counter() - t0) / 3 * 1e3
     res.update(frames=len(frames), rays_per_frame=2048, iterations=25)
     return res
+
+
+# BASELINE.json configs 1-3 at their real iteration sizes (configs/maicity/maicity.yaml, configs/kitti/kitti.yaml, configs/ncd/ncd.yaml):
+# window of keyframes x 2048 rays through the drop-in bundle_adjust_frames / track_frame on a map grown incrementally, + mesh extraction
+REAL_CONFIGS = {
+    "config1_maicity": dict(voxel=0.2, map_step=0.5, map_it=20, track_step=0.2, track_it=20, track_lr=0.06, window=5, max_depth=50.0, min_depth=1.5, lr=(0.01, 0.005, 0.001)),
+    "config2_kitti": dict(voxel=0.3, map_step=0.5, map_it=25, track_step=0.2, track_it=25, track_lr=0.06, window=5, max_depth=40.0, min_depth=5.0, lr=(0.01, 0.005, 0.001)),
+    "config3_newer_college": dict(voxel=0.2, map_step=0.2, map_it=15, track_step=0.1, track_it=30, track_lr=0.04, window=6, max_depth=40.0, min_depth=1.0, lr=(0.002, 0.005, 0.001)),
+}
+
+
+def configs_real_size(nl, dev):
+    from types import SimpleNamespace
+    syn = nl.synthetic
+    out = {}
+    for name, c in REAL_CONFIGS.items():
+        vs = c["voxel"]
+        crit = nl.criterion.Criterion(SimpleNamespace(criteria={"eiko_weight": 0.1, "sdf_weight": 10000.0, "fs_weight": 1.0, "sdf_truncation": 0.3},
+                                                      data_specs={"max_depth": c["max_depth"]}))
+        scans = [syn.make_scan(seed=900 + i, sensor_xyz=(1.0 * i, 0.0, 0.0), min_depth=c["min_depth"], max_depth=c["max_depth"]) for i in range(c["window"])]
+        mu = nl.mapping.MapUpdater(vs, init_std=0.01, seed=777, device=dev)
+        t_upd = []
+        for pts, cos, pose in scans:
+            vox = torch.from_numpy(syn.voxelize(pts, pose, vs))
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            ms = mu.insert_voxels(vox)
+            torch.cuda.synchronize(); t_upd.append((time.perf_counter() - t0) * 1e3)
+        torch.manual_seed(777)
+        dec = nl.lidar.Decoder(depth=2, width=256, in_dim=16, skips=[], embedder="none", multires=0).to(dev)
+        frames = [nl.frame.LidarFrame(i, torch.from_numpy(p), torch.from_numpy(cs), nl.se3pose.OptimizablePose.from_matrix(torch.from_numpy(T.copy())), new_keyframe=True)
+                  for i, (p, cs, T) in enumerate(scans)]
+
+        def ba():
+            nl.render_helpers.bundle_adjust_frames(frames, mu.embeddings, ms, dec, crit, vs, c["map_step"] * vs, N_rays=2048, num_iterations=c["map_it"],
+                                                   truncation=0.3, max_voxel_hit=20, max_distance=c["max_depth"], learning_rate=list(c["lr"]))
+
+        def tk():
+            return nl.render_helpers.track_frame(frames[-1].pose, frames[-1], ms, dec, crit, vs, N_rays=2048, step_size=c["track_step"] * vs,
+                                                 num_iterations=c["track_it"], truncation=0.3, learning_rate=c["track_lr"], max_voxel_hit=20,
+                                                 max_distance=c["max_depth"])
+        res = {}
+        for key, fn, n in (("bundle_adjust_frames_ms", ba, 3), ("track_frame_ms", tk, 5)):
+            fn(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                fn()
+            torch.cuda.synchronize()
+            res[key] = (time.perf_counter() - t0) / n * 1e3
+        nl.mesh.extract_mesh(dec, ms, vs, res=8); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        v, f = nl.mesh.extract_mesh(dec, ms, vs, res=8)
+        torch.cuda.synchronize()
+        res.update(extract_mesh_res8_ms=(time.perf_counter() - t0) * 1e3, mesh_vertices=int(v.shape[0]), mesh_triangles=int(f.shape[0]),
+                   map_update_ms=[round(x, 2) for x in t_upd], octree_nodes=ms.n_nodes, last_update_dirty_rows=mu.last_update.get("dirty_rows"),
+                   frames=len(frames), mapping_iterations=c["map_it"], tracking_iterations=c["track_it"], rays_per_frame=2048)
+        out[name] = res
+        del mu, ms, dec, frames
+        torch.cuda.empty_cache()
+    out["note"] = ("default drop-in paths: device-side ray selection, captured CUDA graph on the MapUpdater's stable buffers; wall clock per call; "
+                   "map_update_ms = incremental octree insert + dirty-row export + device patch per scan; synthetic 64x1563-beam scans 1 m apart")
+    return out
 
 
 def cpu_baseline(n_rays=4096, iters=3, threads=None):

@@ -390,7 +390,7 @@ def test_incremental_map_update_equals_full_and_graphs_survive_it(nl):
     syn = nl.synthetic
     rh = nl.render_helpers
     scans = [syn.make_scan(n_beams=16, n_az=160, seed=300 + i, sensor_xyz=(0.8 * i, 0.1 * i, 0.0)) for i in range(4)]
-    inc = nl.mapping.MapUpdater(0.3, init_std=0.01, seed=3)
+    inc = nl.mapping.MapUpdater(0.3, init_std=0.01, seed=3, reserve_nodes=100_000, reserve_rows=100_000)
     ful = nl.mapping.MapUpdater(0.3, init_std=0.01, seed=3, incremental=False)
     torch.manual_seed(5)
     dec = nl.lidar.Decoder(depth=2, width=256, in_dim=16, skips=[], embedder="none", multires=0).cuda()
@@ -416,9 +416,8 @@ def test_incremental_map_update_equals_full_and_graphs_survive_it(nl):
             rh.bundle_adjust_frames(frames[-2:], inc.embeddings, a, dec, crit, 0.3, 0.15, N_rays=512, num_iterations=2, truncation=0.3,
                                     max_voxel_hit=20, max_distance=40.0, learning_rate=[0.01, 0.005, 0.001])
             graphs.append(rh._MapGraph._cache["g"])
-    assert len(ptrs) <= 2                                        # at most one capacity doubling while the map grew 2x
-    assert len({id(g) for g in graphs}) <= 2                     # captures are reused across map versions (a new one only after a doubling)
-    assert graphs[-1] is graphs[-2]
+    assert len(ptrs) == 1                                        # reserved capacity: no buffer ever moved while the map grew
+    assert all(g is graphs[0] for g in graphs)                   # ONE capture served every map version
     torch.cuda.synchronize()
     assert bool(torch.isfinite(inc.embeddings.float()).all())
 

@@ -87,8 +87,16 @@ def test_sphere_mesh_properties(nl):
     cen = T.mean(1) - c
     assert float(((n * cen).sum(-1) > 0).double().mean()) == 1.0
     # welded inside each voxel, closed across voxels once coincident vertices on shared voxel faces are merged
-    key = torch.round(V * 2e3).long()                    # 0.5 mm: coincident vertices of neighbouring voxels differ in the last fp32 bits (|x| ~ 2000)
-    uniq, inv = torch.unique(key, dim=0, return_inverse=True)
+    # coincident vertices of neighbouring voxels differ in the last fp32 bits (|x| ~ 2000, ulp 1.2e-4 m): merge within 0.5 mm
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    from scipy.spatial import cKDTree
+    Vn = V.numpy()
+    pairs = cKDTree(Vn).query_pairs(5e-4, output_type="ndarray")
+    g = coo_matrix((np.ones(len(pairs)), (pairs[:, 0], pairs[:, 1])), shape=(len(Vn), len(Vn)))
+    n_uniq, lab = connected_components(g, directed=False)
+    inv = torch.from_numpy(lab).long()
+    uniq = torch.zeros(n_uniq, 1)
     F = inv[faces.long().cpu()]
     e = torch.cat([F[:, [0, 1]], F[:, [1, 2]], F[:, [2, 0]]])
     fwd = {}
