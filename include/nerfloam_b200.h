@@ -309,6 +309,19 @@ NL_API int nl_stats_pack(const nl_render_stats *d_stats, void *d_buf, int rank, 
 NL_API int nl_stats_unpack(nl_render_stats *d_stats, const void *d_buf, int world, int phase, float fs_weight, float sdf_weight, void *stream);
 
 
+/* Fused reduce-scatter -> Adam -> all-gather over NVLink peer memory (csrc/peer.cu): the embedding-gradient reduction and the
+ * bf16 Adam step of the embedding table as ONE kernel per rank.  d_grad_peers / d_param_peers: device arrays of `world` pointers
+ * to every rank's fp32 gradient table / bf16 parameter table (symmetric memory, n_elems elements each, 16 per row);
+ * d_grad_mc / d_param_mc: the NVLS multicast addresses of the same buffers, or both NULL (plain P2P loads / stores then).
+ * Rank r reduces and updates rows [r*V/W, (r+1)*V/W) -- d_m / d_v are indexed like the table but only that slice is touched --
+ * and writes the new parameters into every rank's table.  Step count and skip flag come from d_ctl (section 8).
+ * The caller brackets the call with cross-rank barriers: all scatters complete before, all tables written after. */
+NL_API int nl_peer_reduce_adam_bf16(int64_t n_elems, int rank, int world, const float *const *d_grad_peers, const float *d_grad_mc,
+                             uint16_t *const *d_param_peers, uint16_t *d_param_mc, uint16_t *d_m, uint16_t *d_v, double lr, double beta1,
+                             double beta2, double eps, const int32_t *d_ctl, void *stream);
+/* out[i] = sum over ranks of peer_q[i], i < n (n % 4 == 0; loss sums and pose accumulators), into a LOCAL buffer */
+NL_API int nl_peer_reduce_f32(int64_t n, int world, const float *const *d_peers, const float *d_mc, float *d_out, void *stream);
+
 /* ============================================================================================
  * 10. Sparse marching cubes over the per-voxel SDF lattices of get_scores -- replaces MeshExtractor.marching_cubes
  *     (src/utils/mesh_util.py:145-169: a Python loop calling skimage.measure.marching_cubes once per voxel on the host).

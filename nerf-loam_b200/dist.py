@@ -107,3 +107,57 @@ def shard_bounds(n, rank, world):
     lo = (n * rank) // world
     hi = (n * (rank + 1)) // world
     return lo, hi
+
+
+class PeerReduceAdam:
+    """Embedding-gradient reduction fused with the table's Adam step over NVLink peer memory (csrc/peer.cu): per iteration ONE
+    kernel does reduce-scatter -> Adam -> all-gather -- through the NVLS multicast addresses of the two symmetric buffers when the
+    fabric offers them (multimem.ld_reduce / multimem.st, the sum happens inside the NVSwitch), through plain P2P loads and stores
+    otherwise -- instead of an NCCL all-reduce followed by a separate Adam launch.  Optimiser state is sharded over the ranks.
+
+    The flat fp32 gradient buffer has the engine's layout [header(16) | pose accumulators | table V*16] (SDFEngine.adopt_gradflat
+    makes the scatter kernels write straight into it) and the bf16 table is the map's embedding table (MapState.emb must be
+    `self.param`).  step() = barrier, small reduce (loss sums + pose accumulators), fused kernel, barrier."""
+
+    def __init__(self, group, device, n_rows, n_frames, lr, betas=(0.9, 0.999), eps=1e-8):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.n_rows, self.n_frames = int(n_rows), int(n_frames)
+        self.npose = (n_frames * 12 + 15) // 16 * 16
+        self.n_hdr = 16 + self.npose
+        self.lr, self.betas, self.eps = float(lr), betas, float(eps)
+        self.grad = symm.empty(self.n_hdr + self.n_rows * 16, dtype=torch.float32, device=device)
+        self.param = symm.empty((self.n_rows, 16), dtype=torch.bfloat16, device=device)
+        self.grad.zero_(); self.param.zero_()
+        self.h_grad = symm.rendezvous(self.grad, self.group)
+        self.h_param = symm.rendezvous(self.param, self.group)
+        off = self.n_hdr * 4
+        i64 = lambda xs: torch.tensor(list(xs), dtype=torch.int64, device=device)
+        self._hdr_peers = i64(self.h_grad.buffer_ptrs)
+        self._grad_peers = i64(p + off for p in self.h_grad.buffer_ptrs)
+        self._param_peers = i64(self.h_param.buffer_ptrs)
+        mc_g, mc_p = int(self.h_grad.multicast_ptr or 0), int(self.h_param.multicast_ptr or 0)
+        self.multicast = bool(mc_g and mc_p)
+        self._grad_mc = C.c_void_p(mc_g + off) if self.multicast else None
+        self._hdr_mc = C.c_void_p(mc_g) if self.multicast else None
+        self._param_mc = C.c_void_p(mc_p) if self.multicast else None
+        self.m = torch.zeros((self.n_rows, 16), dtype=torch.bfloat16, device=device)
+        self.v = torch.zeros((self.n_rows, 16), dtype=torch.bfloat16, device=device)
+        self.hdr_out = torch.zeros(self.n_hdr, dtype=torch.float32, device=device)
+
+    def step(self, stats_u8, ctl, pose_acc=None):
+        """After the local scatter: make loss sums / pose accumulators / embedding gradients global and apply the table's Adam step."""
+        lib, st = _capi.lib(), _capi.stream_ptr()
+        pack_stats(stats_u8, self.grad[:4], 0, self.world, 1)                       # loss sums ride in the header
+        self.h_grad.barrier(channel=0)                                              # every rank's scatter + header are complete
+        _capi.check(lib.nl_peer_reduce_f32(self.n_hdr, self.world, _capi.ptr(self._hdr_peers), self._hdr_mc, _capi.ptr(self.hdr_out), st),
+                    "nl_peer_reduce_f32")
+        _capi.check(lib.nl_peer_reduce_adam_bf16(self.n_rows * 16, self.rank, self.world, _capi.ptr(self._grad_peers), self._grad_mc,
+                                                 _capi.ptr(self._param_peers), self._param_mc, _capi.ptr(self.m), _capi.ptr(self.v), self.lr,
+                                                 self.betas[0], self.betas[1], self.eps, _capi.ptr(ctl), st), "nl_peer_reduce_adam_bf16")
+        _capi.LAUNCHES += 2
+        self.h_param.barrier(channel=1)                                             # every rank's slice has landed in every table
+        unpack_stats(stats_u8, self.hdr_out[:4], self.world, 1)
+        if pose_acc is not None:
+            pose_acc.copy_(self.hdr_out[16:16 + pose_acc.numel()].view(pose_acc.shape))

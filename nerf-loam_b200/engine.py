@@ -313,6 +313,17 @@ class SDFEngine:
         torch.cuda.current_stream().synchronize()
         return self._ctl_host.tolist()
 
+    def adopt_gradflat(self, flat, V, n_frames):
+        """Use an externally allocated flat gradient buffer of the same layout (dist.PeerReduceAdam's symmetric-memory buffer, so
+        that the scatter kernels write where the peers read)."""
+        npose = (n_frames * 12 + 15) // 16 * 16
+        assert flat.numel() == 16 + npose + V * 16 and flat.dtype == torch.float32 and flat.is_contiguous()
+        self.gradflat = flat
+        self.pose_acc = flat[16:16 + n_frames * 12].view(n_frames, 12)
+        self.grad_emb = flat[16 + npose:].view(V, 16)
+        self.pose_grad = torch.zeros((n_frames, 6), dtype=torch.float32, device=self.device)
+        self._gradflat_key = (int(V), int(n_frames))
+
     def _ensure_grads(self, V, n_frames):
         key = (int(V), int(n_frames))
         if self._gradflat_key != key:
@@ -413,7 +424,7 @@ class SDFEngine:
 
     def forward_backward(self, m, dec, R, cfg, gt_depth, cos, dir_local=None, ray_frame=None, n_frames=1, ray_o=None,
                          ray_d=None, noise=None, rng_seed=0, reference_compat=True, update_decoder=True, update_emb=True,
-                         update_pose=True, pose6=None, group=None, refresh_weights=True, rng_seed_dev=None, defer_wgrad=False):
+                         update_pose=True, pose6=None, group=None, refresh_weights=True, rng_seed_dev=None, defer_wgrad=False, peer=None):
         """One optimisation iteration without the optimiser step.  Gradients land in
         self.grad_emb (fp32 [V,16]), dec.grads (fp32), self.pose_grad (fp32 [F,6]); the loss in stats.
         defer_wgrad=True: return without waiting for the decoder's weight gradients -- they (and whatever the caller enqueues on
@@ -467,7 +478,10 @@ class SDFEngine:
             from . import dist as nldist
             if self.gradflat is None:
                 self._ensure_grads(0, n_frames)
-            nldist.allreduce_grads_with_loss(self.stats, self.gradflat, group)     # loss sums + pose accumulators + embedding gradients
+            if peer is not None:     # fused reduce-scatter -> Adam -> all-gather over NVLink peer memory (the table's Adam step is inside)
+                peer.step(self.stats, self.ctl, self.pose_acc if want_pose else None)
+            else:
+                nldist.allreduce_grads_with_loss(self.stats, self.gradflat, group)     # loss sums + pose accumulators + embedding gradients
             if update_decoder:       # the decoder's gradients are reduced where they are produced
                 with (torch.cuda.stream(side) if defer else contextlib.nullcontext()):
                     nldist.allreduce_flat(dec.gradflat, group)
