@@ -134,6 +134,22 @@ def run_ours(args):
     bufs = nl.engine.DecoderBuffers(dec, dev)
     emb = ms.emb
     state = {"opt": None}
+    # multi-GPU: the embedding-gradient reduction fused with the table's Adam step over NVLink peer memory (csrc/peer.cu) and the
+    # statistics exchange through symmetric memory, instead of NCCL all-reduces (NL_PEER=0: plain NCCL, the baseline)
+    peer = pstats = None
+    peer_info = None
+    if world > 1 and os.environ.get("NL_PEER", "1") != "0":
+        try:
+            peer = nl.dist.PeerReduceAdam(group, dev, emb.shape[0], 1, lr=LR[0])
+            peer.param.copy_(emb)
+            ms = nl.engine.MapState(ms.centres, ms.structure, ms.vox2row, peer.param, dev)
+            emb = ms.emb
+            eng.adopt_gradflat(peer.grad, emb.shape[0], 1)
+            pstats = nl.dist.PeerStats(group, dev)
+            peer_info = {"fused_reduce_adam": True, "nvls_multicast": peer.multicast}
+        except Exception as exc:      # no symmetric memory on this system: NCCL path
+            peer = pstats = None
+            peer_info = {"fused_reduce_adam": False, "why": repr(exc)}
 
     pipeline = os.environ.get("NL_PIPELINE", "1") != "0"
 
@@ -141,15 +157,15 @@ def run_ours(args):
         eng.rays_from_poses(pose6, dirs, None)
         eng.forward_backward(ms, bufs, R, CFG, gt, cosv, dir_local=dirs, ray_frame=None, n_frames=1, rng_seed=12345,
                              update_decoder=update_decoder, update_emb=True, update_pose=True, pose6=pose6, group=group,
-                             defer_wgrad=pipeline and update_decoder and eng.overlap_wgrad)
+                             defer_wgrad=pipeline and update_decoder and eng.overlap_wgrad, peer=peer, peer_stats=pstats)
+        emb_group = [] if peer is not None else [dict(param=emb, grad=eng.grad_emb, lr=LR[0])]      # peer: the table's Adam is inside the fused kernel
         if not update_decoder:          # steady-state variant (decoder frozen after freeze_frame frames, mapping.py:196)
             if "opt_frozen" not in state:
-                state["opt_frozen"] = nl.engine.FusedAdam([dict(param=emb, grad=eng.grad_emb, lr=LR[0]),
-                                                           dict(param=pose6[0], grad=eng.pose_grad[0], lr=LR[2])], ctl=lambda: eng.ctl)
+                state["opt_frozen"] = nl.engine.FusedAdam(emb_group + [dict(param=pose6[0], grad=eng.pose_grad[0], lr=LR[2])], ctl=lambda: eng.ctl)
             state["opt_frozen"].step()
             return
         if state["opt"] is None:
-            groups = [dict(param=emb, grad=eng.grad_emb, lr=LR[0])]
+            groups = list(emb_group)
             groups += [dict(param=p.data, grad=g, lr=LR[1], side=True) for p, g in zip(bufs.params, bufs.grads)]
             groups += [dict(param=pose6[0], grad=eng.pose_grad[0], lr=LR[2])]
             state["opt"] = nl.engine.FusedAdam(groups, ctl=lambda: eng.ctl)
@@ -295,7 +311,9 @@ def run_ours(args):
     # ---------------- north-star split (BASELINE.json config 5): ONE scan ray-sharded over the ranks (strong scaling) ----------------
     strong = None
     if world > 1:
-        strong = strong_scaling_block(nl, dev, rank, world, group, scans[0], ms, dec, args.steps, sync_all, timed)
+        if peer is not None:
+            peer.wait_params()
+        strong = strong_scaling_block(nl, dev, rank, world, group, scans[0], ms, dec, args.steps, sync_all, timed, use_peer=peer is not None)
 
     clk = clocks.stop() if clocks is not None else None
 
@@ -331,11 +349,14 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "rays_per_gpu": R, "samples_per_gpu_step": n_local, "octree_nodes": ms.n_nodes,
                    "embedding_rows": int(ms.emb.shape[0]), "decoder": "16-256-256-1, fp32 parity (%s)" % nl.engine.mlp_impl(256),
                    "parallelism": f"ray-sharded dp{world}, map replicated" + ("" if world == 1 else
-                                  f": the batch is a window of {world} scans (all rays), split contiguously = one scan per rank; 3 collectives per step"),
+                                  f": the batch is a window of {world} scans (all rays), split contiguously = one scan per rank; per step: statistics exchange, "
+                                  "embedding-gradient reduction (fused with Adam over NVLink peer memory when multi_gpu_exchange.fused_reduce_adam), "
+                                  "decoder-gradient all-reduce (NCCL, side stream)"),
                    "l2": "per-step working set (samples x ~2.2 KB activations+features) ~1.9 GB >> 126 MB L2; no flush needed",
                    "sampler_noise": "in-kernel counter RNG", "loss": loss_val,
                    "untimed_before_clock": f"{W} warm-up steps + {n_settle} settle steps (>= 100 ms)",
-                   "kernel_error_bits_over_all_steps": ctl[nl._capi.CTL_ERROR], "skipped_steps": ctl[nl._capi.CTL_SKIPPED]},
+                   "kernel_error_bits_over_all_steps": ctl[nl._capi.CTL_ERROR], "skipped_steps": ctl[nl._capi.CTL_SKIPPED],
+                   "multi_gpu_exchange": peer_info},
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": int(R * 20 * world), "d2h_bytes_per_step": int(160 * world),
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
@@ -412,7 +433,7 @@ def run_ours(args):
     print(json.dumps(out))
 
 
-def strong_scaling_block(nl, dev, rank, world, group, scan, ms, dec, steps, sync_all, timed):
+def strong_scaling_block(nl, dev, rank, world, group, scan, ms, dec, steps, sync_all, timed, use_peer=False):
     """ONE scan, its rays split contiguously over the ranks (dist.shard_bounds), map / decoder / pose replicated, the three
     collectives of nerf-loam_b200/dist.py per step.  Also checks the parity gate of SURVEY 8(d): the all-reduced gradients of the
     sharded step equal those of an unsharded (1-rank) step over the same rays."""
@@ -449,15 +470,22 @@ def strong_scaling_block(nl, dev, rank, world, group, scan, ms, dec, steps, sync
     torch.cuda.empty_cache()
     # ---- timing ----
     emb = ms.emb.clone()
+    peer = pstats = None
+    if use_peer:
+        peer = nl.dist.PeerReduceAdam(group, dev, emb.shape[0], 1, lr=LR[0])
+        peer.param.copy_(emb)
+        emb = peer.param
+        eng.adopt_gradflat(peer.grad, emb.shape[0], 1)
+        pstats = nl.dist.PeerStats(group, dev)
     ms_s = nl.engine.MapState(ms.centres, ms.structure, ms.vox2row, emb, dev)
     opt = {"o": None}
 
     def step():
         eng.rays_from_poses(pose6, dirs, None)
         eng.forward_backward(ms_s, bufs, Rl, CFG, gt, cosv, dir_local=dirs, ray_frame=None, n_frames=1, rng_seed=12345, update_decoder=True,
-                             update_emb=True, update_pose=True, pose6=pose6, group=group, defer_wgrad=eng.overlap_wgrad)
+                             update_emb=True, update_pose=True, pose6=pose6, group=group, defer_wgrad=eng.overlap_wgrad, peer=peer, peer_stats=pstats)
         if opt["o"] is None:
-            opt["o"] = nl.engine.FusedAdam([dict(param=emb, grad=eng.grad_emb, lr=LR[0])] +
+            opt["o"] = nl.engine.FusedAdam(([] if peer is not None else [dict(param=emb, grad=eng.grad_emb, lr=LR[0])]) +
                                            [dict(param=p.data.clone(), grad=g, lr=LR[1], side=True) for p, g in zip(bufs.params, bufs.grads)] +
                                            [dict(param=pose6[0], grad=eng.pose_grad[0], lr=LR[2])], ctl=lambda: eng.ctl)
         opt["o"].step(side_stream=eng.deferred_stream())

@@ -309,6 +309,10 @@ NL_API int nl_stats_pack(const nl_render_stats *d_stats, void *d_buf, int rank, 
 NL_API int nl_stats_unpack(nl_render_stats *d_stats, const void *d_buf, int world, int phase, float fs_weight, float sdf_weight, void *stream);
 
 
+/* phase-0 unpack reading every rank's packed vector directly (d_peer_bufs: device array of `world` pointers into symmetric memory):
+ * pack -> cross-rank barrier -> this call replaces the all-reduce of the statistics exchange */
+NL_API int nl_stats_unpack_peers(nl_render_stats *d_stats, const double *const *d_peer_bufs, int world, float fs_weight, float sdf_weight,
+                          void *stream);
 /* Fused reduce-scatter -> Adam -> all-gather over NVLink peer memory (csrc/peer.cu): the embedding-gradient reduction and the
  * bf16 Adam step of the embedding table as ONE kernel per rank.  d_grad_peers / d_param_peers: device arrays of `world` pointers
  * to every rank's fp32 gradient table / bf16 parameter table (symmetric memory, n_elems elements each, 16 per row);
@@ -318,7 +322,10 @@ NL_API int nl_stats_unpack(nl_render_stats *d_stats, const void *d_buf, int worl
  * The caller brackets the call with cross-rank barriers: all scatters complete before, all tables written after. */
 NL_API int nl_peer_reduce_adam_bf16(int64_t n_elems, int rank, int world, const float *const *d_grad_peers, const float *d_grad_mc,
                              uint16_t *const *d_param_peers, uint16_t *d_param_mc, uint16_t *d_m, uint16_t *d_v, double lr, double beta1,
-                             double beta2, double eps, const int32_t *d_ctl, void *stream);
+                             double beta2, double eps, const int32_t *d_ctl, int64_t hdr_n, const float *const *d_hdr_peers,
+                             const float *d_hdr_mc, float *d_hdr_out, void *stream);
+/* (hdr_n floats in front of each rank's table -- loss sums, pose accumulators -- are summed over the ranks into the LOCAL
+ * d_hdr_out by the same launch; hdr_n % 4 == 0, may be 0) */
 /* out[i] = sum over ranks of peer_q[i], i < n (n % 4 == 0; loss sums and pose accumulators), into a LOCAL buffer */
 NL_API int nl_peer_reduce_f32(int64_t n, int world, const float *const *d_peers, const float *d_mc, float *d_out, void *stream);
 

@@ -56,7 +56,25 @@ template <bool MC>
 __global__ void __launch_bounds__(256) k_reduce_adam_bf16(long long e0, long long e1, int rank, int world, const float *const *grad_peers,
                                                            const float *grad_mc, uint16_t *const *param_peers, uint16_t *param_mc,
                                                            uint16_t *__restrict__ m, uint16_t *__restrict__ v, double lr, double beta1, double beta2,
-                                                           float eps, const int32_t *__restrict__ ctl) {
+                                                           float eps, const int32_t *__restrict__ ctl, int hdr_n4, const float *const *hdr_peers,
+                                                           const float *hdr_mc, float *__restrict__ hdr_out) {
+    // the small vector in front of the table (loss sums, pose accumulators): every rank reduces all of it into a LOCAL buffer
+    if (blockIdx.x == gridDim.x - 1) {
+        for (int i = threadIdx.x; i < hdr_n4; i += blockDim.x) {
+            float4 s4;
+            if (MC) {
+                s4 = mc_ld_reduce_f32x4(hdr_mc + 4 * i);
+            } else {
+                s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int q = 0; q < world; ++q) {
+                    const float4 a = *reinterpret_cast<const float4 *>(hdr_peers[q] + 4 * i);
+                    s4.x += a.x; s4.y += a.y; s4.z += a.z; s4.w += a.w;
+                }
+            }
+            *reinterpret_cast<float4 *>(hdr_out + 4 * i) = s4;
+        }
+        return;
+    }
     const long long e = e0 + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
     if (e >= e1 || ctl[NL_CTL_SKIP_NOW]) return;        // a skipped iteration leaves parameters and moments untouched on every rank
     float g[8];
@@ -108,21 +126,24 @@ __global__ void k_reduce_small(int n4, int world, const float *const *peers, con
 
 extern "C" int nl_peer_reduce_adam_bf16(int64_t n_elems, int rank, int world, const float *const *d_grad_peers, const float *d_grad_mc,
                                         uint16_t *const *d_param_peers, uint16_t *d_param_mc, uint16_t *d_m, uint16_t *d_v, double lr,
-                                        double beta1, double beta2, double eps, const int32_t *d_ctl, void *stream) {
+                                        double beta1, double beta2, double eps, const int32_t *d_ctl, int64_t hdr_n, const float *const *d_hdr_peers,
+                                        const float *d_hdr_mc, float *d_hdr_out, void *stream) {
+    if (hdr_n < 0 || (hdr_n & 3) || (hdr_n > 0 && (!d_hdr_peers || !d_hdr_out))) return nl_set_error("nl_peer_reduce_adam_bf16: bad header arguments");
     if (n_elems < 0 || (n_elems & 15) || world < 1 || rank < 0 || rank >= world) return nl_set_error("nl_peer_reduce_adam_bf16: bad sizes");
     if (!d_grad_peers || !d_param_peers || !d_m || !d_v || !d_ctl) return nl_set_error("nl_peer_reduce_adam_bf16: null pointer");
     if ((d_grad_mc == nullptr) != (d_param_mc == nullptr)) return nl_set_error("nl_peer_reduce_adam_bf16: both or neither multicast address");
     // row-aligned contiguous slice of this rank
     const long long rows = n_elems / 16;
     const long long e0 = rows * rank / world * 16, e1 = rows * (rank + 1) / world * 16;
-    if (e1 <= e0) return NL_OK;
-    const int blocks = nl_div_up((e1 - e0) / 8, 256);
+    const int blocks = nl_div_up((e1 - e0) / 8, 256) + 1;          // + one block for the header
     if (d_grad_mc)
         k_reduce_adam_bf16<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(e0, e1, rank, world, d_grad_peers, d_grad_mc, d_param_peers, d_param_mc,
-                                                                           d_m, d_v, lr, beta1, beta2, (float)eps, d_ctl);
+                                                                           d_m, d_v, lr, beta1, beta2, (float)eps, d_ctl, (int)(hdr_n / 4), d_hdr_peers,
+                                                                           d_hdr_mc, d_hdr_out);
     else
         k_reduce_adam_bf16<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(e0, e1, rank, world, d_grad_peers, nullptr, d_param_peers, nullptr,
-                                                                            d_m, d_v, lr, beta1, beta2, (float)eps, d_ctl);
+                                                                            d_m, d_v, lr, beta1, beta2, (float)eps, d_ctl, (int)(hdr_n / 4), d_hdr_peers,
+                                                                            nullptr, d_hdr_out);
     NL_CHECK_LAUNCH("nl_peer_reduce_adam_bf16");
     return NL_OK;
 }

@@ -633,7 +633,41 @@ __global__ void k_stats_unpack(nl_render_stats *s, const void *buf_, int world, 
     }
 }
 
+// phase-0 unpack straight from every rank's packed vector in symmetric memory (P2P loads, summed in rank order on every rank):
+// the statistics exchange without a collective library call -- pack, cross-rank barrier, this kernel.
+__global__ void k_stats_unpack_peers(nl_render_stats *s, const double *const *peers, int world) {
+    __shared__ double b[NL_STATS_PACK_FIXED];
+    const int t = threadIdx.x;
+    if (t < NL_STATS_PACK_FIXED) {
+        double acc = 0.0;
+        for (int q = 0; q < world; ++q) acc += peers[q][t];
+        b[t] = acc;
+    }
+    __syncthreads();
+    if (t == 0) {
+        s->cnt_fs_valid = (long long)b[0]; s->cnt_sdf_valid = (long long)b[1]; s->pad_fs_rays = (long long)b[2]; s->pad_fs_nsamp = (long long)b[3];
+        s->pad_sdf_rays = (long long)b[4]; s->pad_sdf_nsamp = (long long)b[5]; s->pad_sdf_d2 = b[6]; s->pad_sdf_d2_nsamp = b[7];
+        s->n_hit_rays = (int32_t)b[8];
+        int smax = 0, err = 0;
+        for (int q = 0; q < world; ++q) {               // slot q of rank q's own vector (the other slots of a vector are zero)
+            smax = max(smax, (int)peers[q][NL_STATS_PACK_FIXED + q]);
+            err |= (int)peers[q][NL_STATS_PACK_FIXED + world + q];
+        }
+        s->max_samples = smax;
+        s->error = err;
+    }
+}
+
 }  // namespace
+
+extern "C" int nl_stats_unpack_peers(nl_render_stats *d_stats, const double *const *d_peer_bufs, int world, float fs_weight, float sdf_weight,
+                                     void *stream) {
+    if (!d_stats || !d_peer_bufs || world < 1) return nl_set_error("nl_stats_unpack_peers: bad arguments");
+    k_stats_unpack_peers<<<1, 32, 0, (cudaStream_t)stream>>>(d_stats, d_peer_bufs, world);
+    k_loss_prepare<<<1, 1, 0, (cudaStream_t)stream>>>(d_stats, fs_weight, sdf_weight);
+    NL_CHECK_LAUNCH("nl_stats_unpack_peers");
+    return NL_OK;
+}
 
 extern "C" int nl_iter_status(const nl_render_stats *d_stats, const int32_t *d_ctl_prev, int32_t *d_ctl, void *stream) {
     if (!d_stats || !d_ctl || !d_ctl_prev) return nl_set_error("nl_iter_status: null pointer");

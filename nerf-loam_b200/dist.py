@@ -146,18 +146,47 @@ class PeerReduceAdam:
         self.v = torch.zeros((self.n_rows, 16), dtype=torch.bfloat16, device=device)
         self.hdr_out = torch.zeros(self.n_hdr, dtype=torch.float32, device=device)
 
-    def step(self, stats_u8, ctl, pose_acc=None):
-        """After the local scatter: make loss sums / pose accumulators / embedding gradients global and apply the table's Adam step."""
+    def step(self, stats_u8, ctl, pose_acc=None, defer_barrier=False):
+        """After the local scatter: make loss sums / pose accumulators / embedding gradients global and apply the table's Adam step.
+        defer_barrier: leave out the closing barrier (every rank's slice has landed in every table); the caller runs wait_params()
+        before the table is read again -- after the next iteration's traversal and sampling, which do not touch it."""
         lib, st = _capi.lib(), _capi.stream_ptr()
         pack_stats(stats_u8, self.grad[:4], 0, self.world, 1)                       # loss sums ride in the header
         self.h_grad.barrier(channel=0)                                              # every rank's scatter + header are complete
-        _capi.check(lib.nl_peer_reduce_f32(self.n_hdr, self.world, _capi.ptr(self._hdr_peers), self._hdr_mc, _capi.ptr(self.hdr_out), st),
-                    "nl_peer_reduce_f32")
         _capi.check(lib.nl_peer_reduce_adam_bf16(self.n_rows * 16, self.rank, self.world, _capi.ptr(self._grad_peers), self._grad_mc,
                                                  _capi.ptr(self._param_peers), self._param_mc, _capi.ptr(self.m), _capi.ptr(self.v), self.lr,
-                                                 self.betas[0], self.betas[1], self.eps, _capi.ptr(ctl), st), "nl_peer_reduce_adam_bf16")
-        _capi.LAUNCHES += 2
-        self.h_param.barrier(channel=1)                                             # every rank's slice has landed in every table
-        unpack_stats(stats_u8, self.hdr_out[:4], self.world, 1)
+                                                 self.betas[0], self.betas[1], self.eps, _capi.ptr(ctl), self.n_hdr, _capi.ptr(self._hdr_peers),
+                                                 self._hdr_mc, _capi.ptr(self.hdr_out), st), "nl_peer_reduce_adam_bf16")
+        _capi.LAUNCHES += 1
+        unpack_stats(stats_u8, self.hdr_out[:4], self.world, 1)                     # local results: no need to wait for the peers
         if pose_acc is not None:
             pose_acc.copy_(self.hdr_out[16:16 + pose_acc.numel()].view(pose_acc.shape))
+        self._pending_barrier = True
+        if not defer_barrier:
+            self.wait_params()
+
+    def wait_params(self):
+        if getattr(self, "_pending_barrier", False):
+            self.h_param.barrier(channel=1)
+            self._pending_barrier = False
+
+
+class PeerStats:
+    """The pre-backward statistics exchange through symmetric memory: pack into this rank's buffer, cross-rank barrier, every rank
+    sums all the vectors itself (nl_stats_unpack_peers) -- three launches on the caller's stream, no collective-library call."""
+
+    def __init__(self, group, device):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.buf = symm.empty(stats_words(self.world), dtype=torch.float64, device=device)
+        self.buf.zero_()
+        self.h = symm.rendezvous(self.buf, self.group)
+        self._peers = torch.tensor(list(self.h.buffer_ptrs), dtype=torch.int64, device=device)
+
+    def exchange(self, stats_u8, fs_weight, sdf_weight):
+        pack_stats(stats_u8, self.buf, self.rank, self.world, 0)
+        self.h.barrier(channel=0)
+        _capi.check(_capi.lib().nl_stats_unpack_peers(_capi.ptr(stats_u8), _capi.ptr(self._peers), self.world, float(fs_weight), float(sdf_weight),
+                                                      _capi.stream_ptr()), "nl_stats_unpack_peers")
+        _capi.LAUNCHES += 2

@@ -424,7 +424,8 @@ class SDFEngine:
 
     def forward_backward(self, m, dec, R, cfg, gt_depth, cos, dir_local=None, ray_frame=None, n_frames=1, ray_o=None,
                          ray_d=None, noise=None, rng_seed=0, reference_compat=True, update_decoder=True, update_emb=True,
-                         update_pose=True, pose6=None, group=None, refresh_weights=True, rng_seed_dev=None, defer_wgrad=False, peer=None):
+                         update_pose=True, pose6=None, group=None, refresh_weights=True, rng_seed_dev=None, defer_wgrad=False, peer=None,
+                         peer_stats=None):
         """One optimisation iteration without the optimiser step.  Gradients land in
         self.grad_emb (fp32 [V,16]), dec.grads (fp32), self.pose_grad (fp32 [F,6]); the loss in stats.
         defer_wgrad=True: return without waiting for the decoder's weight gradients -- they (and whatever the caller enqueues on
@@ -438,9 +439,14 @@ class SDFEngine:
         self.render_samples(m, R, cfg, ray_o, ray_d, gt_depth, cos, noise, rng_seed, reference_compat, rng_seed_dev)
         if group is not None:   # the loss normalisation is global (criterion.py:84-100): ONE tiny exchange before backward
             from . import dist as nldist
-            self._xbuf = nldist.allreduce_sample_stats(self.stats, group, self._xbuf, cfg["fs_weight"], cfg["sdf_weight"])
+            if peer_stats is not None:      # through symmetric memory on this stream: pack, barrier, sum of the peers' vectors
+                peer_stats.exchange(self.stats, cfg["fs_weight"], cfg["sdf_weight"])
+            else:
+                self._xbuf = nldist.allreduce_sample_stats(self.stats, group, self._xbuf, cfg["fs_weight"], cfg["sdf_weight"])
         self._iter_status(alternate=defer_wgrad)      # captured CUDA graphs (tracking) keep one block: fixed pointers
         self._mark("t_samples")
+        if peer is not None:
+            peer.wait_params()       # the previous iteration's table slices of every rank have landed (barrier deferred to here)
         self.gather_forward(m)
         self.join_side()             # decoder weights (and gradient buffers) of the previous iteration are final from here on
         if refresh_weights:
@@ -479,7 +485,7 @@ class SDFEngine:
             if self.gradflat is None:
                 self._ensure_grads(0, n_frames)
             if peer is not None:     # fused reduce-scatter -> Adam -> all-gather over NVLink peer memory (the table's Adam step is inside)
-                peer.step(self.stats, self.ctl, self.pose_acc if want_pose else None)
+                peer.step(self.stats, self.ctl, self.pose_acc if want_pose else None, defer_barrier=True)
             else:
                 nldist.allreduce_grads_with_loss(self.stats, self.gradflat, group)     # loss sums + pose accumulators + embedding gradients
             if update_decoder:       # the decoder's gradients are reduced where they are produced
