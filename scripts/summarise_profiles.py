@@ -54,3 +54,27 @@ if os.path.exists(p):
         lines.append(f"| `{k[:90]}` | {cnt[k]} | {tot[k]:.1f} | {100 * tot[k] / total:.1f}% |")
 open(out, "w").write("\n".join(lines) + "\n")
 print("wrote", out)
+
+# dram traffic per launch of the dominant kernels -> profiles/r02_traffic.json (bench.py's roofline.traffic reads it)
+if len(sys.argv) > 3:
+    import json
+    traffic = {}
+    for f in sorted(os.listdir(src)):
+        if not f.endswith(".ncu-rep"):
+            continue
+        raw = subprocess.run(["ncu", "-i", os.path.join(src, f), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(raw)))
+        if len(rows) < 3:
+            continue
+        d = {h: (v, u) for h, u, v in zip(rows[0], rows[1], rows[2])}
+
+        def to_bytes(key):
+            v, u = d.get(key, ("0", "byte"))
+            x = float(v.replace(",", ""))
+            return x * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(u, 1)
+        rd, wr = to_bytes("dram__bytes_read.sum"), to_bytes("dram__bytes_write.sum")
+        traffic[f[:-8]] = {"dram_bytes": rd + wr, "read": rd, "write": wr, "report": f"gpurun_out/{tag}/{f} (summary: {out})",
+                           "tensor_active_pct": d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", ("", ""))[0],
+                           "duration": " ".join(d.get("gpu__time_duration.sum", ("", ""))), "samples": "775 770 (bench.py headline workload)"}
+    json.dump(traffic, open(sys.argv[3], "w"), indent=1)
+    print("wrote", sys.argv[3])
