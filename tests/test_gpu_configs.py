@@ -410,7 +410,7 @@ def test_incremental_map_update_equals_full_and_graphs_survive_it(nl):
             assert torch.equal(inc.map_states[k], ful.map_states[k]), k
         assert inc.last_update["dirty_rows"] <= a.n_nodes and (i == 0 or inc.last_update["dirty_rows"] < 0.7 * a.n_nodes)
         ptrs.add((a.centres.data_ptr(), a.structure.data_ptr(), a.vox2row.data_ptr(), a.packed_children().data_ptr(), a.emb.data_ptr()))
-        frames.append(nl.frame.LidarFrame(i, torch.from_numpy(pts[:N]), torch.from_numpy(cos[:N]), nl.se3pose.OptimizablePose.from_matrix(torch.from_numpy(pose.copy())),
+        frames.append(nl.frame.LidarFrame(i + 1, torch.from_numpy(pts[:N]), torch.from_numpy(cos[:N]), nl.se3pose.OptimizablePose.from_matrix(torch.from_numpy(pose.copy())),
                                           new_keyframe=True))
         if i >= 1:      # a mapping call on the growing map after every update, through the default (captured) path
             rh.bundle_adjust_frames(frames[-2:], inc.embeddings, a, dec, crit, 0.3, 0.15, N_rays=512, num_iterations=2, truncation=0.3,
@@ -477,3 +477,52 @@ def test_tracker_mapper_handoff_on_device(nl):
     assert all(torch.equal(a, b) for a, b in zip(d2.state_dict().values(), dec.state_dict().values()))
     m2 = sd.map_state()
     assert m2.emb.is_cuda and torch.equal(m2.vox2row, ms2.vox2row)
+
+
+def _ipc_child(q_in, q_out):
+    """Runs in a spawned process: receives share.ShareData's device tensors (CUDA IPC handles under the hood), reads them and
+    writes into one of them in place."""
+    import torch
+    st, dec_flat = q_in.get(timeout=120)
+    emb = st["emb"]
+    assert emb.is_cuda and st["vox2row"].is_cuda
+    q_out.put((float(emb.float().sum()), int(st["vox2row"].long().clamp(min=0).sum()), float(dec_flat.sum())))
+    emb[0, 0] = 123.0                                    # visible to the parent only if the memory is really shared
+    torch.cuda.synchronize()
+    q_out.put("done")
+    q_in.get(timeout=120)                                # keep the mapping alive until the parent has looked
+
+
+def test_share_data_crosses_processes_as_cuda_ipc(nl):
+    """share.ShareData's payload goes to another process as CUDA IPC handles: no host staging, and the receiver sees the very
+    same device memory (the reference pickles CPU copies of every tensor through a Manager, mapping.py:227-232)."""
+    import torch.multiprocessing as mp
+    syn = nl.synthetic
+    pts, cos, pose = syn.make_scan(n_beams=16, n_az=100, seed=41)
+    mu = nl.mapping.MapUpdater(0.3, init_std=0.02, seed=4)
+    mu.insert_voxels(torch.from_numpy(syn.voxelize(pts, pose, 0.3)))
+    torch.manual_seed(3)
+    dec = nl.lidar.Decoder(depth=2, width=256, in_dim=16, skips=[], embedder="none", multires=0).cuda()
+    sd = nl.share.ShareData()
+    sd.decoder = dec
+    sd.states = mu.map_states
+    st = sd.states
+    flat = sd._decoder_flat
+    want = (float(st["emb"].float().sum()), int(st["vox2row"].long().clamp(min=0).sum()), float(flat.sum()))
+    ctx = mp.get_context("spawn")
+    q_in, q_out = ctx.Queue(), ctx.Queue()
+    p = ctx.Process(target=_ipc_child, args=(q_in, q_out))
+    p.start()
+    try:
+        q_in.put(({"emb": st["emb"], "vox2row": st["vox2row"]}, flat))
+        got = q_out.get(timeout=180)
+        assert got[1] == want[1] and abs(got[0] - want[0]) < 1e-3 and abs(got[2] - want[2]) < 1e-3
+        assert q_out.get(timeout=60) == "done"
+        torch.cuda.synchronize()
+        assert float(st["emb"][0, 0]) == 123.0             # the child's in-place write landed in the parent's tensor
+    finally:
+        q_in.put("bye")
+        p.join(timeout=60)
+        if p.is_alive():
+            p.kill()
+    assert p.exitcode == 0
