@@ -77,6 +77,24 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// the same arrive delivered to the barrier at this offset in BOTH CTAs of a 2-CTA cluster (weight stages shared by multicast)
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3) : "memory");
+}
+// bulk copy global -> the same shared-memory offset of both CTAs of the pair; each CTA's barrier at `bar` receives the bytes
+__device__ __forceinline__ void bulk_g2s_pair(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_cta_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30)
 // (ignored for swizzled K-major, set to 1), SBO>>4 = 1024>>4 [32,46), version 1 [46,48), layout SWIZZLE_128B = 2 [61,64)
@@ -441,7 +459,13 @@ __device__ __forceinline__ void store_a_row_fast(uint32_t stage, const uint32_t 
 // those 8 K-blocks need no activation stage, no smem stores and no per-chunk hand-shake; the dh1 chunks of backward
 // layer 1 go through two 64-column TMEM slots (hi | lo), one per epilogue group.  Shared-memory traffic of those 16
 // steps drops to the weight panels, and the tiny N = 16 MMAs no longer fetch a 4 KB A tile from smem each.
-template <bool WGRAD, bool TS>
+// PAIR = true (launched as clusters of 2 CTAs): the two CTAs of a pair walk through the SAME sequence of weight stages, each
+// on its own tile, so every stage is fetched from L2 once per pair -- CTA 0 loads the hi panel, CTA 1 the lo panel, each copy
+// multicast into both shared memories -- instead of once per CTA.  Backward layer 2 is bound by exactly that stream (64 KB per
+// K-block and SM, ~57 B/clk/SM, the L2's limit chip-wide); halving it is what moves it towards its tensor floor.  A stage is
+// refilled only when BOTH CTAs' MMAs have retired it (their tcgen05.commit is multicast to both b_empty barriers, count 2), and
+// both CTAs run the same number of rounds (a missing last tile is processed with all rows dead).
+template <bool WGRAD, bool TS, bool PAIR>
 __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -464,11 +488,14 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
 #define NL_STAMP(role, step, k) do { if (dbg && tl == 1 && (threadIdx.x & 31) == 0) dbg[((role) * 25 + (step)) * 8 + (k)] = clock64(); } while (0)
     const long long M = p.M_dev ? min((long long)*p.M_dev, p.M_host) : p.M_host;
     const long long ntiles = (M + TM - 1) / TM;
+    // tiles this CTA loops over: with PAIR every CTA runs the same number of rounds (tiles >= ntiles have only dead rows)
+    const long long nt_loop = PAIR ? ((ntiles + gridDim.x - 1) / gridDim.x) * gridDim.x : ntiles;
+    const uint32_t pair_rank = PAIR ? cluster_cta_rank() : 0u;
 
     for (int i = tid; i < WN; i += NTHREADS_TRAIN) { b0s[i] = p.b0[i]; b1s[i] = p.b1[i]; w2s[i] = p.w2[i]; }
     if (tid == 0) {
         mbar_init(BAR(0), 1); mbar_init(BAR(1), 1);
-        mbar_init(BAR(2), 1); mbar_init(BAR(3), 1);
+        mbar_init(BAR(2), PAIR ? 2 : 1); mbar_init(BAR(3), PAIR ? 2 : 1);   // b_empty: the MMAs of both CTAs of a pair
         mbar_init(BAR(4), 4); mbar_init(BAR(5), 4);      // a_full: the 4 warps of the group that owns the chunk
         mbar_init(BAR(6), 1); mbar_init(BAR(7), 1);
         mbar_init(BAR(8), 1); mbar_init(BAR(9), 1); mbar_init(BAR(10), 1); mbar_init(BAR(11), 1);
@@ -484,6 +511,7 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();                // the partner's barriers exist before any multicast copy / commit can reach them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t D1 = tmem, D2 = tmem + 256;   // D3 aliases D1, D4 aliases D2[0:16]
@@ -495,7 +523,7 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
     if (warp == 8) {
         // ===== producer (warp-uniform loop, one elected lane issues the copies) =====
         uint32_t it = 0, tl = 0;
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
+        for (long long tile = blockIdx.x; tile < nt_loop; tile += gridDim.x, ++tl) {
             for (int step = 0; step < STEPS_TRAIN; ++step, ++it) {
                 const uint32_t s = it & 1, ph = (it >> 1) & 1;
                 const uint32_t bytes = (step < 17) ? PANEL_B : PANEL_B16;
@@ -503,10 +531,14 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
                 mbar_wait(BAR(2 + s), ph ^ 1);
                 NL_STAMP(0, step, 1);
                 if (elect_one()) {
-                    mbar_expect_tx(BAR(0 + s), 2 * bytes);
+                    mbar_expect_tx(BAR(0 + s), 2 * bytes);            // hi + lo land in this CTA whoever fetches them
                     const uint8_t *src = p.panels + (size_t)step * STAGE_B;
-                    bulk_g2s(sB + s * STAGE_B, src, bytes, BAR(0 + s));
-                    bulk_g2s(sB + s * STAGE_B + PANEL_B, src + PANEL_B, bytes, BAR(0 + s));
+                    if (PAIR) {                                       // this CTA fetches one of the two panels for both CTAs
+                        bulk_g2s_pair(sB + s * STAGE_B + pair_rank * PANEL_B, src + pair_rank * PANEL_B, bytes, BAR(0 + s));
+                    } else {
+                        bulk_g2s(sB + s * STAGE_B, src, bytes, BAR(0 + s));
+                        bulk_g2s(sB + s * STAGE_B + PANEL_B, src + PANEL_B, bytes, BAR(0 + s));
+                    }
                 }
                 __syncwarp();
             }
@@ -515,7 +547,7 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
         // ===== MMA issuer (warp-uniform loop, one elected lane issues) =====
         constexpr uint32_t idesc256 = make_idesc(TM, WN), idesc16 = make_idesc(TM, 16);
         uint32_t it = 0, tl = 0;
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
+        for (long long tile = blockIdx.x; tile < nt_loop; tile += gridDim.x, ++tl) {
             for (int step = 0; step < STEPS_TRAIN; ++step, ++it) {
                 const uint32_t s = it & 1, ph = (it >> 1) & 1;
                 NL_STAMP(1, step, 0);
@@ -535,7 +567,7 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
                         else if (step <= 16) issue_kblock<4, 2>(D1, a_hi, b_hi, idesc256, step == 9 ? 0u : 1u);   // backward layer 2: the 0/1
                                                                                                                   // mask operand has no lo part
                         else issue_kblock<4, 3>(D2, a_hi, b_hi, idesc16, step == 17 ? 0u : 1u);                   // backward layer 1 (N = 16)
-                        tc_commit(BAR(2 + s));
+                        if (PAIR) tc_commit_pair(BAR(2 + s)); else tc_commit(BAR(2 + s));
                         tc_commit(BAR(6 + as));
                         if (step == 0) tc_commit(BAR(8));
                         if (step == 8) tc_commit(BAR(9));
@@ -559,7 +591,7 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
                                 acc = 1u;
                             }
                         }
-                        tc_commit(BAR(2 + s));
+                        if (PAIR) tc_commit_pair(BAR(2 + s)); else tc_commit(BAR(2 + s));
                         if (step == 16) tc_commit(BAR(10));
                     }
                 } else {
@@ -581,7 +613,7 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
                                 acc = 1u;
                             }
                         }
-                        tc_commit(BAR(2 + s));
+                        if (PAIR) tc_commit_pair(BAR(2 + s)); else tc_commit(BAR(2 + s));
                         tc_commit(BAR(16 + g));
                         if (step == 24) tc_commit(BAR(11));
                     }
@@ -631,7 +663,7 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
         };
         prefetch(blockIdx.x);
         uint32_t tl = 0;
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
+        for (long long tile = blockIdx.x; tile < nt_loop; tile += gridDim.x, ++tl) {
             const long long m = tile * TM + row;
             const bool live = m < M;
             const uint32_t fl = fl_n;
@@ -686,7 +718,7 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
                 fence_proxy_async();
                 if (q == 0 && lane == 0) NL_STAMP(2 + g, 1 + kb, 7);
                 __syncwarp();
-                if (WGRAD && lane == 0) bulk_s2g(p.act_h1 + ((size_t)(tile * 8 + kb) * TM + q * 32) * 32, sA + s * STAGE_A + q * 4096, 4096);
+                if (WGRAD && lane == 0 && tile < ntiles) bulk_s2g(p.act_h1 + ((size_t)(tile * 8 + kb) * TM + q * 32) * 32, sA + s * STAGE_A + q * 4096, 4096);
                 if (lane == 0) mbar_arrive(BAR(4 + s));
                 if (q == 0 && lane == 0) NL_STAMP(2 + g, 1 + kb, 3);
             }
@@ -744,7 +776,7 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
                     }
                 }
             }
-            if (WGRAD) {
+            if (WGRAD && tile < ntiles) {            // (PAIR: a padding tile beyond the data has no panel rows)
                 if (g == 0) {
                     gb2r += dsdf;
                     p.act_dsdf[tile * TM + row] = dsdf;
@@ -811,7 +843,7 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
                         for (int c = 0; c < 8; ++c) st_shared_v4(sg + offc[c], h[c * 4], h[c * 4 + 1], h[c * 4 + 2], h[c * 4 + 3]);
                         fence_proxy_async();
                         __syncwarp();
-                        if (lane == 0) bulk_s2g(p.act_dh1 + ((size_t)(tile * 8 + kb) * TM + q * 32) * 32, sg + q * 4096, 4096);
+                        if (lane == 0 && tile < ntiles) bulk_s2g(p.act_dh1 + ((size_t)(tile * 8 + kb) * TM + q * 32) * 32, sg + q * 4096, 4096);
                     }
                 } else {
                     const uint32_t it = AIT(tl, 17 + kb), s = it & 1, ph = (it >> 1) & 1;
@@ -821,7 +853,7 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
                     store_a_row_fast(sA + s * STAGE_A, offc, h);
                     fence_proxy_async();
                     __syncwarp();
-                    if (WGRAD && lane == 0) bulk_s2g(p.act_dh1 + ((size_t)(tile * 8 + kb) * TM + q * 32) * 32, sA + s * STAGE_A + q * 4096, 4096);
+                    if (WGRAD && lane == 0 && tile < ntiles) bulk_s2g(p.act_dh1 + ((size_t)(tile * 8 + kb) * TM + q * 32) * 32, sA + s * STAGE_A + q * 4096, 4096);
                     if (lane == 0) mbar_arrive(BAR(4 + s));
                 }
                 if (q == 0 && lane == 0) NL_STAMP(2 + g, 17 + kb, 3);
@@ -830,7 +862,7 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
                 if (lane == 0) bulk_wait_read();
                 asm volatile("bar.sync 2, 256;" ::: "memory");
             }
-            if (TS && g == 0 && tile + gridDim.x < ntiles) {
+            if (TS && g == 0 && tile + gridDim.x < nt_loop) {
                 // x of the next tile (prefetched above) -> its activation stage now: the MMA warp can issue the next layer 1
                 // right behind this tile's last backward MMAs instead of waiting for the d x read-back below
                 const uint32_t it = AIT(tl + 1, 0), s = it & 1, ph = (it >> 1) & 1;
@@ -884,10 +916,31 @@ __global__ void __launch_bounds__(NTHREADS_TRAIN, 1) k_mlp_tc_train(TrainParams 
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();                // neither CTA leaves while the other may still multicast into it
     if (warp == 9) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
     }
+}
+
+// launch as clusters of two CTAs (even grid, at most one CTA per SM)
+template <class K>
+int launch_pair(K kernel, int grid, int sms, const TrainParams &p, cudaStream_t stream) {
+    grid = (grid + 1) & ~1;
+    if (grid > (sms & ~1)) grid = sms & ~1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3(NTHREADS_TRAIN, 1, 1);
+    cfg.dynamicSmemBytes = SMEM_TOTAL;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, p);
+    if (e != cudaSuccess) return nl_set_error_code(NL_ERR_CUDA, cudaGetErrorString(e));
+    return NL_OK;
 }
 
 // ================================================================================================
@@ -1368,10 +1421,12 @@ extern "C" int nl_mlp_tc_train(int64_t M, const int32_t *d_M_dev, const float *f
     std::lock_guard<std::mutex> dev_lock(dev_mu);
     bool &configured = configured_dev[cur_dev];
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc::k_mlp_tc_train<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::k_mlp_tc_train<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::k_mlp_tc_train<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::k_mlp_tc_train<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL);
+        cudaError_t e = cudaFuncSetAttribute(tc::k_mlp_tc_train<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::k_mlp_tc_train<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::k_mlp_tc_train<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::k_mlp_tc_train<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::k_mlp_tc_train<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::k_mlp_tc_train<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL);
 #define NL_DW_ATTR(K, NR, NC, SM)                                                                                               \
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::K<4, NR, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SM(NR, NC)); \
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::K<8, NR, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SM(NR, NC));
@@ -1388,7 +1443,9 @@ extern "C" int nl_mlp_tc_train(int64_t M, const int32_t *d_M_dev, const float *f
     p.truncation = truncation; p.dsdf_ext = dsdf_ext;
     const long long ntiles = (M + tc::TM - 1) / tc::TM;
     const int sms = nl_num_sms();
-    const int grid = (int)(ntiles < (long long)sms ? ntiles : (long long)sms);
+    int grid = (int)(ntiles < (long long)sms ? ntiles : (long long)sms);
+    // NL_TC_PAIR=1: CTA pairs share every weight stage through multicast copies (see k_mlp_tc_train); needs TS and an even grid
+    static const bool use_pair = [] { const char *e = getenv("NL_TC_PAIR"); return e ? atoi(e) != 0 : false; }();
     static long long *dbg_dev = nullptr;
     static int dbg_calls = 0;
     const bool want_dbg = getenv("NL_TC_TIMELINE") != nullptr;
@@ -1405,8 +1462,9 @@ extern "C" int nl_mlp_tc_train(int64_t M, const int32_t *d_M_dev, const float *f
         p.act_h1 = act; p.act_dh1 = act + panel; p.act_dsdf = act + 2 * panel;
         p.act_mask2 = reinterpret_cast<uint32_t *>(act + 2 * panel + (size_t)ntiles * tc::TM);
         p.gb2 = grads->gb2;
-        if (use_ts) tc::k_mlp_tc_train<true, true><<<grid, tc::NTHREADS_TRAIN, tc::SMEM_TOTAL, stream>>>(p);
-        else tc::k_mlp_tc_train<true, false><<<grid, tc::NTHREADS_TRAIN, tc::SMEM_TOTAL, stream>>>(p);
+        if (use_ts && use_pair) { if (int rc = tc::launch_pair(tc::k_mlp_tc_train<true, true, true>, grid, sms, p, stream)) return rc; }
+        else if (use_ts) tc::k_mlp_tc_train<true, true, false><<<grid, tc::NTHREADS_TRAIN, tc::SMEM_TOTAL, stream>>>(p);
+        else tc::k_mlp_tc_train<true, false, false><<<grid, tc::NTHREADS_TRAIN, tc::SMEM_TOTAL, stream>>>(p);
         // The weight-gradient kernels only need what the kernel above wrote; on a second stream they overlap with whatever the
         // caller enqueues next on `stream` (the embedding scatter, which is L2-atomic bound and leaves the SMs mostly idle).
         cudaStream_t ws = wgrad_stream_ ? (cudaStream_t)wgrad_stream_ : stream;
@@ -1431,8 +1489,9 @@ extern "C" int nl_mlp_tc_train(int64_t M, const int32_t *d_M_dev, const float *f
 #undef NL_DW_LAUNCH
         tc::k_mask_colsum<<<sms * 8, 256, 0, ws>>>(M, d_M_dev, p.act_mask2, p.act_dsdf, b1, w2, grads->gb1, grads->gW2);
     } else {
-        if (use_ts) tc::k_mlp_tc_train<false, true><<<grid, tc::NTHREADS_TRAIN, tc::SMEM_TOTAL, stream>>>(p);
-        else tc::k_mlp_tc_train<false, false><<<grid, tc::NTHREADS_TRAIN, tc::SMEM_TOTAL, stream>>>(p);
+        if (use_ts && use_pair) { if (int rc = tc::launch_pair(tc::k_mlp_tc_train<false, true, true>, grid, sms, p, stream)) return rc; }
+        else if (use_ts) tc::k_mlp_tc_train<false, true, false><<<grid, tc::NTHREADS_TRAIN, tc::SMEM_TOTAL, stream>>>(p);
+        else tc::k_mlp_tc_train<false, false, false><<<grid, tc::NTHREADS_TRAIN, tc::SMEM_TOTAL, stream>>>(p);
     }
     NL_CHECK_LAUNCH("nl_mlp_tc_train");
     if (want_dbg && ++dbg_calls == 8) {   // debug only: dump one steady-state tile timeline of CTA 0 (synchronises)
