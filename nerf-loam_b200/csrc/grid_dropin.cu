@@ -1,6 +1,7 @@
 // Drop-in replacements for the two live kernels of the reference's `grid` CUDA extension
 // (third_party/sparse_voxels/src/binding.cpp:12-20): svo_intersect and inverse_cdf_sampling.
 // Same tensor layouts in and out, results bit-identical to the reference kernels on the same GPU.
+#include "sampler.cuh"
 #include "traverse.cuh"
 
 namespace {
@@ -30,75 +31,46 @@ __global__ void __launch_bounds__(128) svo_intersect_kernel(int n, int m, float 
     });
 }
 
-// sample_gpu.cu:133-239, one thread per ray, grid = (ceil(num_rays/128), b).
-// `min + u*(max-min)` is one FMA in the reference binary (nvcc -fmad default), written explicitly here.
-__global__ void __launch_bounds__(128) inverse_cdf_sampling_kernel(
-    int num_rays, int max_hits, int max_steps, float fixed_step_size, const int32_t *__restrict__ pts_idx,
-    const float *__restrict__ min_depth, const float *__restrict__ max_depth, const float *__restrict__ uniform_noise,
-    const float *__restrict__ probs, const float *__restrict__ steps, int32_t *__restrict__ sampled_idx,
-    float *__restrict__ sampled_depth, float *__restrict__ sampled_dists) {
-    const int batch = blockIdx.y;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= num_rays) return;
-    pts_idx += (size_t)batch * num_rays * max_hits;
-    min_depth += (size_t)batch * num_rays * max_hits;
-    max_depth += (size_t)batch * num_rays * max_hits;
-    probs += (size_t)batch * num_rays * max_hits;
-    steps += (size_t)batch * num_rays;
-    uniform_noise += (size_t)batch * num_rays * max_steps;
-    sampled_idx += (size_t)batch * num_rays * max_steps;
-    sampled_depth += (size_t)batch * num_rays * max_steps;
-    sampled_dists += (size_t)batch * num_rays * max_steps;
+// grid.inverse_cdf_sampling: one thread per ray, grid = (ceil(num_rays/128), b); outputs padded with -1 / 0 like sample.cpp:82-90.
+// The walk itself is nl_inverse_cdf_walk (sampler.cuh), the same routine the fused sampler runs; this wrapper only adapts the
+// reference's [b, num_rays, max_hits] / [b, num_rays, max_steps] tensors and states its two tail quirks in their original form:
+// the tail is flushed only while  num_rays > ray * max_hits + bin,  and its continuation test reads pts_idx[bin] of the
+// batch's FIRST ray (sample_gpu.cu:224-231).
+struct RayBinsGlobal {
+    const int32_t *i; const float *a, *b, *p;
+    __device__ __forceinline__ int idx(int c) const { return i[c]; }
+    __device__ __forceinline__ float lo(int c) const { return a[c]; }
+    __device__ __forceinline__ float hi(int c) const { return b[c]; }
+    __device__ __forceinline__ float prob(int c) const { return p[c]; }
+};
 
-    const int H = j * max_hits;
-    const size_t K = (size_t)j * max_steps;
-    for (int s = 0; s < max_steps; ++s) { sampled_idx[K + s] = -1; sampled_depth[K + s] = 0.f; sampled_dists[K + s] = 0.f; }  // sample.cpp:82-90
-    int curr_bin = 0, s = 0;
-    float curr_min_depth = min_depth[H];
-    float curr_max_depth = max_depth[H];
-    float curr_min_cdf = 0.f;
-    float curr_max_cdf = probs[H];
-    float step_size = __frcp_rn(steps[j]);  // (float)(1.0 / (double)x) == correctly rounded 1/x
-    float z_low = curr_min_depth;
-    const int total_steps = (int)ceilf(steps[j]);
-    bool done = false;
-    if (fixed_step_size > 0.0f) step_size = fixed_step_size;
-    for (int curr_step = 0; curr_step < total_steps; ++curr_step) {
-        const float curr_cdf = __fmul_rn(__fadd_rn((float)curr_step, uniform_noise[K + curr_step]), step_size);
-        while (curr_cdf > curr_max_cdf) {
-            sampled_idx[K + s] = pts_idx[H + curr_bin];
-            sampled_dists[K + s] = __fsub_rn(curr_max_depth, z_low);
-            sampled_depth[K + s] = __fmul_rn(__fadd_rn(curr_max_depth, z_low), 0.5f);
-            ++curr_bin;
-            ++s;
-            if ((curr_bin >= max_hits) || (pts_idx[H + curr_bin] == -1)) { done = true; break; }
-            curr_min_depth = min_depth[H + curr_bin];
-            curr_max_depth = max_depth[H + curr_bin];
-            curr_min_cdf = curr_max_cdf;
-            curr_max_cdf = __fadd_rn(curr_max_cdf, probs[H + curr_bin]);
-            z_low = curr_min_depth;
-        }
-        if (done) break;
-        const float u = __fdiv_rn(__fsub_rn(curr_cdf, curr_min_cdf), __fsub_rn(curr_max_cdf, curr_min_cdf));
-        const float z = __fmaf_rn(u, __fsub_rn(curr_max_depth, curr_min_depth), curr_min_depth);
-        sampled_idx[K + s] = pts_idx[H + curr_bin];
-        sampled_dists[K + s] = __fsub_rn(z, z_low);
-        sampled_depth[K + s] = __fmul_rn(__fadd_rn(z, z_low), 0.5f);
-        z_low = z;
-        ++s;
-    }
-    // sample_gpu.cu:224-238, quirks kept: `num_rays > H + curr_bin` and `pts_idx[curr_bin]` (no +H)
-    while ((z_low < curr_max_depth) && (!done) && (num_rays > (H + curr_bin))) {
-        sampled_idx[K + s] = pts_idx[H + curr_bin];
-        sampled_dists[K + s] = __fsub_rn(curr_max_depth, z_low);
-        sampled_depth[K + s] = __fmul_rn(__fadd_rn(curr_max_depth, z_low), 0.5f);
-        ++curr_bin;
-        ++s;
-        if ((curr_bin >= max_hits) || (pts_idx[curr_bin] == -1)) break;
-        curr_min_depth = min_depth[H + curr_bin];
-        curr_max_depth = max_depth[H + curr_bin];
-        z_low = curr_min_depth;
-    }
+__global__ void __launch_bounds__(128) k_inverse_cdf_dropin(int num_rays, int max_hits, int max_steps, float fixed_step_size,
+                                                             const int32_t *__restrict__ pts_idx, const float *__restrict__ min_depth,
+                                                             const float *__restrict__ max_depth, const float *__restrict__ uniform_noise,
+                                                             const float *__restrict__ probs, const float *__restrict__ steps,
+                                                             int32_t *__restrict__ sampled_idx, float *__restrict__ sampled_depth,
+                                                             float *__restrict__ sampled_dists) {
+    const int ray = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= num_rays) return;
+    const size_t batch_hits = (size_t)blockIdx.y * num_rays * max_hits, batch_steps = (size_t)blockIdx.y * num_rays * max_steps;
+    const int32_t *first_ray_idx = pts_idx + batch_hits;
+    const size_t h0 = batch_hits + (size_t)ray * max_hits, s0 = batch_steps + (size_t)ray * max_steps;
+    const RayBinsGlobal bins = {pts_idx + h0, min_depth + h0, max_depth + h0, probs + h0};
+    int32_t *o_idx = sampled_idx + s0;
+    float *o_depth = sampled_depth + s0, *o_len = sampled_dists + s0;
+    for (int s = 0; s < max_steps; ++s) { o_idx[s] = -1; o_depth[s] = 0.f; o_len[s] = 0.f; }
+    const float *nz = uniform_noise + s0;
+    const int flat = ray * max_hits;
+    int n = 0;
+    nl_inverse_cdf_walk(
+        max_hits, bins, steps[(size_t)blockIdx.y * num_rays + ray], fixed_step_size, [&](int i) { return nz[i]; },
+        [&](int vox, float z0, float z1) {
+            o_idx[n] = vox;
+            o_len[n] = __fsub_rn(z1, z0);
+            o_depth[n] = __fmul_rn(__fadd_rn(z1, z0), 0.5f);
+            ++n;
+        },
+        [&](int bin) { return num_rays > flat + bin; }, [&](int bin) { return first_ray_idx[bin]; });
 }
 
 }  // namespace
@@ -128,9 +100,8 @@ extern "C" int nl_inverse_cdf_sampling(int b, int num_rays, int max_hits, int ma
         return nl_set_error("nl_inverse_cdf_sampling: null pointer");
     if (b > 65535) return nl_set_error("nl_inverse_cdf_sampling: more than 65535 batches");
     dim3 grid(nl_div_up(num_rays, 128), b);
-    inverse_cdf_sampling_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(num_rays, max_hits, max_steps, fixed_step_size, pts_idx,
-                                                                        min_depth, max_depth, noise, probs, steps, sampled_idx,
-                                                                        sampled_depth, sampled_dists);
+    k_inverse_cdf_dropin<<<grid, 128, 0, (cudaStream_t)stream>>>(num_rays, max_hits, max_steps, fixed_step_size, pts_idx, min_depth, max_depth,
+                                                                 noise, probs, steps, sampled_idx, sampled_depth, sampled_dists);
     NL_CHECK_LAUNCH("nl_inverse_cdf_sampling");
     return NL_OK;
 }

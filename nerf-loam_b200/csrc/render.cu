@@ -16,6 +16,7 @@
 // The reference keeps every intermediate as a padded dense tensor and syncs the host 6 times to size them.
 #include <cstdlib>
 
+#include "sampler.cuh"
 #include "traverse.cuh"
 
 namespace {
@@ -481,49 +482,26 @@ __global__ void __launch_bounds__(128) k_sample(SampleParams p, Workspace ws, nl
             ++nsamp;
         };
 
-        // ---- sample_gpu.cu:165-238 ----
-        int curr_bin = 0;
-        float curr_min_depth = bmin[0], curr_max_depth = bmax[0];
-        float curr_min_cdf = 0.f, curr_max_cdf = prob[0];
-        const float inv_steps = __frcp_rn(steps);
-        float z_low = curr_min_depth;
-        const int total_steps = (int)ceilf(steps);
+        // ---- the walk (sampler.cuh).  Tail quirks of the reference's batched launch, in terms of this ray's slot j in its
+        //      (batch, chunk) of num_rays rays: flush only while num_rays > j*P + bin; continuation test on the chunk's leader ray ----
         uint32_t seed = p.rng_seed;
         if (p.rng_seed_dev) { seed = *p.rng_seed_dev; seed = seed ? seed : 1u; }
-        bool done = false;
-        for (int curr_step = 0; curr_step < total_steps; ++curr_step) {
-            float nz = 0.5f;
-            if (p.noise) nz = p.noise[(size_t)q * p.noise_stride + curr_step];
-            else if (seed) nz = hash_uniform(seed, (uint32_t)r, (uint32_t)curr_step);
-            const float curr_cdf = __fmul_rn(__fadd_rn((float)curr_step, nz), inv_steps);
-            while (curr_cdf > curr_max_cdf) {
-                emit(bidx[curr_bin], __fmul_rn(__fadd_rn(curr_max_depth, z_low), 0.5f));
-                ++curr_bin;
-                if (curr_bin >= P || bidx[curr_bin] == -1) { done = true; break; }
-                curr_min_depth = bmin[curr_bin];
-                curr_max_depth = bmax[curr_bin];
-                curr_min_cdf = curr_max_cdf;
-                curr_max_cdf = __fadd_rn(curr_max_cdf, prob[curr_bin]);
-                z_low = curr_min_depth;
-            }
-            if (done) break;
-            const float u = __fdiv_rn(__fsub_rn(curr_cdf, curr_min_cdf), __fsub_rn(curr_max_cdf, curr_min_cdf));
-            const float z = __fmaf_rn(u, __fsub_rn(curr_max_depth, curr_min_depth), curr_min_depth);
-            emit(bidx[curr_bin], __fmul_rn(__fadd_rn(z, z_low), 0.5f));
-            z_low = z;
-        }
-        // tail (sample_gpu.cu:224-238).  compat: `num_rays > j*P + curr_bin` gate and the leader ray's pts_idx
-        // in the continuation test; otherwise the evidently intended per-ray versions.
-        while ((z_low < curr_max_depth) && !done && (!p.compat || num_rays > (H + curr_bin))) {
-            emit(bidx[curr_bin], __fmul_rn(__fadd_rn(curr_max_depth, z_low), 0.5f));
-            ++curr_bin;
-            if (curr_bin >= P) break;
-            const int probe = p.compat ? ws.h_idx[(size_t)curr_bin * R + r_lead] : bidx[curr_bin];
-            if (probe == -1) break;
-            curr_min_depth = bmin[curr_bin];
-            curr_max_depth = bmax[curr_bin];
-            z_low = curr_min_depth;
-        }
+        struct {
+            const int32_t *i; const float *a, *b, *pr;
+            __device__ __forceinline__ int idx(int c) const { return i[c]; }
+            __device__ __forceinline__ float lo(int c) const { return a[c]; }
+            __device__ __forceinline__ float hi(int c) const { return b[c]; }
+            __device__ __forceinline__ float prob(int c) const { return pr[c]; }
+        } bins = {bidx, bmin, bmax, prob};
+        nl_inverse_cdf_walk(
+            P, bins, steps, -1.0f,
+            [&](int i) {
+                if (p.noise) return p.noise[(size_t)q * p.noise_stride + i];
+                return seed ? hash_uniform(seed, (uint32_t)r, (uint32_t)i) : 0.5f;
+            },
+            [&](int vox, float z0, float z1) { emit(vox, __fmul_rn(__fadd_rn(z1, z0), 0.5f)); },
+            [&](int bin) { return !p.compat || num_rays > (H + bin); },
+            [&](int bin) { return p.compat ? ws.h_idx[(size_t)bin * R + r_lead] : bidx[bin]; });
 
         if (!FILL) {
             p.ray_nsamp[r] = nsamp;
