@@ -26,4 +26,19 @@ def install(reference_src=None):
         ref_lidar.Decoder = lidar.Decoder                        # get_decoder: variations.<name>.Decoder (import_util.py:8-10)
     except ModuleNotFoundError:
         pass                                                      # reference sources not on the path: only `grid` is installed
+    # the two seams outside the per-iteration path; their reference modules import open3d / skimage / the data loaders, so they are
+    # rebound only where those imports succeed (a real NeRF-LOAM environment)
+    try:
+        mesh_util = importlib.import_module("utils.mesh_util")
+        mesh = importlib.import_module(pkg.__name__ + ".mesh")
+        mesh_util.get_scores = rh.get_scores                      # mesh_util.py:8 imported the name at module level
+        mesh_util.MeshExtractor.marching_cubes = lambda self, voxels, sdf: mesh.marching_cubes(voxels, sdf, self.voxel_size)   # mesh_util.py:145
+    except Exception:
+        pass
+    try:
+        ref_share = importlib.import_module("share")
+        share = importlib.import_module(pkg.__name__ + ".share")
+        ref_share.ShareData, ref_share.ShareDataProxy = share.ShareData, share.ShareDataProxy    # nerfloam.py registers these with its BaseManager
+    except Exception:
+        pass
     return pkg

@@ -165,7 +165,26 @@ class MapState:
 
 
 class DecoderBuffers:
-    """Flat device views of the decoder parameters for the kernels + transposes + fp32 gradient buffers."""
+    """Flat device views of the decoder parameters for the kernels + transposes + fp32 gradient buffers.
+    DecoderBuffers.of(decoder, device) returns a cached instance per decoder module (weakly referenced, validated against the
+    parameters' addresses): the drop-in entry points are called once per scan / per autograd node, and re-allocating 1.6 MB of weight
+    panels + gradient buffers each time is pure overhead.  The kernel-side weight images are still re-derived from the parameters
+    whenever they are used (refresh_transposes): the optimiser kernels update parameters through raw pointers."""
+    _cache = None
+
+    @classmethod
+    def of(cls, decoder, device):
+        import weakref
+        if cls._cache is None:
+            cls._cache = weakref.WeakKeyDictionary()
+        lin = list(decoder.pts_linears)
+        key = (str(device), mlp_impl(lin[0].weight.shape[0])) + tuple(p.data_ptr() for p in (lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias,
+                                                                                            decoder.sdf_out.weight, decoder.sdf_out.bias))
+        hit = cls._cache.get(decoder)
+        if hit is None or hit[0] != key:
+            hit = (key, cls(decoder, device))
+            cls._cache[decoder] = hit
+        return hit[1]
 
     def __init__(self, decoder, device):
         lin = list(decoder.pts_linears)

@@ -28,7 +28,7 @@ class Same(nn.Module):
 class _DecoderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, dec, *params):
-        bufs = DecoderBuffers(dec, x.device)
+        bufs = DecoderBuffers.of(dec, x.device)
         bufs.refresh_transposes()
         M = x.shape[0]
         sdf = torch.empty(M, dtype=torch.float32, device=x.device)
@@ -41,7 +41,7 @@ class _DecoderFn(torch.autograd.Function):
     def backward(ctx, gout):
         (x,) = ctx.saved_tensors
         dec = ctx.dec
-        bufs = DecoderBuffers(dec, x.device)
+        bufs = DecoderBuffers.of(dec, x.device)
         bufs.refresh_transposes()
         M, W = x.shape[0], bufs.width
         sdf = torch.empty(M, dtype=torch.float32, device=x.device)
@@ -49,8 +49,9 @@ class _DecoderFn(torch.autograd.Function):
         need_w = any(ctx.needs_input_grad[2:])
         act = alloc_act(W, M, x.device) if need_w else None
         g = gout.reshape(-1).contiguous().float()
+        bufs.gradflat.zero_()                       # the buffers are cached per decoder (DecoderBuffers.of): start from zero ...
         mlp_train(bufs, M, None, x, sdf, dx, need_w, act, dsdf_ext=g)
-        grads = bufs.grads if need_w else [None] * 6
+        grads = [t.clone() for t in bufs.grads] if need_w else [None] * 6      # ... and hand autograd its own copies
         return (dx if ctx.needs_input_grad[0] else None, None, *grads)
 
 

@@ -88,8 +88,9 @@ class _RenderSDF(torch.autograd.Function):
         m, dec_mod, cfg = s["m"], s["dec"], s["cfg"]
         M = s["xyz"].shape[0]
         dev = s["xyz"].device
-        bufs = DecoderBuffers(dec_mod, dev)
+        bufs = DecoderBuffers.of(dec_mod, dev)
         bufs.refresh_transposes()
+        bufs.gradflat.zero_()
         need_dec = any(ctx.needs_input_grad[4:])
         W = bufs.width
         sdf = torch.empty(M, dtype=torch.float32, device=dev)
@@ -113,7 +114,7 @@ class _RenderSDF(torch.autograd.Function):
             ray = s["ray"].long()
             g_o = torch.zeros((s["R"], 3), dtype=torch.float32, device=dev).index_add_(0, ray, dxyz)
             g_d = torch.zeros((s["R"], 3), dtype=torch.float32, device=dev).index_add_(0, ray, dxyz * s["depth"].unsqueeze(-1))
-        dec_grads = bufs.grads if need_dec else [None] * 6
+        dec_grads = [t.clone() for t in bufs.grads] if need_dec else [None] * 6      # own copies: the buffers are cached per decoder
         return (g_o, g_d, grad_emb.to(m.emb.dtype) if need_emb else None, None, *dec_grads)
 
 
@@ -141,7 +142,7 @@ def render_rays(rays_o, rays_d, map_states, sdf_network, step_size, voxel_size, 
         emb_in = m.emb
     cfg = _cfg(step_size, voxel_size, max_distance)
     seed = 0 if (deterministic or noise is not None) else _seed_from_torch()
-    bufs = DecoderBuffers(sdf_network, dev)
+    bufs = DecoderBuffers.of(sdf_network, dev)
     with torch.no_grad():
         eng, st = _run_with_capacity(lambda e: e.forward(m, bufs, R, cfg, ro.detach(), rd.detach(), noise, seed, reference_compat),
                                      R, dev)
@@ -182,7 +183,7 @@ def scores_device(sdf_network, map_states, voxel_size, bits=8, nodes=None, chunk
     if nodes is None:
         nodes = (m.vox2row[:, 0] >= 0).nonzero().view(-1)
     offs = _lattice_offsets(res, voxel_size, dev)
-    bufs = DecoderBuffers(sdf_network, dev)
+    bufs = DecoderBuffers.of(sdf_network, dev)
     bufs.refresh_transposes()
     out = torch.empty((nodes.shape[0], res ** 3), dtype=torch.float32, device=dev)
     chunk = max(1, chunk // (res ** 3) * 8)                   # voxels per launch (~0.5 M lattice points)
@@ -210,7 +211,7 @@ def get_scores(sdf_network, map_states, voxel_size, bits=8):
     m = map_states if isinstance(map_states, MapState) else MapState.from_map_states(map_states, dev)
     res = int(bits)
     lat, nodes = scores_device(sdf_network, m, voxel_size, res)
-    bufs = DecoderBuffers(sdf_network, dev)
+    bufs = DecoderBuffers.of(sdf_network, dev)
     bufs.refresh_transposes()
     zero = torch.zeros((1, 16), dtype=torch.float32, device=dev)
     const = torch.empty(1, dtype=torch.float32, device=dev)
