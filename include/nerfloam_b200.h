@@ -326,8 +326,6 @@ NL_API int nl_peer_reduce_adam_bf16(int64_t n_elems, int rank, int world, const 
                              const float *d_hdr_mc, float *d_hdr_out, void *stream);
 /* (hdr_n floats in front of each rank's table -- loss sums, pose accumulators -- are summed over the ranks into the LOCAL
  * d_hdr_out by the same launch; hdr_n % 4 == 0, may be 0) */
-/* out[i] = sum over ranks of peer_q[i], i < n (n % 4 == 0; loss sums and pose accumulators), into a LOCAL buffer */
-NL_API int nl_peer_reduce_f32(int64_t n, int world, const float *const *d_peers, const float *d_mc, float *d_out, void *stream);
 
 /* ============================================================================================
  * 10. Sparse marching cubes over the per-voxel SDF lattices of get_scores -- replaces MeshExtractor.marching_cubes

@@ -107,7 +107,6 @@ _SIGNATURES = {
     "nl_stats_unpack_peers": (C.c_int, [vp, vp, C.c_int, C.c_float, C.c_float, vp]),
     "nl_peer_reduce_adam_bf16": (C.c_int, [C.c_int64, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, C.c_double, vp,
                                           C.c_int64, vp, vp, vp, vp]),
-    "nl_peer_reduce_f32": (C.c_int, [C.c_int64, C.c_int, vp, vp, vp, vp]),
     "nl_mc_count": (C.c_int, [C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp]),
     "nl_mc_emit": (C.c_int, [C.c_int32, C.c_int32, C.c_float, vp, vp, vp, vp, vp, C.c_int64, C.c_int64, vp, vp, vp]),
     "nl_mc_case_table": (C.c_int, [vp, vp, vp]),

@@ -104,24 +104,6 @@ __global__ void __launch_bounds__(256) k_reduce_adam_bf16(long long e0, long lon
     }
 }
 
-// small vectors (loss sums, pose accumulators): every rank reduces all n floats into a LOCAL output (n <= a few hundred)
-template <bool MC>
-__global__ void k_reduce_small(int n4, int world, const float *const *peers, const float *mc, float *__restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n4) return;
-    float4 s;
-    if (MC) {
-        s = mc_ld_reduce_f32x4(mc + 4 * i);
-    } else {
-        s = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int q = 0; q < world; ++q) {
-            const float4 a = *reinterpret_cast<const float4 *>(peers[q] + 4 * i);
-            s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
-        }
-    }
-    *reinterpret_cast<float4 *>(out + 4 * i) = s;
-}
-
 }  // namespace
 
 extern "C" int nl_peer_reduce_adam_bf16(int64_t n_elems, int rank, int world, const float *const *d_grad_peers, const float *d_grad_mc,
@@ -145,16 +127,5 @@ extern "C" int nl_peer_reduce_adam_bf16(int64_t n_elems, int rank, int world, co
                                                                             d_m, d_v, lr, beta1, beta2, (float)eps, d_ctl, (int)(hdr_n / 4), d_hdr_peers,
                                                                             nullptr, d_hdr_out);
     NL_CHECK_LAUNCH("nl_peer_reduce_adam_bf16");
-    return NL_OK;
-}
-
-extern "C" int nl_peer_reduce_f32(int64_t n, int world, const float *const *d_peers, const float *d_mc, float *d_out, void *stream) {
-    if (n < 0 || (n & 3) || world < 1) return nl_set_error("nl_peer_reduce_f32: n must be a non-negative multiple of 4");
-    if (n == 0) return NL_OK;
-    if (!d_peers || !d_out) return nl_set_error("nl_peer_reduce_f32: null pointer");
-    const int n4 = (int)(n / 4);
-    if (d_mc) k_reduce_small<true><<<nl_div_up(n4, 128), 128, 0, (cudaStream_t)stream>>>(n4, world, d_peers, d_mc, d_out);
-    else k_reduce_small<false><<<nl_div_up(n4, 128), 128, 0, (cudaStream_t)stream>>>(n4, world, d_peers, nullptr, d_out);
-    NL_CHECK_LAUNCH("nl_peer_reduce_f32");
     return NL_OK;
 }
