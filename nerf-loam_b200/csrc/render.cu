@@ -27,7 +27,10 @@ struct Workspace {
     float *h_max;     // [20][R]
     int32_t *nvalid;  // [R]
     int32_t *hitray;  // [R] ray index of the q-th hit ray
+    unsigned long long *scan;   // [2][SCAN_SCRATCH]: tile ticket + per-tile (ready << 32 | total) of the two chained scans; zeroed per call
 };
+constexpr int SCAN_MAX_TILES = 1024;                 // tiles of 4096 elements: up to 4 M rays per call in one wave of look-back
+constexpr int SCAN_SCRATCH = SCAN_MAX_TILES + 8;     // words per scan: [0] = ticket counter, [8 + tile] = published tile total
 
 __host__ __device__ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -39,6 +42,7 @@ inline Workspace carve(void *base, int R) {
     w.h_max = (float *)p; p += align256(sizeof(float) * NL_MAX_HITS * (size_t)R);
     w.nvalid = (int32_t *)p; p += align256(sizeof(int32_t) * (size_t)R);
     w.hitray = (int32_t *)p; p += align256(sizeof(int32_t) * (size_t)R);
+    w.scan = (unsigned long long *)p; p += align256(sizeof(unsigned long long) * 2 * SCAN_SCRATCH);
     return w;
 }
 
@@ -380,6 +384,119 @@ __global__ void __launch_bounds__(1024) k_scan(int n, const int32_t *__restrict_
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_scan_chained: the same two scans over many blocks (one 4096-element tile each) in a single pass.  A block takes a ticket
+// (so that every tile it may have to wait for belongs to a block that is already running), scans its tile, publishes the tile
+// total, and adds up the totals of the tiles before it -- one thread per predecessor, spinning until that total is published.
+// At 83 k rays that is 21 blocks and ~5 us instead of 17-30 us for the single-block loop above (which stays as the fallback for
+// more than 4 M rays).  scratch: [0] ticket, [8 + tile] (1 << 32 | total); zeroed by nl_render_samples before the chain starts.
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(1024) k_scan_chained(int n, const int32_t *__restrict__ in, int32_t *__restrict__ out,
+                                                        int32_t *__restrict__ hitray, nl_render_stats *stats, int sample_capacity,
+                                                        unsigned long long *scratch) {
+    __shared__ int s_warp[32];
+    __shared__ int s_tile, s_carry;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (t == 0) s_tile = (int)atomicAdd(&scratch[0], 1ULL);
+    __syncthreads();
+    const int tile = s_tile;
+    const int i0 = tile * 4096 + t * 4;
+    int4 x = make_int4(0, 0, 0, 0);
+    if (i0 + 3 < n) {
+        x = *reinterpret_cast<const int4 *>(in + i0);
+    } else {
+        if (i0 < n) x.x = in[i0];
+        if (i0 + 1 < n) x.y = in[i0 + 1];
+        if (i0 + 2 < n) x.z = in[i0 + 2];
+    }
+    int v[4] = {x.x, x.y, x.z, x.w};
+    if (MODE == SCAN_HITS) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = v[k] > 0;
+    }
+    const int mine = v[0] + v[1] + v[2] + v[3];
+    int incl = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += y;
+    }
+    if (lane == 31) s_warp[w] = incl;
+    __syncthreads();
+    const int ws_ = s_warp[lane];
+    int wi = ws_;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, wi, off);
+        if (lane >= off) wi += y;
+    }
+    const int wexcl = __shfl_sync(0xffffffffu, wi - ws_, w);
+    const int tile_total = __shfl_sync(0xffffffffu, wi, 31);
+    if (t == 0) {
+        __threadfence();
+        atomicExch(&scratch[8 + tile], (1ULL << 32) | (unsigned long long)(unsigned)tile_total);
+    }
+    // totals of the tiles before this one (gridDim.x <= 1024 = one thread per predecessor)
+    int prev = 0;
+    if (t < tile) {
+        unsigned long long a;
+        do { a = *((volatile unsigned long long *)&scratch[8 + t]); } while ((a >> 32) == 0ULL);
+        prev = (int)(unsigned)(a & 0xffffffffULL);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) prev += __shfl_down_sync(0xffffffffu, prev, off);
+    __syncthreads();                       // s_warp is reused
+    if (lane == 0) s_warp[w] = prev;
+    __syncthreads();
+    if (t == 0) {
+        int c = 0;
+        for (int k = 0; k < 32; ++k) c += s_warp[k];
+        s_carry = c;
+    }
+    __syncthreads();
+    const int carry = s_carry;
+    const int run = carry + wexcl + incl - mine;
+    if (MODE == SCAN_HITS) {
+        int4 o;
+        o.x = v[0] ? run : -1;
+        o.y = v[1] ? run + v[0] : -1;
+        o.z = v[2] ? run + v[0] + v[1] : -1;
+        o.w = v[3] ? run + v[0] + v[1] + v[2] : -1;
+        if (i0 + 3 < n) {
+            *reinterpret_cast<int4 *>(out + i0) = o;
+        } else {
+            if (i0 < n) out[i0] = o.x;
+            if (i0 + 1 < n) out[i0 + 1] = o.y;
+            if (i0 + 2 < n) out[i0 + 2] = o.z;
+        }
+        int loc = run;                     // positions ascend with the thread index: a warp's writes fall into one short range
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (v[k]) hitray[loc] = i0 + k;
+            loc += v[k];
+        }
+    } else {
+        const int4 o = make_int4(run, run + v[0], run + v[0] + v[1], run + v[0] + v[1] + v[2]);
+        if (i0 + 3 < n) {
+            *reinterpret_cast<int4 *>(out + i0) = o;
+        } else {
+            if (i0 < n) out[i0] = o.x;
+            if (i0 + 1 < n) out[i0 + 1] = o.y;
+            if (i0 + 2 < n) out[i0 + 2] = o.z;
+        }
+    }
+    if (tile == (int)gridDim.x - 1 && t == 0) {
+        const int total = carry + tile_total;
+        if (MODE == SCAN_HITS) {
+            stats->n_hit_rays = total;
+        } else {
+            stats->n_samples = total;
+            if (total > sample_capacity) atomicOr(&stats->error, 2);
+        }
+    }
+}
+
 // counter-based uniform noise in (0,1) for the stochastic sampler when no noise tensor is passed in
 __device__ __forceinline__ float hash_uniform(uint32_t seed, uint32_t ray, uint32_t step) {
     uint32_t x = seed ^ (ray * 0x9E3779B1u) ^ (step * 0x85EBCA77u);
@@ -707,7 +824,7 @@ extern "C" int nl_octree_pack_children_rows(int32_t n_ids, const int32_t *d_ids,
 extern "C" int64_t nl_render_workspace_bytes(int32_t n_rays) {
     if (n_rays < 0) return -1;
     const size_t R = (size_t)(n_rays > 0 ? n_rays : 1);
-    return (int64_t)(3 * align256(4 * NL_MAX_HITS * R) + 2 * align256(4 * R) + 256);
+    return (int64_t)(3 * align256(4 * NL_MAX_HITS * R) + 2 * align256(4 * R) + align256(8 * 2 * SCAN_SCRATCH) + 256);
 }
 
 extern "C" int nl_render_samples(const nl_render_args *a, void *stream_) {
@@ -740,7 +857,14 @@ extern "C" int nl_render_samples(const nl_render_args *a, void *stream_) {
                                                               a->d_ray_d, ws, a->d_ray_nsamp, a->d_stats);
     // NL_SCAN_STAGE=0: the hit scan without its 16 KB staging buffer (see k_scan)
     static const bool scan_stage = [] { const char *e = getenv("NL_SCAN_STAGE"); return e ? atoi(e) != 0 : true; }();
-    if (scan_stage) k_scan<SCAN_HITS, true><<<1, 1024, 0, stream>>>(R, ws.nvalid, a->d_hit_rank, ws.hitray, a->d_stats, 0);
+    // NL_SCAN=single: the single-block scans (the fallback for more than 4 M rays)
+    static const bool scan_chained = [] { const char *e = getenv("NL_SCAN"); return !(e && e[0] == 's'); }();
+    const int scan_tiles = nl_div_up(R, 4096);
+    const bool chained = scan_chained && scan_tiles <= SCAN_MAX_TILES;
+    if (chained) {
+        cudaMemsetAsync(ws.scan, 0, sizeof(unsigned long long) * 2 * SCAN_SCRATCH, stream);
+        k_scan_chained<SCAN_HITS><<<scan_tiles, 1024, 0, stream>>>(R, ws.nvalid, a->d_hit_rank, ws.hitray, a->d_stats, 0, ws.scan);
+    } else if (scan_stage) k_scan<SCAN_HITS, true><<<1, 1024, 0, stream>>>(R, ws.nvalid, a->d_hit_rank, ws.hitray, a->d_stats, 0);
     else k_scan<SCAN_HITS, false><<<1, 1024, 0, stream>>>(R, ws.nvalid, a->d_hit_rank, ws.hitray, a->d_stats, 0);
     SampleParams p;
     p.R = R; p.sample_capacity = a->sample_capacity; p.compat = a->reference_compat;
@@ -750,7 +874,8 @@ extern "C" int nl_render_samples(const nl_render_args *a, void *stream_) {
     p.s_ray = a->d_s_ray; p.s_vox = a->d_s_vox; p.s_depth = a->d_s_depth; p.s_xyz = a->d_s_xyz; p.s_flag = a->d_s_flag;
     p.ray_nsamp = a->d_ray_nsamp; p.ray_offset = a->d_ray_offset;
     k_sample<false><<<blocks, 128, 0, stream>>>(p, ws, a->d_stats);
-    k_scan<SCAN_SAMPLES><<<1, 1024, 0, stream>>>(R, a->d_ray_nsamp, a->d_ray_offset, nullptr, a->d_stats, a->sample_capacity);
+    if (chained) k_scan_chained<SCAN_SAMPLES><<<scan_tiles, 1024, 0, stream>>>(R, a->d_ray_nsamp, a->d_ray_offset, nullptr, a->d_stats, a->sample_capacity, ws.scan + SCAN_SCRATCH);
+    else k_scan<SCAN_SAMPLES><<<1, 1024, 0, stream>>>(R, a->d_ray_nsamp, a->d_ray_offset, nullptr, a->d_stats, a->sample_capacity);
     k_sample<true><<<blocks, 128, 0, stream>>>(p, ws, a->d_stats);
     if (a->d_gt_depth) k_loss_prepare<<<1, 1, 0, stream>>>(a->d_stats, a->fs_weight, a->sdf_weight);
     NL_CHECK_LAUNCH("nl_render_samples");
