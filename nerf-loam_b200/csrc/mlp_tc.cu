@@ -1416,6 +1416,8 @@ extern "C" int nl_mlp_tc_train(int64_t M, const int32_t *d_M_dev, const float *f
     static std::mutex dev_mu;
     static bool configured_dev[NL_MAX_DEV] = {};
     static cudaEvent_t ev_dev[NL_MAX_DEV] = {};
+    static cudaStream_t s2_dev[NL_MAX_DEV] = {};                    // internal stream of k_dw0_tc when the two weight-gradient kernels run side by side
+    static cudaEvent_t e2_dev[NL_MAX_DEV] = {}, e3_dev[NL_MAX_DEV] = {};
     int cur_dev = 0;
     if (cudaGetDevice(&cur_dev) != cudaSuccess || cur_dev < 0 || cur_dev >= NL_MAX_DEV) return nl_set_error_code(NL_ERR_CUDA, "nl_mlp_tc_train: cudaGetDevice");
     std::lock_guard<std::mutex> dev_lock(dev_mu);
@@ -1477,16 +1479,38 @@ extern "C" int nl_mlp_tc_train(int64_t M, const int32_t *d_M_dev, const float *f
         // ring depths (raw, converted): "deep" (4,3)/(4,4) = 219 KB of shared memory per CTA, "mid" (3,3)/(4,3) = 201/183 KB,
         // "shallow" (3,2)/(3,3) = 149/161 KB -- the smaller ones leave room for blocks of other kernels on the same SM when
         // the engine pipelines iterations (NL_DW_RINGS)
+        // Experiment kept behind a switch (default off): the two weight-gradient kernels are independent -- k_dw1_tc tensor-bound,
+        // k_dw0_tc streaming 1 KB/sample for a 256x32 result -- so they could run side by side on disjoint SM subsets
+        // (NL_DW_SPLIT = SMs given to k_dw1_tc, the rest to k_dw0_tc on an internal third stream) instead of back to back.
+        // Measured on the B200: slower for every split (100: +0.05 ms ... 126: +0.6 ms per step) -- k_dw0_tc is limited per SM
+        // (its converter warps), not by HBM chip-wide, so it needs all 148 SMs.
+        static const int dw_split = [] { const char *e = getenv("NL_DW_SPLIT"); return e ? atoi(e) : 0; }();
+        const bool split = dw_split > 0 && dw_split < sms - 8;
+        const int sms1 = split ? dw_split : sms, sms0 = split ? sms - dw_split : sms;
+        cudaStream_t ws0 = ws;
+        if (split) {
+            if (!s2_dev[cur_dev] && (cudaStreamCreateWithFlags(&s2_dev[cur_dev], cudaStreamNonBlocking) != cudaSuccess ||
+                                     cudaEventCreateWithFlags(&e2_dev[cur_dev], cudaEventDisableTiming) != cudaSuccess ||
+                                     cudaEventCreateWithFlags(&e3_dev[cur_dev], cudaEventDisableTiming) != cudaSuccess))
+                return nl_set_error_code(NL_ERR_CUDA, "nl_mlp_tc_train: could not create the internal weight-gradient stream");
+            ws0 = s2_dev[cur_dev];
+            if (cudaEventRecord(e2_dev[cur_dev], ws) != cudaSuccess || cudaStreamWaitEvent(ws0, e2_dev[cur_dev], 0) != cudaSuccess)   // fork behind the decoder kernel
+                return nl_set_error_code(NL_ERR_CUDA, "nl_mlp_tc_train: could not fork the internal weight-gradient stream");
+        }
 #define NL_DW_LAUNCH(NCW_, THR, R1, C1, R0, C0)                                                                                     \
-        tc::k_dw1_tc<NCW_, R1, C1><<<sms, THR, tc::dw_smem(R1, C1), ws>>>(M, d_M_dev, p.act_mask2, p.act_dsdf, p.act_h1, W1, w2, grads->gW1, \
-                                                                           grads->gW2);                                              \
-        tc::k_dw0_tc<NCW_, R0, C0><<<sms, THR, tc::d0_smem(R0, C0), ws>>>(M, d_M_dev, p.act_dh1, feats, grads->gW0, grads->gb0);
+        tc::k_dw1_tc<NCW_, R1, C1><<<sms1, THR, tc::dw_smem(R1, C1), ws>>>(M, d_M_dev, p.act_mask2, p.act_dsdf, p.act_h1, W1, w2, grads->gW1, \
+                                                                            grads->gW2);                                             \
+        tc::k_dw0_tc<NCW_, R0, C0><<<sms0, THR, tc::d0_smem(R0, C0), ws0>>>(M, d_M_dev, p.act_dh1, feats, grads->gW0, grads->gb0);
         if (conv_warps == 8) {
             if (dw_rings == 2) { NL_DW_LAUNCH(8, 320, 4, 3, 4, 4) } else if (dw_rings == 1) { NL_DW_LAUNCH(8, 320, 3, 3, 4, 3) } else { NL_DW_LAUNCH(8, 320, 3, 2, 3, 3) }
         } else {
             if (dw_rings == 2) { NL_DW_LAUNCH(4, 192, 4, 3, 4, 4) } else if (dw_rings == 1) { NL_DW_LAUNCH(4, 192, 3, 3, 4, 3) } else { NL_DW_LAUNCH(4, 192, 3, 2, 3, 3) }
         }
 #undef NL_DW_LAUNCH
+        if (split) {      // join: `ws` (what the caller waits on) completes only after k_dw0_tc
+            if (cudaEventRecord(e3_dev[cur_dev], ws0) != cudaSuccess || cudaStreamWaitEvent(ws, e3_dev[cur_dev], 0) != cudaSuccess)
+                return nl_set_error_code(NL_ERR_CUDA, "nl_mlp_tc_train: could not join the internal weight-gradient stream");
+        }
         tc::k_mask_colsum<<<sms * 8, 256, 0, ws>>>(M, d_M_dev, p.act_mask2, p.act_dsdf, b1, w2, grads->gb1, grads->gW2);
     } else {
         if (use_ts && use_pair) { if (int rc = tc::launch_pair(tc::k_mlp_tc_train<false, true, true>, grid, sms, p, stream)) return rc; }
