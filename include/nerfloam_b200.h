@@ -258,6 +258,15 @@ NL_API int nl_rays_from_poses(int64_t R, const float *d_dir_local, const int32_t
                        float *d_ray_o, float *d_ray_d, void *stream);                    /* render_helpers.py:374-376 */
 NL_API int nl_pose_grad(int n_frames, const float *d_pose6, const float *d_pose_acc, float *d_grad6, void *stream);
 
+/* Per-iteration ray selection (LidarFrame.sample_rays, src/lidarFrame.py:55-57 / src/utils/sample_util.py:4-19): for each of
+ * n_frames scans, n_select distinct points uniformly at random out of its d_n_points[f] points (int64, device; a scan's arrays have
+ * `cap` rows), in ascending point order like the reference's mask, and the gather of their ray data in the same launch:
+ * d_dirs f32[n_frames*n_select,3], d_gt, d_cos f32[n_frames*n_select], optional d_idx i32 (the chosen point indices).
+ * Seed: *d_seed if given (a captured graph advances it between replays), else `seed`.  cap <= 2^20. */
+NL_API int nl_select_rays(int n_frames, int cap, int n_select, const int64_t *d_n_points, const uint32_t *d_seed, uint32_t seed,
+                   const float *d_dirs_all, const float *d_gt_all, const float *d_cos_all, float *d_dirs, float *d_gt, float *d_cos,
+                   int32_t *d_idx, void *stream);
+
 /* ============================================================================================
  * 7. Optimiser (torch.optim.Adam semantics, render_helpers.py:353/448): fp32 tensors and the bf16
  *    embedding table (every intermediate rounded to bf16 where torch's per-op kernels round).

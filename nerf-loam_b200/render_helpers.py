@@ -224,6 +224,31 @@ def get_scores(sdf_network, map_states, voxel_size, bits=8):
 # ======================================================================================================
 # optimisation loops
 # ======================================================================================================
+def _seed_from_cuda(dev):
+    """A fresh 32-bit seed drawn from torch's CUDA generator without a host round trip being needed later: a 1-element device tensor."""
+    return torch.randint(1, 2 ** 31 - 1, (1,), device=dev, dtype=torch.int32)
+
+
+def select_rays_device(dirs_all, gt_all, cos_all, n_select, n_dev=None, seed=None, out=None):
+    """nl_select_rays: n_select distinct rays per scan, uniformly at random, in point order (the distribution of
+    LidarFrame.sample_rays), gathered in the same launch.  dirs_all f32[F,cap,3] or [cap,3]; n_dev int64[F] device (None: all cap rows
+    are points); seed int32[1] device tensor.  Returns (dirs [F*n_select,3], gt, cos)."""
+    if dirs_all.dim() == 2:
+        dirs_all, gt_all, cos_all = dirs_all[None], gt_all[None], cos_all[None]
+    F, cap = dirs_all.shape[0], dirs_all.shape[1]
+    dev = dirs_all.device
+    if n_dev is None:
+        n_dev = torch.full((F,), cap, dtype=torch.int64, device=dev)
+    if out is None:
+        out = (torch.empty((F * n_select, 3), dtype=torch.float32, device=dev), torch.empty(F * n_select, dtype=torch.float32, device=dev),
+               torch.empty(F * n_select, dtype=torch.float32, device=dev))
+    _capi.check(_capi.lib().nl_select_rays(F, cap, int(n_select), _capi.ptr(n_dev.view(-1)), _capi.ptr(seed), 0, _capi.ptr(dirs_all.contiguous()),
+                                           _capi.ptr(gt_all.contiguous()), _capi.ptr(cos_all.contiguous()), _capi.ptr(out[0]), _capi.ptr(out[1]),
+                                           _capi.ptr(out[2]), None, _capi.stream_ptr()), "nl_select_rays")
+    _capi.LAUNCHES += 1
+    return out
+
+
 class _few_threads:
     """The reference's host-side ray selection is a handful of small element-wise CPU ops + a top-k over ~10^5 values; on a
     many-core host torch fans each of them out over every core and the fork/join costs far more than the work (measured on the
@@ -260,11 +285,14 @@ class _FrameBatch:
         for i, f in enumerate(self.frames):
             if mode == "device":
                 n = self.dirs[i].shape[0]
-                idx = torch.rand(n, device=dev).topk(min(N_rays, n)).indices.sort().values
-            else:
-                with _few_threads():
-                    f.sample_rays(N_rays, track=True) if track else f.sample_rays(N_rays)
-                    idx = f.sample_mask.view(-1).nonzero().view(-1).to(dev, non_blocking=True)
+                k = min(N_rays, n)
+                di, gi, ci = select_rays_device(self.dirs[i], self.gt[i], self.cos[i], k, n_dev=None, seed=_seed_from_cuda(dev))
+                d.append(di); g.append(gi); c.append(ci)
+                fid.append(torch.full((k,), i, dtype=torch.int32, device=dev))
+                continue
+            with _few_threads():
+                f.sample_rays(N_rays, track=True) if track else f.sample_rays(N_rays)
+                idx = f.sample_mask.view(-1).nonzero().view(-1).to(dev, non_blocking=True)
             d.append(self.dirs[i][idx]); g.append(self.gt[i][idx]); c.append(self.cos[i][idx])
             fid.append(torch.full((idx.shape[0],), i, dtype=torch.int32, device=dev))
         return torch.cat(d).contiguous(), torch.cat(g).contiguous(), torch.cat(c).contiguous(), torch.cat(fid).contiguous()
@@ -305,7 +333,8 @@ class _MapGraph:
         self.gt = torch.ones((F, cap), device=dev)
         self.cos = torch.ones((F, cap), device=dev)
         self.n_dev = torch.full((F, 1), cap, dtype=torch.int64, device=dev)
-        self.arange = torch.arange(cap, device=dev)[None, :]
+        self.sel_seed = torch.ones(1, dtype=torch.int32, device=dev)        # ray-selection stream, advanced inside the graph
+        self.sel_out = (torch.empty((R, 3), device=dev), torch.empty(R, device=dev), torch.empty(R, device=dev))
         self.fid = torch.arange(F, dtype=torch.int32, device=dev).repeat_interleave(N_rays).contiguous()
         self.pose6 = torch.zeros((F, 6), device=dev)
         self.seed_dev = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -316,11 +345,9 @@ class _MapGraph:
         state = {"opt": None}
 
         def body():
-            keys = torch.where(self.arange < self.n_dev, torch.rand((F, cap), device=dev), torch.full((), -1.0, device=dev))
-            idx = keys.topk(N_rays, dim=1).indices.sort(dim=1).values          # uniform without replacement among each scan's points
-            dirs = torch.gather(self.dirs, 1, idx[..., None].expand(-1, -1, 3)).reshape(R, 3).contiguous()
-            gt = torch.gather(self.gt, 1, idx).reshape(R).contiguous()
-            cos = torch.gather(self.cos, 1, idx).reshape(R).contiguous()
+            # per frame: uniform without replacement among the scan's points, in point order, gathered -- one launch (csrc/select.cu)
+            dirs, gt, cos = select_rays_device(self.dirs, self.gt, self.cos, N_rays, n_dev=self.n_dev, seed=self.sel_seed, out=self.sel_out)
+            self.sel_seed.add_(0x632BE5)
             eng.rays_from_poses(self.pose6, dirs, self.fid)
             eng.forward_backward(m, bufs, R, cfg, gt, cos, dir_local=dirs, ray_frame=self.fid, n_frames=F, update_decoder=update_decoder,
                                  update_emb=True, update_pose=any_pose, pose6=self.pose6,
@@ -384,6 +411,7 @@ class _MapGraph:
             self.n_dev[i].fill_(n)
         self.pose6.copy_(pose6_init)
         self.seed_dev.fill_(seed if seed < 2 ** 31 else seed - 2 ** 32)
+        self.sel_seed.copy_(_seed_from_cuda(dev))          # ray selection follows torch's CUDA generator (torch.manual_seed reproduces it)
         for g in self.opt.groups:
             g["m"].zero_(); g["v"].zero_()
         self.eng.begin_call()
@@ -521,16 +549,17 @@ class _TrackGraph:
         self.gt = torch.ones(cap, device=dev)
         self.cos = torch.ones(cap, device=dev)
         self.n_dev = torch.zeros(1, dtype=torch.int64, device=dev)
-        self.arange = torch.arange(cap, device=dev)
         self.pose6 = torch.zeros((1, 6), device=dev)
         self.seed_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.sel_seed = torch.ones(1, dtype=torch.int32, device=dev)        # ray-selection stream, advanced inside the graph
+        self.sel_out = (torch.empty((N_rays, 3), device=dev), torch.empty(N_rays, device=dev), torch.empty(N_rays, device=dev))
         self.adam_m, self.adam_v = torch.zeros(6, device=dev), torch.zeros(6, device=dev)
         lib = _capi.lib()
 
         def body():
-            keys = torch.where(self.arange < self.n_dev, torch.rand(cap, device=dev), torch.full((), -1.0, device=dev))
-            idx = keys.topk(N_rays).indices.sort().values        # uniform without replacement among the scan's n points
-            dirs, gt, cos = self.dirs[idx].contiguous(), self.gt[idx].contiguous(), self.cos[idx].contiguous()
+            # uniform without replacement among the scan's n points, in point order, gathered -- one launch (csrc/select.cu)
+            dirs, gt, cos = select_rays_device(self.dirs, self.gt, self.cos, N_rays, n_dev=self.n_dev, seed=self.sel_seed, out=self.sel_out)
+            self.sel_seed.add_(0x632BE5)
             eng.rays_from_poses(self.pose6, dirs, None)
             eng.forward_backward(m, bufs, N_rays, cfg, gt, cos, dir_local=dirs, ray_frame=None, n_frames=1, update_decoder=False,
                                  update_emb=False, update_pose=True, pose6=self.pose6, refresh_weights=False,
@@ -582,6 +611,7 @@ class _TrackGraph:
         self.n_dev.fill_(n)
         self.pose6.copy_(pose6_init)
         self.seed_dev.fill_(seed if seed < 2 ** 31 else seed - 2 ** 32)
+        self.sel_seed.copy_(_seed_from_cuda(dev))          # ray selection follows torch's CUDA generator (torch.manual_seed reproduces it)
         self.adam_m.zero_(); self.adam_v.zero_()
         self.eng.begin_call()
         for _ in range(num_iterations):

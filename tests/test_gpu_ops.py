@@ -293,3 +293,43 @@ def test_stats_pack_kernels_match_the_host_layout(nl):
     nld.unpack_stats(dev2, h_d, world, 1)
     c = cap.RenderStats.from_buffer_copy(dev2.cpu().numpy().tobytes())
     assert abs(c.fs_sum - st.fs_sum) < 1e-13 * st.fs_sum + 1e-15 and abs(c.sdf_sum - st.sdf_sum) < 1e-13
+
+
+def test_select_rays_is_a_uniform_subset_in_point_order(nl):
+    """nl_select_rays (LidarFrame.sample_rays on the device): exactly N distinct points per scan, ascending, gathered correctly, every
+    point equally likely (chi-square over many draws), also when more than half of the points are wanted (complement path) and for
+    several scans of different length in one launch."""
+    rh = nl.render_helpers
+    dev = torch.device("cuda")
+    torch.manual_seed(0)
+    F, cap = 3, 5000
+    n = torch.tensor([5000, 3777, 64], dtype=torch.int64, device=dev)
+    dirs = torch.randn(F, cap, 3, device=dev)
+    gt = torch.arange(F * cap, device=dev, dtype=torch.float32).view(F, cap)             # gt[f, i] identifies the point
+    cos = -gt
+    for N in (64, 1000):
+        counts = torch.zeros(F, cap, device=dev)
+        draws = 300
+        for it in range(draws):
+            seed = torch.tensor([it * 7919 + 1], dtype=torch.int32, device=dev)
+            d, g, c = rh.select_rays_device(dirs, gt, cos, N, n_dev=n, seed=seed)
+            g = g.view(F, N)
+            for f in range(F):
+                k = min(N, int(n[f]))
+                idx = (g[f, :k] - f * cap).long()
+                assert bool((idx[1:] > idx[:-1]).all()) and int(idx.min()) >= 0 and int(idx.max()) < int(n[f])      # distinct, ascending, in range
+                assert torch.equal(d.view(F, N, 3)[f, :k], dirs[f, idx]) and torch.equal(c.view(F, N)[f, :k], cos[f, idx])
+                counts[f, idx] += 1
+        for f in range(2):                                   # (the third scan has exactly 64 points: always all of them)
+            nf = int(n[f])
+            p = N / nf
+            x = counts[f, :nf]
+            z = (x - draws * p) / (draws * p * (1 - p)) ** 0.5
+            assert abs(float(z.mean())) < 0.05 and 0.9 < float(z.std()) < 1.1, (N, f, float(z.mean()), float(z.std()))
+        assert bool((counts[2, :64] == draws).all())
+    # different seeds give different subsets, the same seed the same subset
+    s1 = torch.tensor([5], dtype=torch.int32, device=dev)
+    a = rh.select_rays_device(dirs, gt, cos, 100, n_dev=n, seed=s1)[1].clone()
+    b = rh.select_rays_device(dirs, gt, cos, 100, n_dev=n, seed=s1)[1].clone()
+    c2 = rh.select_rays_device(dirs, gt, cos, 100, n_dev=n, seed=torch.tensor([6], dtype=torch.int32, device=dev))[1]
+    assert torch.equal(a, b) and not torch.equal(a[:100], c2[:100])
