@@ -332,4 +332,4 @@ def test_select_rays_is_a_uniform_subset_in_point_order(nl):
     a = rh.select_rays_device(dirs, gt, cos, 100, n_dev=n, seed=s1)[1].clone()
     b = rh.select_rays_device(dirs, gt, cos, 100, n_dev=n, seed=s1)[1].clone()
     c2 = rh.select_rays_device(dirs, gt, cos, 100, n_dev=n, seed=torch.tensor([6], dtype=torch.int32, device=dev))[1]
-    assert torch.equal(a, b) and not torch.equal(a[:100], c2[:100])
+    assert torch.equal(a[:264], b[:264]) and not torch.equal(a[:100], c2[:100])     # (scan 3 has only 64 points: its last 36 slots stay unwritten)
