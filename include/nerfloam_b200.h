@@ -262,7 +262,8 @@ NL_API int nl_pose_grad(int n_frames, const float *d_pose6, const float *d_pose_
  * n_frames scans, n_select distinct points uniformly at random out of its d_n_points[f] points (int64, device; a scan's arrays have
  * `cap` rows), in ascending point order like the reference's mask, and the gather of their ray data in the same launch:
  * d_dirs f32[n_frames*n_select,3], d_gt, d_cos f32[n_frames*n_select], optional d_idx i32 (the chosen point indices).
- * Seed: *d_seed if given (a captured graph advances it between replays), else `seed`.  cap <= 2^20. */
+ * Seed: *d_seed if given (a captured graph advances it between replays), else `seed`.  The subset is a function of the seed alone
+ * (radix select over per-point hashed keys; equal keys go to the lower point index). */
 NL_API int nl_select_rays(int n_frames, int cap, int n_select, const int64_t *d_n_points, const uint32_t *d_seed, uint32_t seed,
                    const float *d_dirs_all, const float *d_gt_all, const float *d_cos_all, float *d_dirs, float *d_gt, float *d_cos,
                    int32_t *d_idx, void *stream);

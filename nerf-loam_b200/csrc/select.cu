@@ -4,12 +4,15 @@
 // selected rays' direction / range / cosine, as ONE launch.
 //
 // The torch formulation of the same thing (rand -> top-k of 131 072 keys -> sort -> three gathers) is ~10 kernels and 140-160 us,
-// a third of a 2048-ray tracking iteration whose other 20 kernels take 270 us.  Here one block per frame keeps a bitmap of the
-// scan's points in shared memory: every thread draws indices from a counter-based generator and claims them with atomicOr,
-// redrawing when the bit was already taken (rejection of duplicates = sampling without replacement; whatever order the threads
-// interleave in corresponds to some sequential order, so the subset is uniform); a block-wide scan of the words' popcounts then
-// yields the chosen indices in ascending order together with their output slots.
+// a third of a 2048-ray tracking iteration whose other 20 kernels take 270 us.  Here one 8-CTA cluster per frame gives every point an
+// independent 32-bit key from a counter-based generator (seed, frame, point index) and selects the N smallest keys with a
+// three-pass radix select (11 + 11 + 10 bits, histograms in shared memory, summed across the cluster through DSMEM): that is exactly "top-k of iid keys", i.e. a uniform
+// N-subset, it is deterministic for a given seed (ties between equal keys go to the lower point index), and the last pass walks
+// the points in order, so the output is in point order without a sort.  Keys are recomputed in every pass (a handful of integer
+// operations), nothing but the three small histograms is stored.
 #include "nl_cuda.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -17,80 +20,128 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
     x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
     return x;
 }
+__device__ __forceinline__ uint32_t point_key(uint32_t seed, uint32_t i) { return mix32(seed ^ mix32(i * 0x9E3779B1u + 0x7F4A7C15u)); }
 
 constexpr int SEL_THREADS = 1024;
+constexpr int SEL_BINS = 2048;
+constexpr int SEL_CLUSTER = 8;      // CTAs per scan: each hashes an eighth of the points, histograms are summed over distributed shared memory
 
-__global__ void __launch_bounds__(SEL_THREADS) k_select_rays(int cap, int n_select, const int64_t *__restrict__ n_points, const uint32_t *__restrict__ seed_dev,
-                                                              uint32_t seed_host, const float *__restrict__ dirs_all, const float *__restrict__ gt_all,
-                                                              const float *__restrict__ cos_all, float *__restrict__ dirs, float *__restrict__ gt,
-                                                              float *__restrict__ cosv, int32_t *__restrict__ idx_out) {
-    extern __shared__ uint32_t bits[];                 // ceil(cap / 32) words
-    __shared__ int s_warp[SEL_THREADS / 32];
-    const int f = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
-    const int n = (int)min((long long)n_points[f], (long long)cap);
-    const int N = min(n_select, n);
-    const int words = (cap + 31) >> 5;
-    for (int i = t; i < words; i += SEL_THREADS) bits[i] = 0u;
+// Among this scan's keys that pass `match`, find the bin (of `digit`) in which the `want`-th smallest key (1-based) lies, and the
+// number of matching keys in lower bins.  Every CTA of the cluster histograms its own points [p0, p1), reads the other CTAs'
+// histograms through DSMEM and finds the bin redundantly.  hist: SEL_BINS ints of shared memory (same offset in every CTA).
+template <int CL, class Match, class Digit>
+__device__ void find_bin(cg::cluster_group &cluster, int p0, int p1, uint32_t seed, int want, Match match, Digit digit, int *hist, int *s_scan, int &bin,
+                         int &below) {
+    const int t = threadIdx.x;
+    for (int i = t; i < SEL_BINS; i += SEL_THREADS) hist[i] = 0;
     __syncthreads();
-    uint32_t seed = seed_dev ? *seed_dev : seed_host;
-    seed = mix32(seed ^ 0x9E3779B9u * (uint32_t)(f + 1));
-    // more than half of the points wanted: draw the ones to LEAVE OUT instead (the complement of a uniform subset is uniform),
-    // so the rejection loop never fishes for the last few free bits
-    const bool invert = N > n / 2;
-    const int draws = invert ? n - N : N;
-    for (int j = t; j < draws; j += SEL_THREADS) {
-        uint32_t ctr = 0;
-        while (true) {
-            const uint32_t r = mix32(seed ^ mix32((uint32_t)j * 0x85EBCA77u + ctr * 0xC2B2AE3Du + 0x27D4EB2Fu));
-            ++ctr;
-            const uint32_t i = (uint32_t)(((unsigned long long)r * (unsigned long long)n) >> 32);      // uniform in [0, n)
-            const uint32_t bit = 1u << (i & 31);
-            if (!(atomicOr(&bits[i >> 5], bit) & bit)) break;                                          // claimed a free point
-        }
+    for (int i = p0 + t; i < p1; i += SEL_THREADS) {
+        const uint32_t k = point_key(seed, (uint32_t)i);
+        if (match(k)) atomicAdd(&hist[digit(k)], 1);
     }
-    __syncthreads();
-    if (invert) {
-        for (int i = t; i < words; i += SEL_THREADS) {
-            const int base = i * 32;
-            const uint32_t valid = base + 32 <= n ? 0xffffffffu : (base < n ? (1u << (n - base)) - 1u : 0u);
-            bits[i] = ~bits[i] & valid;
-        }
-        __syncthreads();
+    cluster.sync();
+    int a = 0, b = 0;
+#pragma unroll
+    for (int q = 0; q < CL; ++q) {
+        const int2 h = *reinterpret_cast<const int2 *>(cluster.map_shared_rank(hist, q) + 2 * t);
+        a += h.x; b += h.y;
     }
-    // ascending order: exclusive scan of the words' popcounts (each thread owns a contiguous run of words)
-    const int per = (words + SEL_THREADS - 1) / SEL_THREADS;
-    const int w0 = t * per, w1 = min(w0 + per, words);
-    int mine = 0;
-    for (int i = w0; i < w1; ++i) mine += __popc(bits[i]);
-    int incl = mine;
+    // inclusive scan over the 2048 bins: 2 per thread + block scan of the pair sums
+    int incl = a + b;
+    const int lane = t & 31, w = t >> 5;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
         const int y = __shfl_up_sync(0xffffffffu, incl, off);
         if (lane >= off) incl += y;
     }
-    if (lane == 31) s_warp[w] = incl;
+    if (lane == 31) s_scan[w] = incl;
     __syncthreads();
     int pre = 0;
-    for (int q = 0; q < w; ++q) pre += s_warp[q];
-    int slot = pre + incl - mine;
-    const size_t in0 = (size_t)f * cap, out0 = (size_t)f * n_select;
-    for (int i = w0; i < w1; ++i) {
-        uint32_t b = bits[i];
-        while (b) {
-            const int k = __ffs(b) - 1;
-            b &= b - 1;
-            const int p = i * 32 + k;
-            const size_t o = out0 + slot;
-            dirs[o * 3] = dirs_all[(in0 + p) * 3]; dirs[o * 3 + 1] = dirs_all[(in0 + p) * 3 + 1]; dirs[o * 3 + 2] = dirs_all[(in0 + p) * 3 + 2];
-            gt[o] = gt_all[in0 + p];
-            cosv[o] = cos_all[in0 + p];
-            if (idx_out) idx_out[o] = p;
-            ++slot;
-        }
-    }
+    for (int q = 0; q < w; ++q) pre += s_scan[q];
+    const int upto_a = pre + incl - b, upto_b = pre + incl;        // keys in bins <= 2t and <= 2t+1
+    const int before = upto_a - a;                                 // keys in bins < 2t
+    if (before < want && want <= upto_a) { s_scan[32] = 2 * t; s_scan[33] = before; }
+    else if (upto_a < want && want <= upto_b) { s_scan[32] = 2 * t + 1; s_scan[33] = upto_a; }
+    cluster.sync();                                                // bin found; every CTA is done reading the histograms
+    bin = s_scan[32];
+    below = s_scan[33];
 }
 
-NlPerDevice g_sel_attr;
+template <int CL>
+__global__ void __launch_bounds__(SEL_THREADS)
+    k_select_rays(int cap, int n_select, const int64_t *__restrict__ n_points, const uint32_t *__restrict__ seed_dev, uint32_t seed_host,
+                  const float *__restrict__ dirs_all, const float *__restrict__ gt_all, const float *__restrict__ cos_all, float *__restrict__ dirs,
+                  float *__restrict__ gt, float *__restrict__ cosv, int32_t *__restrict__ idx_out) {
+    __shared__ __align__(8) int hist[SEL_BINS];
+    __shared__ int s_scan[36];
+    __shared__ unsigned long long s_w[SEL_THREADS / 32];
+    __shared__ unsigned long long s_total;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int f = blockIdx.x / CL, c = (int)cluster.block_rank(), t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int n = (int)min((long long)n_points[f], (long long)cap);
+    const int N = min(n_select, n);
+    uint32_t seed = seed_dev ? *seed_dev : seed_host;
+    seed = mix32(seed ^ 0x9E3779B9u * (uint32_t)(f + 1));
+    // this CTA's contiguous share of the scan, and inside it every thread's contiguous run (for the ordered emission)
+    const int share = (n + CL - 1) / CL;
+    const int c0 = min(c * share, n), c1 = min(c0 + share, n);
+    // threshold key T = the N-th smallest key; `ties` = how many of the keys equal to T belong to the N smallest
+    uint32_t T = 0xffffffffu;
+    int ties = 0;
+    if (N < n && N > 0) {
+        int bA, bB, bC, below;
+        find_bin<CL>(cluster, c0, c1, seed, N, [](uint32_t) { return true; }, [](uint32_t k) { return (int)(k >> 21); }, hist, s_scan, bA, below);
+        int want = N - below;
+        find_bin<CL>(cluster, c0, c1, seed, want, [bA](uint32_t k) { return (int)(k >> 21) == bA; }, [](uint32_t k) { return (int)((k >> 10) & 2047u); }, hist,
+                 s_scan, bB, below);
+        want -= below;
+        const uint32_t top22 = ((uint32_t)bA << 11) | (uint32_t)bB;
+        find_bin<CL>(cluster, c0, c1, seed, want, [top22](uint32_t k) { return (k >> 10) == top22; }, [](uint32_t k) { return (int)(k & 1023u); }, hist, s_scan,
+                 bC, below);
+        T = (top22 << 10) | (uint32_t)bC;
+        ties = want - below;
+    }
+    const int per = (c1 - c0 + SEL_THREADS - 1) / SEL_THREADS;
+    const int p0 = min(c0 + t * per, c1), p1 = min(p0 + per, c1);
+    int lt = 0, eq = 0;
+    for (int i = p0; i < p1; ++i) {
+        const uint32_t k = point_key(seed, (uint32_t)i);
+        lt += (N == n) || (k < T);
+        eq += (N < n) && (k == T);
+    }
+    // two exclusive scans (below-threshold counts and tie counts) packed into one 64-bit scan: over the block, then over the cluster
+    const unsigned long long pk = ((unsigned long long)(unsigned)eq << 32) | (unsigned)lt;
+    unsigned long long incl = pk;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned long long y = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += y;
+    }
+    if (lane == 31) s_w[w] = incl;
+    __syncthreads();
+    unsigned long long pre = 0;
+    for (int q = 0; q < w; ++q) pre += s_w[q];
+    if (t == SEL_THREADS - 1) s_total = pre + incl;
+    cluster.sync();
+    for (int q = 0; q < c; ++q) pre += *cluster.map_shared_rank(&s_total, q);
+    const unsigned long long excl = pre + incl - pk;
+    const int lt_before = (int)(excl & 0xffffffffULL);
+    int eq_before = (int)(excl >> 32);
+    int slot = lt_before + min(eq_before, ties);                  // selected points in front of this thread's run
+    const size_t in0 = (size_t)f * cap, out0 = (size_t)f * n_select;
+    for (int i = p0; i < p1; ++i) {
+        const uint32_t k = point_key(seed, (uint32_t)i);
+        bool take = (N == n) || (k < T);
+        if (!take && k == T) take = eq_before++ < ties;           // equal keys: the lower point index wins
+        if (!take) continue;
+        const size_t o = out0 + (size_t)slot++;
+        dirs[o * 3] = dirs_all[(in0 + i) * 3]; dirs[o * 3 + 1] = dirs_all[(in0 + i) * 3 + 1]; dirs[o * 3 + 2] = dirs_all[(in0 + i) * 3 + 2];
+        gt[o] = gt_all[in0 + i];
+        cosv[o] = cos_all[in0 + i];
+        if (idx_out) idx_out[o] = i;
+    }
+    cluster.sync();                                                // nobody leaves while its totals may still be read
+}
 
 }  // namespace
 
@@ -98,15 +149,24 @@ extern "C" int nl_select_rays(int n_frames, int cap, int n_select, const int64_t
                               const float *d_dirs_all, const float *d_gt_all, const float *d_cos_all, float *d_dirs, float *d_gt, float *d_cos,
                               int32_t *d_idx, void *stream) {
     if (n_frames <= 0 || cap <= 0 || n_select <= 0) return nl_set_error("nl_select_rays: sizes must be positive");
-    if (cap > (1 << 20)) return nl_set_error("nl_select_rays: at most 2^20 points per scan (bitmap in shared memory)");
     if (!d_n_points || !d_dirs_all || !d_gt_all || !d_cos_all || !d_dirs || !d_gt || !d_cos) return nl_set_error("nl_select_rays: null pointer");
-    const int smem = ((cap + 31) >> 5) * 4;
-    if (smem > 48 * 1024) {
-        const cudaError_t e = g_sel_attr.once([] { return cudaFuncSetAttribute(k_select_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024); });
+    static const bool single = [] { const char *e = getenv("NL_SEL_CLUSTER"); return e && e[0] == '0'; }();
+    if (single) {
+        k_select_rays<1><<<n_frames, SEL_THREADS, 0, (cudaStream_t)stream>>>(cap, n_select, d_n_points, d_seed, seed, d_dirs_all, d_gt_all, d_cos_all,
+                                                                                d_dirs, d_gt, d_cos, d_idx);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(n_frames * SEL_CLUSTER);
+        cfg.blockDim = dim3(SEL_THREADS);
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = SEL_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, k_select_rays<SEL_CLUSTER>, cap, n_select, d_n_points, d_seed, seed, d_dirs_all, d_gt_all, d_cos_all,
+                                                 d_dirs, d_gt, d_cos, d_idx);
         if (e != cudaSuccess) return nl_set_error_code(NL_ERR_CUDA, cudaGetErrorString(e));
     }
-    k_select_rays<<<n_frames, SEL_THREADS, smem, (cudaStream_t)stream>>>(cap, n_select, d_n_points, d_seed, seed, d_dirs_all, d_gt_all, d_cos_all, d_dirs,
-                                                                         d_gt, d_cos, d_idx);
     NL_CHECK_LAUNCH("nl_select_rays");
     return NL_OK;
 }

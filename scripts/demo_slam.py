@@ -18,6 +18,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scans", type=int, default=12); ap.add_argument("--spacing", type=float, default=0.5)
     ap.add_argument("--init-calls", type=int, default=12); ap.add_argument("--json", default=None)
+    ap.add_argument("--ray-selection", default="device", choices=["device", "host"])
     a = ap.parse_args()
     dev = torch.device("cuda"); syn, rh = nl.synthetic, nl.render_helpers
     vs, md, trunc = 0.3, 40.0, 0.3
@@ -36,7 +37,8 @@ def main():
     mk = lambda i, pose: nl.frame.LidarFrame(i, torch.from_numpy(scans[i][0]), torch.from_numpy(scans[i][1]), pose, new_keyframe=True)
     lr = [0.01, 0.005, 0.001]
     ba = lambda fr, upd_dec, it=25: rh.bundle_adjust_frames(fr, mu.embeddings, ms, dec, crit, vs, 0.5 * vs, N_rays=2048, num_iterations=it, truncation=trunc,
-                                                            max_voxel_hit=20, max_distance=md, learning_rate=lr, update_pose=True, update_decoder=upd_dec)
+                                                            max_voxel_hit=20, max_distance=md, learning_rate=lr, update_pose=True, update_decoder=upd_dec,
+                                                            ray_selection=a.ray_selection)
     # ---- first scan: map it, then train on it while "waiting for the tracker" (mapping.py:100-108) ----
     f0 = mk(0, nl.se3pose.OptimizablePose.from_matrix(gt[0].clone()))
     ms = mu.create_voxels(scans[0][0], gt[0])
@@ -51,10 +53,12 @@ def main():
         last = est[-1]
         guess = last @ rel if rel is not None else last.clone()                            # constant-velocity model (tracking.py:112-117)
         fr = mk(i, nl.se3pose.OptimizablePose.from_matrix(guess.clone()))
+        # KITTI's tracking rate (0.06, /3 from the third scan on).  The first tracked scan has no motion prior: 125 iterations, and a rate of
+        # 0.01 because frame index < 2 doubles it -- 0.12 m Adam steps on 0.3 m voxels are bistable (scripts/sweep_tracking_lr.py)
         t0 = tick()
         m_t, dec_t, slot = shared.acquire()
         pose, hit = rh.track_frame(fr.pose, fr, m_t, dec_t, crit, vs, N_rays=2048, step_size=0.2 * vs, num_iterations=25 if rel is not None else 125,
-                                   truncation=trunc, learning_rate=0.06, max_voxel_hit=20, max_distance=md)
+                                   truncation=trunc, learning_rate=0.06 if rel is not None else 0.01, max_voxel_hit=20, max_distance=md, ray_selection=a.ray_selection)
         shared.release(slot)
         T["track"].append((tick() - t0) * 1e3)
         if hit is None:

@@ -9,6 +9,23 @@ d=json.load(open("$out/bench.json"))
 print("value", d["value"], "ms", d["ms_per_step"])
 print("tracking", {k:v for k,v in d["tracking"].items() if k!="note"})
 for k,v in d["configs"].items():
-    if k!="note": print(k, {kk: round(vv,2) for kk,vv in v.items() if kk.endswith("_ms")})
+    if k!="note": print(k, {kk: round(vv,2) for kk,vv in v.items() if kk.endswith("_ms") and not isinstance(vv, list)})
+PY
+python - <<PY
+import sys, torch, importlib
+sys.path.insert(0, ".")
+nl = importlib.import_module("nerf-loam_b200")
+from importlib import import_module
+rh = import_module("nerf-loam_b200.render_helpers")
+for F in (1, 5):
+    cap = 100000
+    d = torch.randn(F, cap, 3, device="cuda"); g = torch.rand(F, cap, device="cuda"); c = torch.rand(F, cap, device="cuda")
+    seed = torch.tensor([12345], dtype=torch.int32, device="cuda")
+    out = rh.select_rays_device(d, g, c, 2048, seed=seed)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(200): rh.select_rays_device(d, g, c, 2048, seed=seed, out=out)
+    e1.record(); torch.cuda.synchronize()
+    print("select_rays F=%d n=%d: %.1f us/launch" % (F, cap, e0.elapsed_time(e1) * 5))
 PY
 timeout 300 python scripts/demo_slam.py 2>/dev/null | tail -1 | cut -c1-700

@@ -333,3 +333,43 @@ def test_select_rays_is_a_uniform_subset_in_point_order(nl):
     b = rh.select_rays_device(dirs, gt, cos, 100, n_dev=n, seed=s1)[1].clone()
     c2 = rh.select_rays_device(dirs, gt, cos, 100, n_dev=n, seed=torch.tensor([6], dtype=torch.int32, device=dev))[1]
     assert torch.equal(a[:264], b[:264]) and not torch.equal(a[:100], c2[:100])     # (scan 3 has only 64 points: its last 36 slots stay unwritten)
+
+
+def _select_keys_torch(seed, f, n, dev):
+    """The key generator of csrc/select.cu restated with int64 torch ops: key(i) = mix32(seed_f ^ mix32(i * 0x9E3779B1 + 0x7F4A7C15))."""
+    M = 0xFFFFFFFF
+
+    def mix(x):
+        x = x ^ (x >> 16); x = (x * 0x7FEB352D) & M; x = x ^ (x >> 15); x = (x * 0x846CA68B) & M; return x ^ (x >> 16)
+
+    sf = mix(torch.tensor([(seed ^ ((0x9E3779B9 * (f + 1)) & M)) & M], dtype=torch.int64, device=dev))
+    i = torch.arange(n, dtype=torch.int64, device=dev)
+    return mix(sf ^ mix((i * 0x9E3779B1 + 0x7F4A7C15) & M))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [2048, 70000])
+def test_select_rays_equals_top_n_of_the_hashed_keys_at_scan_size(nl, N):
+    """At the size of a real scan (10^5 points, several scans per launch) the kernel's subset is exactly the N smallest keys
+    (ties to the lower index) -- the radix select, the cluster-wide histograms and the ordered emission against torch's sort."""
+    rh = nl.render_helpers
+    dev = torch.device("cuda")
+    F, cap = 5, 131072
+    n = torch.tensor([131072, 100003, 99999, 65537, 1500], dtype=torch.int64, device=dev)
+    dirs = torch.randn(F, cap, 3, device=dev)
+    gt = torch.arange(F * cap, device=dev, dtype=torch.float32).view(F, cap)
+    for seed in (1, 0x7FFFFFF1, 424242):
+        idx = torch.full((F * N,), -1, dtype=torch.int32, device=dev)
+        out = (torch.empty(F * N, 3, device=dev), torch.empty(F * N, device=dev), torch.empty(F * N, device=dev))
+        sd = torch.tensor([seed], dtype=torch.int32, device=dev)
+        nl._capi.check(nl._capi.lib().nl_select_rays(F, cap, N, nl._capi.ptr(n), nl._capi.ptr(sd), 0, nl._capi.ptr(dirs), nl._capi.ptr(gt), nl._capi.ptr(gt),
+                                                     nl._capi.ptr(out[0]), nl._capi.ptr(out[1]), nl._capi.ptr(out[2]), nl._capi.ptr(idx), nl._capi.stream_ptr()),
+                       "nl_select_rays")
+        for f in range(F):
+            nf = int(n[f]); k = min(N, nf)
+            key = _select_keys_torch(seed, f, nf, dev)
+            want = torch.sort(torch.topk((key << 24) | torch.arange(nf, device=dev), k, largest=False).indices).values
+            got = idx.view(F, N)[f, :k].long()
+            assert torch.equal(got, want), (seed, f, int((got != want).sum()))
+            assert torch.equal(out[1].view(F, N)[f, :k], gt[f, want]) and torch.equal(out[0].view(F, N, 3)[f, :k], dirs[f, want])
+
