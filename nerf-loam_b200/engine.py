@@ -537,11 +537,20 @@ class FusedAdam:
             p = g["param"]
             g["m"] = torch.zeros_like(p)
             g["v"] = torch.zeros_like(p)
+        # the moments are zero-filled on the constructing stream; a side stream that updates some of the groups has to be ordered
+        # behind that (its only other dependency is the decoder kernel of the iteration, enqueued BEFORE this constructor ran)
+        self._init_event = None
+        if any(g.get("side") for g in groups) and groups[0]["param"].is_cuda:
+            self._init_event = torch.cuda.Event()
+            self._init_event.record(torch.cuda.current_stream(groups[0]["param"].device))
 
     def step(self, side_stream=None):
         """side_stream: the groups marked side=True (the decoder, whose gradients are produced there) are updated on that stream."""
         self.step_count += 1
         lib = _capi.lib()
+        if side_stream is not None and self._init_event is not None:
+            side_stream.wait_event(self._init_event)
+            self._init_event = None
         passes = [(None, self.groups)] if side_stream is None else \
             [(None, [g for g in self.groups if not g.get("side")]), (side_stream, [g for g in self.groups if g.get("side")])]
         for stream, gs in passes:

@@ -29,3 +29,11 @@ for F in (1, 5):
     print("select_rays F=%d n=%d: %.1f us/launch" % (F, cap, e0.elapsed_time(e1) * 5))
 PY
 timeout 300 python scripts/demo_slam.py 2>/dev/null | tail -1 | cut -c1-700
+for env in "A=1" "A=2" "A=3" "NL_MAP_GRAPH=0" "NL_MAP_GRAPH=0"; do
+  echo -n "demo 6 scans $env: "; env $env timeout 300 python scripts/demo_slam.py --scans 6 --init-calls 8 2>&1 | tail -1 | python -c "
+import sys, json
+s = sys.stdin.read()
+try:
+    d = json.loads(s); print(d['per_scan_translation_error_m'])
+except Exception: print('ERR', s[-200:])"
+done

@@ -384,6 +384,32 @@ def test_bundle_adjust_frames_cuda_graph_equals_eager(nl):
     assert float((e0 - e_init).abs().max()) > 1e-3                         # and it did train
 
 
+def test_eager_mapping_with_device_selection_never_synchronises_and_stays_finite(nl):
+    """The default drop-in path for reference-format maps: eager bundle_adjust_frames, rays selected on the device, the decoder's
+    weight gradients and Adam pipelined on the side stream -- a loop without a single host synchronisation.  Repeated calls (fresh
+    optimiser state from recycled device blocks each time) must train like the captured path does."""
+    syn = nl.synthetic
+    pts, cos, pose = syn.make_scan(n_beams=32, n_az=400, seed=12)
+    res = {}
+    for graph in (False, True):
+        mu = nl.mapping.MapUpdater(0.3, init_std=0.01, seed=2)
+        ms = mu.insert_voxels(torch.from_numpy(syn.voxelize(pts, pose, 0.3)))
+        torch.manual_seed(5)
+        dec = nl.lidar.Decoder(depth=2, width=256, in_dim=16, skips=[], embedder="none", multires=0).cuda()
+        fr = [nl.frame.LidarFrame(0, torch.from_numpy(pts), torch.from_numpy(cos), nl.se3pose.OptimizablePose.from_matrix(torch.from_numpy(pose.copy())),
+                                  new_keyframe=True)]
+        for call in range(8):
+            junk = [torch.full((n,), float("nan"), device="cuda") for n in (256, 256, 4096, 4096, 65536, 65536)]   # what recycled blocks may hold
+            del junk
+            nl.render_helpers.bundle_adjust_frames(fr, mu.embeddings, ms, dec, nl.criterion.Criterion(Args()), 0.3, 0.15, N_rays=1024, num_iterations=25,
+                                                   truncation=0.3, max_voxel_hit=20, max_distance=40.0, learning_rate=[0.01, 0.005, 0.001],
+                                                   ray_selection="device", cuda_graph=graph)
+        torch.cuda.synchronize()
+        assert bool(torch.isfinite(mu.embeddings.float()).all()) and all(bool(torch.isfinite(p).all()) for p in dec.parameters())
+        res[graph] = float(mu.embeddings.float().abs().mean())
+    assert abs(res[False] - res[True]) < 0.1 * res[True], res
+
+
 def test_incremental_map_update_equals_full_and_graphs_survive_it(nl):
     """mapping.MapUpdater: the device-resident, incrementally patched map equals the fully re-exported one after every
     scan, its arrays keep their addresses while the map grows, and the captured mapping graph is therefore reused across map updates."""

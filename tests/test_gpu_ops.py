@@ -208,6 +208,28 @@ def test_fused_adam_vs_torch(nl, dtype):
             np.testing.assert_allclose(a, b, rtol=1e-2, atol=1e-4)
 
 
+def test_fused_adam_side_stream_is_ordered_behind_the_moments_zero_fill(nl):
+    """bundle_adjust_frames updates the decoder on the engine's side stream (engine.SDFEngine.forward_backward, defer_wgrad).  The
+    optimiser's moments are zero-filled on the MAIN stream when it is constructed, after the side stream forked: without an explicit
+    dependency the first side-stream step may read whatever the recycled blocks held (NaN moments -> NaN decoder after a few calls of a
+    loop that never synchronises).  Made deterministic here: the recycled blocks hold NaN and the main stream is stalled."""
+    dev = torch.device("cuda")
+    n = 64 * 1024
+    p = torch.ones(n, device=dev)
+    g = torch.full((n,), 0.5, device=dev)
+    side = torch.cuda.Stream(device=dev)
+    poison = [torch.full((n,), float("nan"), device=dev) for _ in range(2)]
+    torch.cuda.synchronize()
+    del poison                                     # the caching allocator hands these blocks to the next two allocations of n floats
+    torch.cuda._sleep(400_000_000)                 # main stream busy for ~0.2 s: the zero fills below queue up behind it
+    opt = nl.engine.FusedAdam([dict(param=torch.ones(16, device=dev), grad=torch.zeros(16, device=dev), lr=0.01),
+                               dict(param=p, grad=g, lr=0.01, side=True)])
+    opt.step(side_stream=side)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(p).all())
+    torch.testing.assert_close(p, torch.full_like(p, 0.99), rtol=0, atol=1e-6)       # first Adam step: p - lr * sign(g)
+
+
 def test_adam_ctl_reads_step_and_skip_from_the_device(nl):
     """nl_adam_*_ctl: the step count comes from the control block; a skipped iteration leaves parameter AND moments untouched
     (the reference `continue`s before optim.step(), render_helpers.py:405-409)."""
