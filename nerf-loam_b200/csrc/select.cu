@@ -8,8 +8,8 @@
 // independent 32-bit key from a counter-based generator (seed, frame, point index) and selects the N smallest keys with a
 // three-pass radix select (11 + 11 + 10 bits, histograms in shared memory, summed across the cluster through DSMEM): that is exactly "top-k of iid keys", i.e. a uniform
 // N-subset, it is deterministic for a given seed (ties between equal keys go to the lower point index), and the last pass walks
-// the points in order, so the output is in point order without a sort.  Keys are recomputed in every pass (a handful of integer
-// operations), nothing but the three small histograms is stored.
+// the points in order, so the output is in point order without a sort.  A thread hashes its (strided) points once and keeps the keys in registers for the three
+// histogram passes; the ordered emission re-hashes the thread's contiguous run.  Nothing but the histograms is stored.
 #include "nl_cuda.cuh"
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
@@ -24,20 +24,27 @@ __device__ __forceinline__ uint32_t point_key(uint32_t seed, uint32_t i) { retur
 
 constexpr int SEL_THREADS = 1024;
 constexpr int SEL_BINS = 2048;
-constexpr int SEL_CLUSTER = 8;      // CTAs per scan: each hashes an eighth of the points, histograms are summed over distributed shared memory
+constexpr int SEL_CLUSTER = 8;
+constexpr int SEL_KEYS = 16;        // keys a thread keeps in registers between the passes (covers scans of up to 8 x 1024 x 16 = 131 072 points)      // CTAs per scan: each hashes an eighth of the points, histograms are summed over distributed shared memory
 
 // Among this scan's keys that pass `match`, find the bin (of `digit`) in which the `want`-th smallest key (1-based) lies, and the
 // number of matching keys in lower bins.  Every CTA of the cluster histograms its own points [p0, p1), reads the other CTAs'
 // histograms through DSMEM and finds the bin redundantly.  hist: SEL_BINS ints of shared memory (same offset in every CTA).
 template <int CL, class Match, class Digit>
-__device__ void find_bin(cg::cluster_group &cluster, int p0, int p1, uint32_t seed, int want, Match match, Digit digit, int *hist, int *s_scan, int &bin,
-                         int &below) {
+__device__ void find_bin(cg::cluster_group &cluster, int p0, int p1, uint32_t seed, const uint32_t (&keys)[SEL_KEYS], bool cached, int want, Match match,
+                         Digit digit, int *hist, int *s_scan, int &bin, int &below) {
     const int t = threadIdx.x;
     for (int i = t; i < SEL_BINS; i += SEL_THREADS) hist[i] = 0;
     __syncthreads();
-    for (int i = p0 + t; i < p1; i += SEL_THREADS) {
-        const uint32_t k = point_key(seed, (uint32_t)i);
-        if (match(k)) atomicAdd(&hist[digit(k)], 1);
+    if (cached) {
+#pragma unroll
+        for (int j = 0; j < SEL_KEYS; ++j)
+            if (p0 + t + j * SEL_THREADS < p1 && match(keys[j])) atomicAdd(&hist[digit(keys[j])], 1);
+    } else {
+        for (int i = p0 + t; i < p1; i += SEL_THREADS) {
+            const uint32_t k = point_key(seed, (uint32_t)i);
+            if (match(k)) atomicAdd(&hist[digit(k)], 1);
+        }
     }
     cluster.sync();
     int a = 0, b = 0;
@@ -88,15 +95,25 @@ __global__ void __launch_bounds__(SEL_THREADS)
     // threshold key T = the N-th smallest key; `ties` = how many of the keys equal to T belong to the N smallest
     uint32_t T = 0xffffffffu;
     int ties = 0;
+    // the three histogram passes look at the same keys: hash them once (strided over the CTA's share), keep them in registers
+    uint32_t keys[SEL_KEYS];
+    const bool cached = (c1 - c0) <= SEL_KEYS * SEL_THREADS;
+    if (cached && N < n && N > 0) {
+#pragma unroll
+        for (int j = 0; j < SEL_KEYS; ++j) {
+            const int i = c0 + t + j * SEL_THREADS;
+            keys[j] = i < c1 ? point_key(seed, (uint32_t)i) : 0u;
+        }
+    }
     if (N < n && N > 0) {
         int bA, bB, bC, below;
-        find_bin<CL>(cluster, c0, c1, seed, N, [](uint32_t) { return true; }, [](uint32_t k) { return (int)(k >> 21); }, hist, s_scan, bA, below);
+        find_bin<CL>(cluster, c0, c1, seed, keys, cached, N, [](uint32_t) { return true; }, [](uint32_t k) { return (int)(k >> 21); }, hist, s_scan, bA, below);
         int want = N - below;
-        find_bin<CL>(cluster, c0, c1, seed, want, [bA](uint32_t k) { return (int)(k >> 21) == bA; }, [](uint32_t k) { return (int)((k >> 10) & 2047u); }, hist,
+        find_bin<CL>(cluster, c0, c1, seed, keys, cached, want, [bA](uint32_t k) { return (int)(k >> 21) == bA; }, [](uint32_t k) { return (int)((k >> 10) & 2047u); }, hist,
                  s_scan, bB, below);
         want -= below;
         const uint32_t top22 = ((uint32_t)bA << 11) | (uint32_t)bB;
-        find_bin<CL>(cluster, c0, c1, seed, want, [top22](uint32_t k) { return (k >> 10) == top22; }, [](uint32_t k) { return (int)(k & 1023u); }, hist, s_scan,
+        find_bin<CL>(cluster, c0, c1, seed, keys, cached, want, [top22](uint32_t k) { return (k >> 10) == top22; }, [](uint32_t k) { return (int)(k & 1023u); }, hist, s_scan,
                  bC, below);
         T = (top22 << 10) | (uint32_t)bC;
         ties = want - below;
