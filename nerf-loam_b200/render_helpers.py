@@ -536,6 +536,7 @@ class _TrackGraph:
     version and every scan is 25 graph replays plus one statistics read-back."""
 
     _cache = {}
+    _max_live = 4
 
     def __init__(self, key, m, sdf_network, cfg, N_rays, lr, deterministic, cap, samples_per_ray=64):
         dev = m.centres.device
@@ -592,11 +593,14 @@ class _TrackGraph:
         key = (N_rays, float(lr), bool(deterministic), cap, int(samples_per_ray), m.centres.data_ptr(), m.structure.data_ptr(), m.vox2row.data_ptr(),
                m.packed_children().data_ptr(), m.emb.data_ptr(), -1 if stable else m.n_nodes, -1 if stable else int(m.emb.shape[0]),
                tuple(p.data_ptr() for p in _decoder_params(sdf_network)), tuple(sorted(cfg.items())))
-        g = cls._cache.get("g")
-        if g is None or g.key != key:
-            cls._cache = {}                                     # one live graph: a new map / decoder version replaces it
+        g = cls._cache.pop(key, None)
+        if g is None:
+            # a few live graphs, least recently used first out: the tracker of a running system alternates between the two snapshot
+            # slots of share.SharedMap (two tables, two decoder copies) and uses a different rate for the first scans
+            while len(cls._cache) >= cls._max_live:
+                cls._cache.pop(next(iter(cls._cache)))
             g = cls(key, m, sdf_network, cfg, N_rays, lr, deterministic, cap, samples_per_ray)
-            cls._cache = {"g": g}
+        cls._cache[key] = g                                     # (re-)inserted last = most recently used
         return g
 
     def run(self, frame, pose6_init, num_iterations, seed):

@@ -289,6 +289,13 @@ def test_c_abi_rejects_bad_arguments_without_touching_the_gpu(nl):
     assert L.nl_octree_create(0, 16, 0.3) is None and err() != ""                                        # grid_dim must be positive
     with pytest.raises(nl._capi.NerfLoamError):
         nl._capi.check(L.nl_svo_intersect(1, 1, 1, 0.3, 20, None, None, None, None, None, None, None, None), "nl_svo_intersect")
+    # round-2 entry points
+    assert L.nl_select_rays(0, 100, 10, None, None, 1, None, None, None, None, None, None, None, None) != 0 and "positive" in err()
+    assert L.nl_select_rays(1, 100, 10, None, None, 1, None, None, None, None, None, None, None, None) != 0 and "null" in err()
+    assert L.nl_peer_reduce_adam_bf16(32, 2, 2, None, None, None, None, None, None, 1e-2, 0.9, 0.999, 1e-8, None, 0, None, None, None, None) != 0 and "sizes" in err()
+    assert L.nl_peer_reduce_adam_bf16(24, 0, 2, None, None, None, None, None, None, 1e-2, 0.9, 0.999, 1e-8, None, 0, None, None, None, None) != 0   # whole rows of 16
+    assert L.nl_peer_reduce_adam_bf16(32, 0, 2, None, None, None, None, None, None, 1e-2, 0.9, 0.999, 1e-8, None, 6, None, None, None, None) != 0 and "header" in err()
+    assert L.nl_peer_reduce_adam_bf16(32, 0, 2, None, None, None, None, None, None, 1e-2, 0.9, 0.999, 1e-8, None, 0, None, None, None, None) != 0 and "null" in err()
 
 
 def test_incremental_octree_export_equals_full_export():
