@@ -69,9 +69,11 @@ __device__ void find_bin(cg::cluster_group &cluster, int p0, int p1, uint32_t se
     const int before = upto_a - a;                                 // keys in bins < 2t
     if (before < want && want <= upto_a) { s_scan[32] = 2 * t; s_scan[33] = before; }
     else if (upto_a < want && want <= upto_b) { s_scan[32] = 2 * t + 1; s_scan[33] = upto_a; }
-    cluster.sync();                                                // bin found; every CTA is done reading the histograms
+    __syncthreads();
     bin = s_scan[32];
     below = s_scan[33];
+    __syncthreads();                                               // s_scan is reused by the next pass
+    // (no cluster barrier here: every pass has its own histogram, so a CTA may start the next pass while a peer still reads this one)
 }
 
 template <int CL>
@@ -79,7 +81,7 @@ __global__ void __launch_bounds__(SEL_THREADS)
     k_select_rays(int cap, int n_select, const int64_t *__restrict__ n_points, const uint32_t *__restrict__ seed_dev, uint32_t seed_host,
                   const float *__restrict__ dirs_all, const float *__restrict__ gt_all, const float *__restrict__ cos_all, float *__restrict__ dirs,
                   float *__restrict__ gt, float *__restrict__ cosv, int32_t *__restrict__ idx_out) {
-    __shared__ __align__(8) int hist[SEL_BINS];
+    __shared__ __align__(8) int hist[3][SEL_BINS];          // one histogram per pass: no barrier needed before re-use
     __shared__ int s_scan[36];
     __shared__ unsigned long long s_w[SEL_THREADS / 32];
     __shared__ unsigned long long s_total;
@@ -107,13 +109,13 @@ __global__ void __launch_bounds__(SEL_THREADS)
     }
     if (N < n && N > 0) {
         int bA, bB, bC, below;
-        find_bin<CL>(cluster, c0, c1, seed, keys, cached, N, [](uint32_t) { return true; }, [](uint32_t k) { return (int)(k >> 21); }, hist, s_scan, bA, below);
+        find_bin<CL>(cluster, c0, c1, seed, keys, cached, N, [](uint32_t) { return true; }, [](uint32_t k) { return (int)(k >> 21); }, hist[0], s_scan, bA, below);
         int want = N - below;
-        find_bin<CL>(cluster, c0, c1, seed, keys, cached, want, [bA](uint32_t k) { return (int)(k >> 21) == bA; }, [](uint32_t k) { return (int)((k >> 10) & 2047u); }, hist,
+        find_bin<CL>(cluster, c0, c1, seed, keys, cached, want, [bA](uint32_t k) { return (int)(k >> 21) == bA; }, [](uint32_t k) { return (int)((k >> 10) & 2047u); }, hist[1],
                  s_scan, bB, below);
         want -= below;
         const uint32_t top22 = ((uint32_t)bA << 11) | (uint32_t)bB;
-        find_bin<CL>(cluster, c0, c1, seed, keys, cached, want, [top22](uint32_t k) { return (k >> 10) == top22; }, [](uint32_t k) { return (int)(k & 1023u); }, hist, s_scan,
+        find_bin<CL>(cluster, c0, c1, seed, keys, cached, want, [top22](uint32_t k) { return (k >> 10) == top22; }, [](uint32_t k) { return (int)(k & 1023u); }, hist[2], s_scan,
                  bC, below);
         T = (top22 << 10) | (uint32_t)bC;
         ties = want - below;
