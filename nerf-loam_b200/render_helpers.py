@@ -597,6 +597,8 @@ class _TrackGraph:
         if g is None:
             # a few live graphs, least recently used first out: the tracker of a running system alternates between the two snapshot
             # slots of share.SharedMap (two tables, two decoder copies) and uses a different rate for the first scans
+            if not stable:
+                cls._cache.clear()                              # a per-frame map (reference dict): its arrays die with it, keep nothing else alive
             while len(cls._cache) >= cls._max_live:
                 cls._cache.pop(next(iter(cls._cache)))
             g = cls(key, m, sdf_network, cfg, N_rays, lr, deterministic, cap, samples_per_ray)
