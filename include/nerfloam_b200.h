@@ -257,6 +257,18 @@ NL_API int nl_pose_matrices(int n_frames, const float *d_pose6, float *d_Rt12, v
 NL_API int nl_rays_from_poses(int64_t R, const float *d_dir_local, const int32_t *d_ray_frame, const float *d_Rt12,
                        float *d_ray_o, float *d_ray_d, void *stream);                    /* render_helpers.py:374-376 */
 NL_API int nl_pose_grad(int n_frames, const float *d_pose6, const float *d_pose_acc, float *d_grad6, void *stream);
+/* nl_pose_matrices + nl_rays_from_poses as one launch (n_frames <= 32; every block evaluates the matrices itself, block 0 also stores
+ * them into d_Rt12 if given): a kernel boundary costs as much as either kernel at the reference's 2048-ray iteration size. */
+NL_API int nl_rays_from_pose6(int64_t R, int n_frames, const float *d_dir_local, const int32_t *d_ray_frame, const float *d_pose6, float *d_Rt12,
+                       float *d_ray_o, float *d_ray_d, void *stream);
+/* The tail of an iteration that optimises poses as one launch (n_frames <= 31): nl_pose_grad for every frame; the Adam update
+ * (nl_adam_f32_ctl's arithmetic, step count and skip flag from d_ctl) of the rows whose bit is set in row_mask, moments d_m / d_v
+ * f32[n_frames,6]; nl_loss_finalize on d_stats (if given); and *d_seed_x += inc_x (wrapping) for up to two device-side RNG seeds
+ * that a captured iteration advances (either may be NULL).  Replaces up to n_frames + 4 launches (optim.step() over the pose
+ * parameters, render_helpers.py:353-357 / :448-452). */
+NL_API int nl_pose_step(int n_frames, float *d_pose6, const float *d_pose_acc, float *d_grad6, uint32_t row_mask, float *d_m, float *d_v,
+                 double lr, double beta1, double beta2, double eps, const int32_t *d_ctl, nl_render_stats *d_stats, float fs_weight,
+                 float sdf_weight, int32_t *d_seed_a, int32_t inc_a, int32_t *d_seed_b, int32_t inc_b, void *stream);
 
 /* Per-iteration ray selection (LidarFrame.sample_rays, src/lidarFrame.py:55-57 / src/utils/sample_util.py:4-19): for each of
  * n_frames scans, n_select distinct points uniformly at random out of its d_n_points[f] points (int64, device; a scan's arrays have

@@ -96,6 +96,9 @@ _SIGNATURES = {
     "nl_pose_matrices": (C.c_int, [C.c_int, vp, vp, vp]),
     "nl_rays_from_poses": (C.c_int, [C.c_int64, vp, vp, vp, vp, vp, vp]),
     "nl_pose_grad": (C.c_int, [C.c_int, vp, vp, vp, vp]),
+    "nl_rays_from_pose6": (C.c_int, [C.c_int64, C.c_int, vp, vp, vp, vp, vp, vp, vp]),
+    "nl_pose_step": (C.c_int, [C.c_int, vp, vp, vp, C.c_uint32, vp, vp, C.c_double, C.c_double, C.c_double, C.c_double, vp, vp, C.c_float, C.c_float,
+                               vp, C.c_int32, vp, C.c_int32, vp]),
     "nl_select_rays": (C.c_int, [C.c_int, C.c_int, C.c_int, vp, vp, C.c_uint32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "nl_adam_f32": (C.c_int, [C.c_int64, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, vp]),
     "nl_adam_f32_devstep": (C.c_int, [C.c_int64, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, C.c_double, vp, vp]),

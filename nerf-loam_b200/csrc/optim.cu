@@ -8,6 +8,7 @@
 // kernel rounds at the same points (the gradient arrives as the fp32 scatter sum and is rounded first,
 // which is what autograd's bf16 embedding backward produces).
 #include "nl_cuda.cuh"
+#include "adam.cuh"
 
 namespace {
 
@@ -91,14 +92,7 @@ __global__ void k_adam_ctl(long long n, void *__restrict__ p_, const float *__re
         v[i] = nl_f32_to_bf16(vi);
     } else {
         float *p = (float *)p_, *m = (float *)m_, *v = (float *)v_;
-        const float gi = g[i];
-        const float mi = __fadd_rn(m[i], __fmul_rn(w1, __fsub_rn(gi, m[i])));
-        float vi = __fmul_rn(v[i], b2);
-        vi = __fadd_rn(vi, __fmul_rn(__fmul_rn(w2, gi), gi));
-        const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vi), bc2_sqrt), eps);
-        p[i] = __fadd_rn(p[i], __fmul_rn(-step_size, __fdiv_rn(mi, denom)));
-        m[i] = mi;
-        v[i] = vi;
+        nl_adam_f32_elem(NlAdamConst{w1, b2, w2, eps, step_size, bc2_sqrt}, g[i], p[i], m[i], v[i]);
     }
 }
 

@@ -16,6 +16,7 @@
 // The reference keeps every intermediate as a padded dense tensor and syncs the host 6 times to size them.
 #include <cstdlib>
 
+#include "loss.cuh"
 #include "sampler.cuh"
 #include "traverse.cuh"
 
@@ -675,12 +676,7 @@ __global__ void k_loss_prepare(nl_render_stats *s, float fs_weight, float sdf_we
     s->loss = s->fs_loss = s->sdf_loss = 0.f;
 }
 
-__global__ void k_loss_finalize(nl_render_stats *s, float fs_weight, float sdf_weight) {
-    const double N = (double)((long long)s->n_hit_rays * (long long)s->max_samples);
-    s->fs_loss = (float)((s->fs_sum + (double)s->pad_fs_sum) / N) * s->w_fs;
-    s->sdf_loss = (float)((s->sdf_sum + (double)s->pad_sdf_sum) / N) * s->w_sdf;
-    s->loss = fs_weight * s->fs_loss + sdf_weight * s->sdf_loss;
-}
+__global__ void k_loss_finalize(nl_render_stats *s, float fs_weight, float sdf_weight) { nl_loss_finalize_dev(s, fs_weight, sdf_weight); }
 
 // Fold one iteration's statistics into the call-wide control block (include/nerfloam_b200.h section 8).
 __global__ void k_iter_status(const nl_render_stats *s, const int32_t *prev, int32_t *ctl) {

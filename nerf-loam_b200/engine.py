@@ -368,6 +368,11 @@ class SDFEngine:
         if self.Rt12 is None or self.Rt12.shape[0] < F:
             self.Rt12 = torch.empty((F, 12), dtype=torch.float32, device=self.device)
         st = _capi.stream_ptr()
+        if F <= 32:      # matrices evaluated inside the ray kernel: one launch
+            _capi.check(_capi.lib().nl_rays_from_pose6(R, F, _capi.ptr(dir_local), _capi.ptr(ray_frame), _capi.ptr(pose6), _capi.ptr(self.Rt12),
+                                                       _capi.ptr(self.ray_o), _capi.ptr(self.ray_d), st), "nl_rays_from_pose6")
+            _capi.LAUNCHES += 1
+            return
         _capi.check(_capi.lib().nl_pose_matrices(F, _capi.ptr(pose6), _capi.ptr(self.Rt12), st), "nl_pose_matrices")
         _capi.check(_capi.lib().nl_rays_from_poses(R, _capi.ptr(dir_local), _capi.ptr(ray_frame), _capi.ptr(self.Rt12),
                                                    _capi.ptr(self.ray_o), _capi.ptr(self.ray_d), st), "nl_rays_from_poses")
@@ -444,11 +449,14 @@ class SDFEngine:
     def forward_backward(self, m, dec, R, cfg, gt_depth, cos, dir_local=None, ray_frame=None, n_frames=1, ray_o=None,
                          ray_d=None, noise=None, rng_seed=0, reference_compat=True, update_decoder=True, update_emb=True,
                          update_pose=True, pose6=None, group=None, refresh_weights=True, rng_seed_dev=None, defer_wgrad=False, peer=None,
-                         peer_stats=None):
+                         peer_stats=None, pose_step=None):
         """One optimisation iteration without the optimiser step.  Gradients land in
         self.grad_emb (fp32 [V,16]), dec.grads (fp32), self.pose_grad (fp32 [F,6]); the loss in stats.
         defer_wgrad=True: return without waiting for the decoder's weight gradients -- they (and whatever the caller enqueues on
-        side_stream(), i.e. the decoder's optimiser step) are joined right before the next iteration's decoder, or by join_side()."""
+        side_stream(), i.e. the decoder's optimiser step) are joined right before the next iteration's decoder, or by join_side().
+        pose_step: dict(mask, m, v, lr, seeds=[(int32 tensor, increment), ...]) -- the pose gradient, the poses' Adam step (rows in
+        `mask`, moments m / v f32[F,6]), the loss read-out and the advance of the listed device-side seeds as ONE launch
+        (nl_pose_step) instead of nl_pose_grad + nl_loss_finalize + one Adam launch per pose + one add per seed."""
         lib = _capi.lib()
         st = _capi.stream_ptr()
         self._vs = cfg["voxel_size"]
@@ -512,6 +520,14 @@ class SDFEngine:
                     nldist.allreduce_flat(dec.gradflat, group)
         if defer:
             self._pending = True
+        if pose_step is not None and want_pose and n_frames <= 31:
+            seeds = list(pose_step.get("seeds", ())) + [(None, 0), (None, 0)]
+            _capi.check(lib.nl_pose_step(n_frames, _capi.ptr(pose6), _capi.ptr(self.pose_acc), _capi.ptr(self.pose_grad), int(pose_step["mask"]),
+                                         _capi.ptr(pose_step["m"]), _capi.ptr(pose_step["v"]), float(pose_step["lr"]), 0.9, 0.999, 1e-8,
+                                         _capi.ptr(self.ctl), C.c_void_p(self.stats.data_ptr()), float(cfg["fs_weight"]), float(cfg["sdf_weight"]),
+                                         _capi.ptr(seeds[0][0]), int(seeds[0][1]), _capi.ptr(seeds[1][0]), int(seeds[1][1]), st), "nl_pose_step")
+            _capi.LAUNCHES += 1
+            return
         if want_pose:
             _capi.check(lib.nl_pose_grad(n_frames, _capi.ptr(pose6), _capi.ptr(self.pose_acc), _capi.ptr(self.pose_grad), st),
                         "nl_pose_grad")

@@ -337,6 +337,7 @@ class _MapGraph:
         self.sel_out = (torch.empty((R, 3), device=dev), torch.empty(R, device=dev), torch.empty(R, device=dev))
         self.fid = torch.arange(F, dtype=torch.int32, device=dev).repeat_interleave(N_rays).contiguous()
         self.pose6 = torch.zeros((F, 6), device=dev)
+        self.pose_m, self.pose_v = torch.zeros((F, 6), device=dev), torch.zeros((F, 6), device=dev)     # Adam moments of the poses (nl_pose_step)
         self.seed_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         any_pose = len(pose_rows) > 0
         groups = [dict(param=emb, grad=None, lr=lrs[0])]
@@ -347,17 +348,21 @@ class _MapGraph:
         def body():
             # per frame: uniform without replacement among the scan's points, in point order, gathered -- one launch (csrc/select.cu)
             dirs, gt, cos = select_rays_device(self.dirs, self.gt, self.cos, N_rays, n_dev=self.n_dev, seed=self.sel_seed, out=self.sel_out)
-            self.sel_seed.add_(0x632BE5)
             eng.rays_from_poses(self.pose6, dirs, self.fid)
+            fused_tail = any_pose and F <= 31     # pose gradients + every pose's Adam step + loss read-out + both seed advances: one launch
             eng.forward_backward(m, bufs, R, cfg, gt, cos, dir_local=dirs, ray_frame=self.fid, n_frames=F, update_decoder=update_decoder,
                                  update_emb=True, update_pose=any_pose, pose6=self.pose6,
-                                 rng_seed_dev=None if deterministic else self.seed_dev)
+                                 rng_seed_dev=None if deterministic else self.seed_dev,
+                                 pose_step=dict(mask=sum(1 << i for i in pose_rows), m=self.pose_m, v=self.pose_v, lr=lrs[2],
+                                                seeds=[(self.sel_seed, 0x632BE5), (self.seed_dev, 0x3779B1)]) if fused_tail else None)
             if state["opt"] is None:
                 groups[0]["grad"] = eng.grad_emb
-                pg = [dict(param=self.pose6[i], grad=eng.pose_grad[i], lr=lrs[2]) for i in pose_rows]
+                pg = [] if fused_tail else [dict(param=self.pose6[i], grad=eng.pose_grad[i], lr=lrs[2]) for i in pose_rows]
                 state["opt"] = FusedAdam(groups + pg, ctl=eng.ctl)     # one fixed control block: forward_backward folds in place
             state["opt"].step()
-            self.seed_dev.add_(0x3779B1)
+            if not fused_tail:
+                self.sel_seed.add_(0x632BE5)
+                self.seed_dev.add_(0x3779B1)
 
         # one throw-away eager iteration on a side stream (allocations, one-time kernel attributes), then the capture; the
         # parameters it touches are put back afterwards
@@ -414,6 +419,7 @@ class _MapGraph:
         self.sel_seed.copy_(_seed_from_cuda(dev))          # ray selection follows torch's CUDA generator (torch.manual_seed reproduces it)
         for g in self.opt.groups:
             g["m"].zero_(); g["v"].zero_()
+        self.pose_m.zero_(); self.pose_v.zero_()
         self.eng.begin_call()
         for _ in range(num_iterations):
             self.graph.replay()
@@ -560,17 +566,14 @@ class _TrackGraph:
         def body():
             # uniform without replacement among the scan's n points, in point order, gathered -- one launch (csrc/select.cu)
             dirs, gt, cos = select_rays_device(self.dirs, self.gt, self.cos, N_rays, n_dev=self.n_dev, seed=self.sel_seed, out=self.sel_out)
-            self.sel_seed.add_(0x632BE5)
             eng.rays_from_poses(self.pose6, dirs, None)
+            # Adam's step count, the "nothing hit" skip and the sticky error bits live in the engine's control block (one fixed
+            # block: forward_backward folds this iteration's statistics into it in place); the iteration ends with ONE launch for
+            # pose gradient + the pose's Adam step + loss read-out + the advance of the two RNG seeds (nl_pose_step)
             eng.forward_backward(m, bufs, N_rays, cfg, gt, cos, dir_local=dirs, ray_frame=None, n_frames=1, update_decoder=False,
                                  update_emb=False, update_pose=True, pose6=self.pose6, refresh_weights=False,
-                                 rng_seed_dev=None if deterministic else self.seed_dev)
-            # Adam's step count, the "nothing hit" skip and the sticky error bits live in the engine's control block (one fixed
-            # block: forward_backward folds this iteration's statistics into it in place)
-            _capi.check(lib.nl_adam_f32_ctl(6, _capi.ptr(self.pose6), _capi.ptr(eng.pose_grad), _capi.ptr(self.adam_m),
-                                            _capi.ptr(self.adam_v), float(lr), 0.9, 0.999, 1e-8, _capi.ptr(eng.ctl),
-                                            _capi.stream_ptr()), "nl_adam_f32_ctl")
-            self.seed_dev.add_(0x3779B1)
+                                 rng_seed_dev=None if deterministic else self.seed_dev,
+                                 pose_step=dict(mask=1, m=self.adam_m, v=self.adam_v, lr=lr, seeds=[(self.sel_seed, 0x632BE5), (self.seed_dev, 0x3779B1)]))
 
         # one throw-away eager iteration on a side stream (allocations, one-time kernel attributes), then the capture
         bufs.refresh_transposes()

@@ -179,6 +179,60 @@ def test_pose_kernels_vs_reference_golden(nl):
     np.testing.assert_allclose(P.data.detach().numpy(), z["data"], atol=1e-6)
 
 
+def test_fused_pose_launches_equal_the_separate_kernels_bit_for_bit(nl):
+    """nl_rays_from_pose6 == nl_pose_matrices + nl_rays_from_poses, and nl_pose_step == nl_pose_grad + nl_adam_f32_ctl per selected
+    pose + nl_loss_finalize + the two seed advances (what a captured iteration used to launch one by one)."""
+    cap, lib = nl._capi, nl._capi.lib()
+    dev = torch.device("cuda")
+    torch.manual_seed(3)
+    F, R = 5, 3001
+    pose6 = (torch.randn(F, 6, device=dev) * torch.tensor([2, 2, 2, 0.3, 0.3, 0.3], device=dev)).contiguous()
+    pose6[2, 3:] = 0                                                   # theta = 0 row (Taylor at 0, zero-angle derivative)
+    dirs = torch.nn.functional.normalize(torch.randn(R, 3, device=dev), dim=-1).contiguous()
+    fid = torch.randint(0, F, (R,), device=dev, dtype=torch.int32)
+    st = cap.stream_ptr()
+    Rt_a, Rt_b = torch.empty(F, 12, device=dev), torch.empty(F, 12, device=dev)
+    o_a, d_a, o_b, d_b = (torch.empty(R, 3, device=dev) for _ in range(4))
+    cap.check(lib.nl_pose_matrices(F, cap.ptr(pose6), cap.ptr(Rt_a), st))
+    cap.check(lib.nl_rays_from_poses(R, cap.ptr(dirs), cap.ptr(fid), cap.ptr(Rt_a), cap.ptr(o_a), cap.ptr(d_a), st))
+    cap.check(lib.nl_rays_from_pose6(R, F, cap.ptr(dirs), cap.ptr(fid), cap.ptr(pose6), cap.ptr(Rt_b), cap.ptr(o_b), cap.ptr(d_b), st))
+    assert torch.equal(Rt_a, Rt_b) and torch.equal(o_a, o_b) and torch.equal(d_a, d_b)
+    cap.check(lib.nl_rays_from_pose6(R, 1, cap.ptr(dirs), None, cap.ptr(pose6), None, cap.ptr(o_b), cap.ptr(d_b), st))     # tracking: one pose, no frame ids
+    cap.check(lib.nl_rays_from_poses(R, cap.ptr(dirs), None, cap.ptr(Rt_a), cap.ptr(o_a), cap.ptr(d_a), st))
+    assert torch.equal(o_a, o_b) and torch.equal(d_a, d_b)
+
+    acc = torch.randn(F, 12, device=dev).contiguous()
+    mask = 0b11010
+    for skip, step in ((0, 1), (0, 7), (1, 7)):
+        ctl = torch.zeros(cap.CTL_WORDS, dtype=torch.int32, device=dev)
+        ctl[cap.CTL_ADAM_STEP], ctl[cap.CTL_SKIP_NOW] = step, skip
+        stats = torch.zeros(nl.engine.STATS_BYTES, dtype=torch.uint8, device=dev)
+        stats.view(torch.int32)[0], stats.view(torch.int32)[2] = 1000, 37
+        stats.view(torch.float64)[16], stats.view(torch.float64)[17] = 123.456, 7.89
+        f32 = stats.view(torch.float32)
+        f32[26], f32[27], f32[30], f32[31] = 0.3, 0.7, 11.0, 5.0
+        m0, v0 = torch.rand(F, 6, device=dev) * 1e-2, torch.rand(F, 6, device=dev) * 1e-4
+        seeds0 = torch.tensor([2 ** 31 - 5, 12345], dtype=torch.int32, device=dev)
+        # separate kernels
+        pa, ma, va, sa, ga = pose6.clone(), m0.clone(), v0.clone(), stats.clone(), torch.empty(F, 6, device=dev)
+        cap.check(lib.nl_pose_grad(F, cap.ptr(pa), cap.ptr(acc), cap.ptr(ga), st))
+        cap.check(lib.nl_loss_finalize(cap.ptr(sa), 1.5, 1000.0, st))
+        for f in range(F):
+            if (mask >> f) & 1:
+                cap.check(lib.nl_adam_f32_ctl(6, cap.ptr(pa[f]), cap.ptr(ga[f]), cap.ptr(ma[f]), cap.ptr(va[f]), 1e-3, 0.9, 0.999, 1e-8, cap.ptr(ctl), st))
+        seeds_a = seeds0.clone()
+        seeds_a[0:1].add_(0x632BE5); seeds_a[1:2].add_(0x3779B1)
+        # one launch
+        pb, mb, vb, sb, gb, seeds_b = pose6.clone(), m0.clone(), v0.clone(), stats.clone(), torch.empty(F, 6, device=dev), seeds0.clone()
+        cap.check(lib.nl_pose_step(F, cap.ptr(pb), cap.ptr(acc), cap.ptr(gb), mask, cap.ptr(mb), cap.ptr(vb), 1e-3, 0.9, 0.999, 1e-8, cap.ptr(ctl),
+                                   cap.ptr(sb), 1.5, 1000.0, cap.ptr(seeds_b[0:1]), 0x632BE5, cap.ptr(seeds_b[1:2]), 0x3779B1, st))
+        torch.cuda.synchronize()
+        assert torch.equal(ga, gb) and torch.equal(pa, pb) and torch.equal(ma, mb) and torch.equal(va, vb), (skip, step)
+        assert torch.equal(sa, sb) and torch.equal(seeds_a, seeds_b)
+        assert (not skip) == (not torch.equal(pb, pose6)) and torch.equal(pb[0], pose6[0]) and torch.equal(pb[2], pose6[2])   # rows 0 and 2 are not selected
+        assert float(sb.view(torch.float32)[36]) != 0.0
+
+
 @pytest.mark.parametrize("dtype", ["f32", "bf16"])
 def test_fused_adam_vs_torch(nl, dtype):
     torch.manual_seed(0)
