@@ -430,8 +430,8 @@ def test_select_rays_equals_top_n_of_the_hashed_keys_at_scan_size(nl, N):
     (ties to the lower index) -- the radix select, the cluster-wide histograms and the ordered emission against torch's sort."""
     rh = nl.render_helpers
     dev = torch.device("cuda")
-    F, cap = 5, 131072
-    n = torch.tensor([131072, 100003, 99999, 65537, 1500], dtype=torch.int64, device=dev)
+    F, cap = 5, 262144          # scans above 131 072 points take the kernel's re-hashing path, smaller ones keep their keys in registers
+    n = torch.tensor([262144, 200003, 131072, 65537, 1500], dtype=torch.int64, device=dev)
     dirs = torch.randn(F, cap, 3, device=dev)
     gt = torch.arange(F * cap, device=dev, dtype=torch.float32).view(F, cap)
     for seed in (1, 0x7FFFFFF1, 424242):
