@@ -49,14 +49,45 @@ inline uint64_t level_mask(int i) {  // utils.h:41-62 MASK[i]: top 3*(i+1) Morto
     for (int k = 0; k <= i; ++k) m |= (0x7000000000000000ULL >> (3 * k));
     return m;
 }
+const uint64_t kAllLevels = level_mask(kMaxBits - 1);
 inline uint64_t morton(int x, int y, int z) {
-    return (spread3((uint64_t)(int64_t)x) | (spread3((uint64_t)(int64_t)y) << 1) | (spread3((uint64_t)(int64_t)z) << 2)) &
-           level_mask(kMaxBits - 1);
+    return (spread3((uint64_t)(int64_t)x) | (spread3((uint64_t)(int64_t)y) << 1) | (spread3((uint64_t)(int64_t)z) << 2)) & kAllLevels;
 }
 
 const int kIncX[8] = {0, 0, 0, 0, 1, 1, 1, 1};  // octree.cpp:12-14: corner j = 4*dx + 2*dy + dz
 const int kIncY[8] = {0, 0, 1, 1, 0, 0, 1, 1};
 const int kIncZ[8] = {0, 1, 0, 1, 0, 1, 0, 1};
+
+// Open-addressing set of 64-bit keys (linear probing, power-of-two capacity, load <= 1/2): membership tests are the inner loop of
+// insertion -- every point of every scan asks "seen before?" -- and std::unordered_set's node chasing made that 2/3 of a map update.
+struct KeySet {
+    std::vector<uint64_t> slot;    // key + 1; 0 = empty (Morton keys never reach 2^64 - 1)
+    size_t used = 0;
+    KeySet() : slot(1024, 0) {}
+    static size_t hash(uint64_t k) { return (size_t)((k * 0x9E3779B97F4A7C15ull) >> 20); }
+    bool contains(uint64_t k) const {
+        const size_t mask = slot.size() - 1;
+        for (size_t i = hash(k) & mask;; i = (i + 1) & mask) {
+            if (slot[i] == k + 1) return true;
+            if (!slot[i]) return false;
+        }
+    }
+    bool insert(uint64_t k) {      // true if the key was new
+        if ((used + 1) * 2 > slot.size()) grow();
+        const size_t mask = slot.size() - 1;
+        for (size_t i = hash(k) & mask;; i = (i + 1) & mask) {
+            if (slot[i] == k + 1) return false;
+            if (!slot[i]) { slot[i] = k + 1; ++used; return true; }
+        }
+    }
+    void grow() {
+        std::vector<uint64_t> old(slot.size() * 2, 0);
+        old.swap(slot);
+        used = 0;
+        for (uint64_t v : old)
+            if (v) insert(v - 1);
+    }
+};
 
 }  // namespace
 
@@ -68,8 +99,8 @@ struct nl_octree {
     std::vector<uint64_t> code;   // Morton code of the min corner, truncated to the node's level
     std::vector<uint32_t> side;
     std::vector<int8_t> type;
-    std::unordered_set<uint64_t> corner_keys;  // all_keys (octree.h:118) -- used by try_insert only
-    std::unordered_set<uint64_t> seen_points;
+    KeySet corner_keys;           // all_keys (octree.h:118) -- used by try_insert only
+    KeySet seen_points;
     // Incremental export (nl_octree_export_dirty): ids of the nodes whose exported row may differ from the last export.  A row
     // changes only when the node is created, when one of its child slots is filled, when a FEATURE leaf becomes SURFACE (its
     // own row appears) or when one of its children does (the child id shows up in the parent's row, octree.cpp:333-337).
@@ -133,7 +164,7 @@ int nl_octree_insert(nl_octree *t, const int32_t *vox, int64_t n) {
             // The reference silently wraps such coordinates through the bit masks; refuse instead of corrupting.
             return nl_set_error("nl_octree_insert: voxel coordinate outside [0, grid_dim-2]");
         }
-        if (!t->seen_points.insert(morton(px, py, pz)).second) continue;
+        if (!t->seen_points.insert(morton(px, py, pz))) continue;
         for (int j = 0; j < 8; ++j) {
             const int x = px + kIncX[j], y = py + kIncY[j], z = pz + kIncZ[j];
             const uint64_t key = morton(x, y, z);
@@ -169,7 +200,7 @@ double nl_octree_try_insert(nl_octree *t, const int32_t *vox, int64_t n) {
     // and de-duplicated after truncation; the ratio is reproduced with that quirk.
     std::unordered_set<int32_t> inter;
     for (uint64_t k : tmp)
-        if (t->corner_keys.count(k)) inter.insert((int32_t)k);
+        if (t->corner_keys.contains(k)) inter.insert((int32_t)k);
     return 1.0 * (double)inter.size() / (double)tmp.size();
 }
 
