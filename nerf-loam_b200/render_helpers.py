@@ -13,6 +13,7 @@ Behavioural notes (also in DESIGN.md):
   * the unused autograd.grad(sdf, xyz) of render_helpers.py:293-297 is not computed.
 """
 import os
+import weakref
 from copy import deepcopy
 
 import torch
@@ -267,14 +268,45 @@ class _few_threads:
             torch.set_num_threads(self.prev)
 
 
+_FRAME_ARRAYS = weakref.WeakKeyDictionary()
+
+
+def _frame_arrays(f, dev):
+    """Device copies of a scan's per-point data: unit directions f32[n,3], incidence cosines f32[n], cosine-corrected ranges f32[n]
+    (criterion.py:30-32).  Computed once per frame OBJECT and kept in a weak-key side table: a keyframe stays in the optimisation
+    window for many calls (window_size 4-8) and the tracked frame goes straight into the next mapping call, while re-uploading
+    5 x 1.3 MB from pageable memory was ~10 % of a captured mapping call.  Tied to the identity of the frame's tensors (a frame whose
+    points / cosines / directions are REPLACED is uploaded again); nothing is attached to the frame itself, so pickling a frame
+    (the reference passes frames between its processes through queues) does not drag device memory along."""
+    dev = torch.device(dev)
+    src = (f.rays_d, f.pointsCos, f.points)
+    try:
+        c = _FRAME_ARRAYS.get(f)
+    except TypeError:          # an unhashable / non-weakrefable frame type: no caching
+        c = False
+    if c and c[0] is src[0] and c[1] is src[1] and c[2] is src[2] and c[3].device.type == dev.type and \
+            (dev.index is None or dev.index == c[3].device.index):
+        return c[3], c[4], c[5]
+    dirs = src[0].reshape(-1, 3).float().to(dev).contiguous()
+    cos = src[1].float().view(-1).to(dev).contiguous()
+    gt = torch.norm(src[2].float().to(dev), 2, -1) * cos
+    if c is not False:
+        try:
+            _FRAME_ARRAYS[f] = src + (dirs, cos, gt)
+        except TypeError:
+            pass
+    return dirs, cos, gt
+
+
 class _FrameBatch:
-    """Device copies of the per-frame point data (uploaded once per call instead of per iteration)."""
+    """Device copies of the per-frame point data (uploaded once per frame object instead of per iteration / per call)."""
 
     def __init__(self, frames, dev):
         self.frames = frames
-        self.dirs = [f.rays_d.reshape(-1, 3).float().to(dev) for f in frames]
-        self.cos = [f.pointsCos.float().view(-1).to(dev) for f in frames]
-        self.gt = [torch.norm(f.points.float().to(dev), 2, -1) * c for f, c in zip(frames, self.cos)]  # criterion.py:30-32
+        arrays = [_frame_arrays(f, dev) for f in frames]
+        self.dirs = [a[0] for a in arrays]
+        self.cos = [a[1] for a in arrays]
+        self.gt = [a[2] for a in arrays]
 
     def select(self, N_rays, dev, track=False, mode="host"):
         """mode "host": ray selection like the reference (frame.sample_rays -> boolean mask, CPU torch RNG: the same seed
@@ -404,16 +436,19 @@ class _MapGraph:
             cls._cache = {"g": g}
         return g
 
+    def _upload(self, frames):
+        """The scans of this call into the graph's static buffers (device-to-device for frames seen before: _frame_arrays)."""
+        for i, f in enumerate(frames):
+            d, c, g = _frame_arrays(f, self.dirs.device)
+            n = d.shape[0]
+            self.dirs[i, :n].copy_(d)
+            self.cos[i, :n].copy_(c)
+            self.gt[i, :n].copy_(g)
+            self.n_dev[i].fill_(n)
+
     def run(self, frames, pose6_init, num_iterations, seed):
         dev = self.dirs.device
-        for i, f in enumerate(frames):
-            rd = f.rays_d.reshape(-1, 3).float()
-            n = rd.shape[0]
-            self.dirs[i, :n].copy_(rd, non_blocking=True)
-            cosv = f.pointsCos.float().view(-1).to(dev, non_blocking=True)
-            self.cos[i, :n].copy_(cosv)
-            self.gt[i, :n].copy_(torch.norm(f.points.float().to(dev, non_blocking=True), 2, -1) * cosv)       # criterion.py:30-32
-            self.n_dev[i].fill_(n)
+        self._upload(frames)
         self.pose6.copy_(pose6_init)
         self.seed_dev.fill_(seed if seed < 2 ** 31 else seed - 2 ** 32)
         self.sel_seed.copy_(_seed_from_cuda(dev))          # ray selection follows torch's CUDA generator (torch.manual_seed reproduces it)
@@ -608,16 +643,19 @@ class _TrackGraph:
         cls._cache[key] = g                                     # (re-)inserted last = most recently used
         return g
 
+    def _upload(self, frame):
+        """The scan into the graph's static buffers; its device arrays stay cached for the mapping call that follows (_frame_arrays)."""
+        d, c, g = _frame_arrays(frame, self.dirs.device)
+        n = d.shape[0]
+        self.dirs[:n].copy_(d)
+        self.cos[:n].copy_(c)
+        self.gt[:n].copy_(g)
+        self.n_dev.fill_(n)
+
     def run(self, frame, pose6_init, num_iterations, seed):
-        rd = frame.rays_d.reshape(-1, 3).float()
-        n = rd.shape[0]
         dev = self.dirs.device
         self.bufs.refresh_transposes()        # the decoder may have been updated in place since the capture (same pointers, new values)
-        self.dirs[:n].copy_(rd, non_blocking=True)
-        cosv = frame.pointsCos.float().view(-1).to(dev, non_blocking=True)
-        self.cos[:n].copy_(cosv)
-        self.gt[:n].copy_(torch.norm(frame.points.float().to(dev, non_blocking=True), 2, -1) * cosv)       # criterion.py:30-32
-        self.n_dev.fill_(n)
+        self._upload(frame)
         self.pose6.copy_(pose6_init)
         self.seed_dev.fill_(seed if seed < 2 ** 31 else seed - 2 ** 32)
         self.sel_seed.copy_(_seed_from_cuda(dev))          # ray selection follows torch's CUDA generator (torch.manual_seed reproduces it)

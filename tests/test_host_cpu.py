@@ -331,3 +331,49 @@ def test_incremental_octree_export_equals_full_export():
         assert np.array_equal(sub, np.where(v >= 0, v2r_full[np.clip(v, 0, None)], -1))
     assert touched[0] == acc[0].shape[0] - sum(0 for _ in ()) or touched[0] > 0
     assert all(t < 0.6 * acc[0].shape[0] for t in touched[1:])                            # later scans touch a fraction of the tree
+
+
+def test_frame_device_arrays_are_cached_per_frame_object_and_fill_the_graph_buffers(nl):
+    """render_helpers._frame_arrays: one upload per LidarFrame object (weak side table, nothing attached to the frame), re-done when a
+    tensor of the frame is replaced; the upload helpers of the captured tracking / mapping iterations copy those arrays into their
+    static buffers (exercised here on CPU tensors: the same code runs on the device)."""
+    import copy, gc, pickle
+    from types import SimpleNamespace
+    rh, syn = nl.render_helpers, nl.synthetic
+    frames = []
+    for i, (nb, na) in enumerate(((8, 50), (8, 40))):
+        pts, cos, pose = syn.make_scan(n_beams=nb, n_az=na, seed=5 + i)
+        frames.append(nl.frame.LidarFrame(i, torch.from_numpy(pts), torch.from_numpy(cos), nl.se3pose.OptimizablePose.from_matrix(torch.from_numpy(pose)),
+                                          new_keyframe=True))
+    f = frames[0]
+    d, c, g = rh._frame_arrays(f, "cpu")
+    n = f.points.shape[0]
+    assert d.shape == (n, 3) and c.shape == (n,) and g.shape == (n,)
+    torch.testing.assert_close(d, f.rays_d.reshape(-1, 3).float())
+    torch.testing.assert_close(g, torch.norm(f.points.float(), 2, -1) * f.pointsCos.float().view(-1))       # criterion.py:30-32
+    d2, c2, g2 = rh._frame_arrays(f, torch.device("cpu"))
+    assert d2 is d and c2 is c and g2 is g                                   # cached
+    assert not any(isinstance(v, tuple) and any(x is d for x in v) for v in vars(f).values())     # nothing attached to the frame
+    assert len(pickle.dumps(f)) < 40 * n + 20000                             # ... so a pickled frame stays its own size
+    f.points = f.points.clone()                                              # a replaced tensor invalidates the entry
+    d3, _, g3 = rh._frame_arrays(f, "cpu")
+    assert d3 is not d and torch.equal(g3, g)
+    fb = rh._FrameBatch(frames, torch.device("cpu"))
+    assert fb.dirs[0] is d3 and fb.gt[1].shape[0] == frames[1].points.shape[0]
+    # the graphs' upload helpers (static buffers of capacity `cap`, ragged scans)
+    cap = 512
+    mg = SimpleNamespace(dirs=torch.zeros(2, cap, 3), cos=torch.zeros(2, cap), gt=torch.zeros(2, cap), n_dev=torch.zeros(2, 1, dtype=torch.int64))
+    rh._MapGraph._upload(mg, frames)
+    for i, fr in enumerate(frames):
+        k = fr.points.shape[0]
+        assert int(mg.n_dev[i]) == k and torch.equal(mg.dirs[i, :k], fb.dirs[i]) and torch.equal(mg.gt[i, :k], fb.gt[i]) and torch.equal(mg.cos[i, :k], fb.cos[i])
+        assert float(mg.dirs[i, k:].abs().sum()) == 0.0
+    tg = SimpleNamespace(dirs=torch.zeros(cap, 3), cos=torch.zeros(cap), gt=torch.zeros(cap), n_dev=torch.zeros(1, dtype=torch.int64))
+    rh._TrackGraph._upload(tg, frames[1])
+    k = frames[1].points.shape[0]
+    assert int(tg.n_dev) == k and torch.equal(tg.dirs[:k], fb.dirs[1]) and torch.equal(tg.gt[:k], fb.gt[1])
+    n_before = len(rh._FRAME_ARRAYS)
+    del fb, frames, f, fr
+    gc.collect()
+    assert len(rh._FRAME_ARRAYS) < n_before                                  # entries die with their frames
+
