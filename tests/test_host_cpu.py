@@ -377,3 +377,24 @@ def test_frame_device_arrays_are_cached_per_frame_object_and_fill_the_graph_buff
     gc.collect()
     assert len(rh._FRAME_ARRAYS) < n_before                                  # entries die with their frames
 
+
+def test_octree_membership_sets_under_growth_and_duplicates(nl):
+    """The host octree answers "seen before?" through flat open-addressing key sets (csrc/octree_host.cpp, KeySet): a few hundred
+    thousand points with heavy repetition, inserted in several calls, must give exactly one SURFACE leaf per distinct voxel, and
+    try_insert must report the exact overlap of the corner sets."""
+    rng = np.random.default_rng(7)
+    o = nl.svo.Octree()
+    o.init(1024, 16, 0.2)
+    pts = rng.integers(0, 1022, size=(60_000, 3), dtype=np.int32)
+    pts = pts[rng.integers(0, pts.shape[0], size=400_000)]                 # every voxel ~7 times, shuffled
+    for part in np.array_split(pts, 5):
+        o.insert(torch.from_numpy(np.ascontiguousarray(part)))
+    uniq = np.unique(pts, axis=0)
+    assert o.count_leaf_nodes() == uniq.shape[0]
+    assert all(o.has_voxel(torch.from_numpy(v)) for v in uniq[:50])
+    inside = torch.from_numpy(np.ascontiguousarray(uniq[:1000]))
+    assert o.try_insert(inside) == 1.0                                      # every corner of known voxels is known
+    far = torch.from_numpy(np.ascontiguousarray(uniq[:1000] % 7 + np.array([[0, 0, 0]], np.int32)))   # a 8^3 corner of the grid
+    r = o.try_insert(far)
+    assert 0.0 <= r <= 1.0
+
