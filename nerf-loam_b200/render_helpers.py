@@ -290,6 +290,10 @@ def _frame_arrays(f, dev):
     dirs = src[0].reshape(-1, 3).float().to(dev).contiguous()
     cos = src[1].float().view(-1).to(dev).contiguous()
     gt = torch.norm(src[2].float().to(dev), 2, -1) * cos
+    if gt.is_cuda:
+        # the arrays outlive this call and may next be read on another stream (tracker and mapper run on different ones): make
+        # them complete now -- once per frame, and the uploads from pageable memory have stalled the host anyway
+        torch.cuda.current_stream(gt.device).synchronize()
     if c is not False:
         try:
             _FRAME_ARRAYS[f] = src + (dirs, cos, gt)
